@@ -1,0 +1,205 @@
+/* slb.h -- C ABI of the B200-native batched sigma-point filter engine.
+ *
+ * This is the drop-in boundary for the hot path of jhidalgocarrio/slam-localization.  The
+ * reference has no FFI: its boundary is the public member surface of header-only C++ class
+ * templates.  Each entry point below names the reference member(s) it replaces (file:line,
+ * relative to the reference root).  The host C++ facade in slam-localization_b200/facade/
+ * re-creates those class surfaces (localization::Usckf / Msckf / DataModel, ukfom::ukf) on top
+ * of exactly these symbols; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are `double*` obtained from cudaMalloc (or a torch
+ *     tensor's data_ptr); `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - every function returns 0 on success or a negative slb_error; nothing throws across the
+ *     ABI.  Numerical trouble is never an error: it is recorded per instance in a status word
+ *     (SLB_ST_* bits) that slb_status() summarises.
+ *   - there is no CPU fallback.  Without a CUDA device slb_create fails with SLB_ERR_NO_DEVICE.
+ *   - all arithmetic is IEEE double, like the reference's Eigen `double` path.
+ *
+ * State representation ("q-vector"): a manifold point is a flat array with 3 doubles per
+ * vect<3> block and 4 doubles (w,x,y,z) per SO3 block, followed by plain feature scalars.
+ * Tangent vectors / covariances use 3 DOF per block, in the same block order
+ * (State.hpp:141-149,246-252,341-352,536-545; test/UKFoMUnitTest.cpp:31-35).
+ */
+#ifndef SLB_H_
+#define SLB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLB_VERSION 100
+
+typedef enum {
+    SLB_OK = 0,
+    SLB_ERR_INVALID = -1,    /* bad argument / unsupported combination            */
+    SLB_ERR_NO_DEVICE = -2,  /* no CUDA device: the engine has no CPU fallback    */
+    SLB_ERR_CUDA = -3,       /* a CUDA runtime call failed (see slb_last_error)   */
+    SLB_ERR_ALLOC = -4,
+    SLB_ERR_NCCL = -5
+} slb_error;
+
+/* Per-instance status bits (never abort the batch; reference behaviour in brackets). */
+enum {
+    SLB_ST_CHOL_FAIL = 1,   /* LLT pivot <= 0 [Eigen::LLT info() ignored, Usckf.hpp:537-538]  */
+    SLB_ST_MEAN_NOCONV = 2, /* manifold mean hit max_it [assert(false), Usckf.hpp:620-624]     */
+    SLB_ST_GATE_REJECT = 4, /* significance test rejected the update [Usckf.hpp:294]           */
+    SLB_ST_NONFINITE = 8    /* NaN/Inf met in the state                                        */
+};
+
+/* Filter kinds (which reference class the batch stands for). */
+enum {
+    SLB_KIND_UKF = 1,   /* ukfom::ukf<state>            (test/UKFoMUnitTest.cpp:104-117)  */
+    SLB_KIND_USCKF = 2, /* localization::Usckf<Aug,State> (Usckf.hpp:44-45)               */
+    SLB_KIND_MSCKF = 3  /* localization::Msckf<Multi,State> (Msckf.hpp:40-41)             */
+};
+
+/* Fixed-DOF manifold layouts for SLB_KIND_UKF. */
+enum {
+    SLB_LAYOUT_POSE6 = 6,   /* vect3 pos, SO3 orient           (SensorState, State.hpp:242-252) */
+    SLB_LAYOUT_MTK9 = 9,    /* vect3 pos, SO3 orient, vect3 vel (test/UKFoMUnitTest.cpp:31-35)  */
+    SLB_LAYOUT_STATE12 = 12 /* pos, orient, velo, angvelo       (State, State.hpp:137-149)      */
+};
+
+/* Device model catalogue.  The reference takes arbitrary host functors f/h (Usckf.hpp:113-114,
+ * 260-263); a GPU batch cannot call back into host code, so the models the reference ships in
+ * its tests are compiled in and selected by id.  `u` is the per-instance control input. */
+enum {
+    /* process models */
+    SLB_PM_UKFOM_IMU = 1,      /* test/UKFoMUnitTest.cpp:45-70 with orient = s.orient [+] w*dt;
+                                  u = acc(3) gyro(3); layout MTK9                               */
+    SLB_PM_UKFOM_IMU_REFBUG = 2, /* same, reproducing :53 (orient = identity [+] w*dt)            */
+    SLB_PM_POSE6_ODOM = 3,     /* pos += R(q) v dt ; q = q*exp(w dt); u = v(3) w(3); POSE6      */
+    SLB_PM_USCKF_TEST = 4,     /* test/UsckfUnitTest.cpp:34-49; u = velocity(3) angvel(3)       */
+    SLB_PM_MSCKF_DELTAPOSE = 5,/* test/MsckfUnitTest.cpp:33-47; u = dp(3) dq(w,x,y,z) v(3) w(3) */
+    /* measurement models */
+    SLB_MM_GPS_POS = 101,      /* test/UKFoMUnitTest.cpp:82-85: z = pos (m = 3)                 */
+    SLB_MM_USCKF_VO = 102,     /* test/UsckfUnitTest.cpp:62-86: featuresk moved by
+                                  (statek [-] statek_i); m = nk                                 */
+    SLB_MM_MSCKF_REPROJ = 103  /* builder-defined (the reference stops before update,
+                                  test/MsckfUnitTest.cpp:215-232): pinhole reprojection of
+                                  shared landmarks, feature f seen from clone f % k; m = 2*nfeat */
+};
+
+/* Cloning modes, Usckf.hpp:37-42 */
+enum { SLB_STATEK = 1, SLB_STATEK_L = 2, SLB_STATEK_I = 3 };
+
+/* Fields for slb_upload / slb_download (host side is always instance-major, dense). */
+enum {
+    SLB_FIELD_MU = 1,     /* batch x qdim q-vectors                              */
+    SLB_FIELD_P = 2,      /* batch x N x N row-major covariances                 */
+    SLB_FIELD_STATUS = 3, /* batch x int32 (download only; pass an int32_t*)     */
+    SLB_FIELD_OUTLIERS = 4/* batch x int32 outlier count of the last MSCKF update */
+};
+
+typedef struct {
+    int32_t kind;      /* SLB_KIND_*                                                     */
+    int32_t layout;    /* SLB_LAYOUT_* for KIND_UKF; ignored otherwise                   */
+    int32_t batch;     /* number of independent filter instances on this device          */
+    int32_t nk, nl;    /* USCKF: featuresk.size(), featuresk_l.size() (State.hpp:539-540)*/
+    int32_t nclones;   /* MSCKF: sensorsk.size() (State.hpp:342)                         */
+    int32_t device;    /* CUDA device ordinal                                            */
+    int32_t reserved[9];
+} slb_config;
+
+typedef struct slb_batch_s *slb_handle;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* ctor of Usckf (Usckf.hpp:83) / Msckf (Msckf.hpp:80) / ukfom::ukf(mu,sigma): allocates the
+ * device-resident batch; state is supplied with slb_upload. */
+int slb_create(const slb_config *cfg, slb_handle *out);
+int slb_destroy(slb_handle h);
+const char *slb_last_error(void);
+int slb_version(void);
+int slb_dof(slb_handle h);   /* N: getDOF() (State.hpp:373-376,590-593) */
+int slb_qdim(slb_handle h);  /* length of a q-vector                    */
+
+/* ---- state access: muState()/PkAugmentedState() (Usckf.hpp:518-526), getPk()/setPk()
+ *      (Msckf.hpp:386-395), ukf::mu()/sigma() ------------------------------------------------ */
+int slb_upload(slb_handle h, int field, const void *host, size_t count, void *stream);
+int slb_download(slb_handle h, int field, void *host, size_t count, void *stream);
+/* Raw device storage (engine-native layout) for zero-copy consumers. */
+int slb_device_ptr(slb_handle h, int field, void **dev);
+
+/* ---- ukfom::ukf<state> ----------------------------------------------------------------- */
+/* predict(g, R): sigma points -> g -> manifold mean -> cov + Q. u_dev: batch x nu (instance-
+ * major), Q_dev: n x n row-major shared by the batch. */
+int slb_ukf_predict(slb_handle h, int pm, const double *u_dev, double dt, const double *Q_dev,
+                    void *stream);
+/* update(z, h, R[, mt]): gate_dof = 0 accepts any Mahalanobis distance, 1..9 applies the 5%
+ * chi-square table (Usckf.hpp:794-855). z_dev: batch x m, R_dev: m x m shared. */
+int slb_ukf_update(slb_handle h, int mm, const double *z_dev, const double *R_dev, int gate_dof,
+                   void *stream);
+/* predict immediately followed by update in one launch (one HBM round trip). */
+int slb_ukf_step(slb_handle h, int pm, int mm, const double *u_dev, double dt,
+                 const double *Q_dev, const double *z_dev, const double *R_dev, int gate_dof,
+                 void *stream);
+/* Same step with HOST buffers: copies u and z to the device, runs the step, copies the
+ * posterior q-vectors back (mu_out_host: batch x qdim, may be NULL) and synchronises. */
+int slb_ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt,
+                      const double *Q_host, const double *z_host, const double *R_host,
+                      int gate_dof, double *mu_out_host, void *stream);
+
+/* ---- localization::Usckf --------------------------------------------------------------- */
+/* predict(f, Q) Usckf.hpp:107-244 */
+int slb_usckf_predict(slb_handle h, int pm, const double *u_dev, double dt, const double *Q_dev,
+                      void *stream);
+/* update(z, h, R[, mt]) Usckf.hpp:246-308; z_dev: batch x m, R_dev: m x m shared */
+int slb_usckf_update(slb_handle h, int mm, const double *z_dev, const double *R_dev,
+                     int gate_dof, void *stream);
+int slb_usckf_step(slb_handle h, int pm, int mm, const double *u_dev, double dt,
+                   const double *Q_dev, const double *z_dev, const double *R_dev, int gate_dof,
+                   void *stream);
+int slb_usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt,
+                        const double *Q_host, const double *z_host, const double *R_host,
+                        int gate_dof, double *mu_out_host, void *stream);
+/* cloning(mode) Usckf.hpp:391-433 */
+int slb_usckf_clone(slb_handle h, int mode, void *stream);
+/* setMeasurement(mode, z, R) Usckf.hpp:322-389; z_dev: batch x len, R_dev: len x len shared.
+ * len must equal the configured nk (mode STATEK) or nl (STATEK_L). */
+int slb_usckf_set_measurement(slb_handle h, int mode, const double *z_dev, const double *R_dev,
+                              void *stream);
+
+/* ---- localization::Msckf --------------------------------------------------------------- */
+/* predict(f, Q) Msckf.hpp:89-189 */
+int slb_msckf_predict(slb_handle h, int pm, const double *u_dev, double dt, const double *Q_dev,
+                      void *stream);
+/* update(z, h, R[, mt]) Msckf.hpp:196-277 (UKF flavour, per-feature 2-dof gate when gate != 0).
+ * params_dev: model parameters shared by the batch (REPROJ: nfeat x 3 landmark coordinates);
+ * z_dev: batch x m; R_dev: m x m shared.  The per-instance outlier count (the reference's
+ * return value, :276) is kept in SLB_FIELD_OUTLIERS. */
+int slb_msckf_update(slb_handle h, int mm, const double *params_dev, int m, const double *z_dev,
+                     const double *R_dev, int gate, void *stream);
+
+/* ---- localization::DataModel<double,D> ---------------------------------------------------
+ * fusion(data2) DataModel.hpp:48-60 over n independent pairs.  Instance-major device arrays:
+ * x*: n x d, C*: n x d x d row-major.  d in {3, 6}.  Output may alias input 1 (in-place, like
+ * the reference's data1.fusion(data2)). */
+int slb_datamodel_fuse(int d, int64_t n, const double *x1, const double *C1, const double *x2,
+                       const double *C2, double *xo, double *Co, void *stream);
+/* operator+ / operator- DataModel.hpp:132-152 (both ADD the covariances). sign = +1 / -1 */
+int slb_datamodel_addsub(int d, int64_t n, int sign, const double *x1, const double *C1,
+                         const double *x2, const double *C2, double *xo, double *Co, void *stream);
+/* Host-buffer variant of slb_datamodel_fuse (H2D, kernel, D2H, synchronise). */
+int slb_datamodel_fuse_host(int d, int64_t n, const double *x1, const double *C1,
+                            const double *x2, const double *C2, double *xo, double *Co);
+
+/* ---- diagnostics ----------------------------------------------------------------------- */
+/* counts[0..3] = instances with CHOL_FAIL / MEAN_NOCONV / GATE_REJECT / NONFINITE set. */
+int slb_status(slb_handle h, int64_t counts[4], void *stream);
+int slb_clear_status(slb_handle h, void *stream);
+/* Ensemble statistics of the instance means over this device's shard (new; no reference
+ * counterpart): out = { count, sum x[nv], sum x x^T[nv*nv] } with x = the vect<3> blocks and
+ * the SO3 log of every block of the q-vector; out_dev has 1 + nv + nv*nv doubles, nv = N.
+ * Multi-GPU callers all-reduce out_dev (NCCL sum) -- see bench.py. */
+int slb_ensemble_stats(slb_handle h, double *out_dev, void *stream);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t slb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLB_H_ */

@@ -1,0 +1,236 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libslo.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The oracle is a dependency-free restatement of the reference's Eigen/MTK
+algorithm (see oracle/slo_core.hpp for what is and is not pinned by the reference's tests).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libslo.so")
+
+# ids shared with include/slb.h
+LAYOUT_POSE6, LAYOUT_MTK9, LAYOUT_STATE12 = 6, 9, 12
+PM_UKFOM_IMU, PM_UKFOM_IMU_REFBUG, PM_POSE6_ODOM, PM_USCKF_TEST, PM_MSCKF_DELTAPOSE = 1, 2, 3, 4, 5
+MM_GPS_POS, MM_USCKF_VO, MM_MSCKF_REPROJ = 101, 102, 103
+STATEK, STATEK_L, STATEK_I = 1, 2, 3
+ST_CHOL_FAIL, ST_MEAN_NOCONV, ST_GATE_REJECT, ST_NONFINITE = 1, 2, 4, 8
+
+LAYOUT_BLOCKS = {LAYOUT_POSE6: [0, 1], LAYOUT_MTK9: [0, 1, 0], LAYOUT_STATE12: [0, 1, 0, 0]}
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++ only, no dependencies)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []),
+                              stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def hardware_threads():
+    return int(lib().slo_hardware_threads())
+
+
+# ---- primitives --------------------------------------------------------------------------------
+def so3_exp(v, scale=1.0):
+    v = _d(v)
+    q = np.empty(4)
+    lib().slo_so3_exp(_p(v), C.c_double(scale), _p(q))
+    return q
+
+
+def so3_log(q):
+    q = _d(q)
+    v = np.empty(3)
+    lib().slo_so3_log(_p(q), _p(v))
+    return v
+
+
+def _lay(blocks):
+    b = _i(blocks)
+    return b, len(blocks)
+
+
+def qdim(blocks, nfeat=0):
+    return sum(4 if s else 3 for s in blocks) + nfeat
+
+
+def boxplus(blocks, x, d, nfeat=0):
+    b, nb = _lay(blocks)
+    x, d = _d(x), _d(d)
+    y = np.empty_like(x)
+    lib().slo_boxplus(_p(b), nb, nfeat, _p(x), _p(d), _p(y))
+    return y
+
+
+def boxminus(blocks, a, bb, nfeat=0):
+    b, nb = _lay(blocks)
+    a, bb = _d(a), _d(bb)
+    d = np.empty(3 * nb + nfeat)
+    lib().slo_boxminus(_p(b), nb, nfeat, _p(a), _p(bb), _p(d))
+    return d
+
+
+def set_from_vector(blocks, v, nfeat=0):
+    b, nb = _lay(blocks)
+    v = _d(v)
+    x = np.empty(qdim(blocks, nfeat))
+    lib().slo_set_from_vector(_p(b), nb, nfeat, _p(v), _p(x))
+    return x
+
+
+def get_vectorized(blocks, x, nfeat=0):
+    b, nb = _lay(blocks)
+    x = _d(x)
+    v = np.empty(3 * nb + nfeat)
+    lib().slo_get_vectorized(_p(b), nb, nfeat, _p(x), _p(v))
+    return v
+
+
+def llt(P):
+    P = _d(P)
+    n = P.shape[0]
+    L = np.empty_like(P)
+    info = lib().slo_llt(n, _p(P), _p(L))
+    return L, info
+
+
+def inverse(A, fixed=False):
+    A = _d(A)
+    Ai = np.empty_like(A)
+    lib().slo_inverse(A.shape[0], _p(A), _p(Ai), int(fixed))
+    return Ai
+
+
+def accept_mahalanobis(m2, dof):
+    lib().slo_accept_mahalanobis.argtypes = [C.c_double, C.c_int]
+    return bool(lib().slo_accept_mahalanobis(float(m2), int(dof)))
+
+
+# ---- filters (batched, instance-major; return new arrays) ----------------------------------------
+def ukf_step(layout, pm, mm, mu, P, u, dt, Q, z, R, gate_dof=0, predict=True, update=True, nthreads=1):
+    mu, P = _d(mu).copy(), _d(P).copy()
+    B = mu.shape[0]
+    u = _d(u) if u is not None else np.zeros((B, 6))
+    z = _d(z) if z is not None else np.zeros((B, 3))
+    n = P.shape[1]
+    Q = _d(Q) if Q is not None else np.zeros((n, n))
+    R = _d(R) if R is not None else np.zeros((3, 3))
+    st = np.zeros(B, np.int32)
+    it = np.zeros(B, np.int32)
+    rc = lib().slo_ukf_step(layout, pm, mm, B, _p(mu), _p(P), _p(u), C.c_double(dt), _p(Q), _p(z), _p(R),
+                            gate_dof, int(predict), int(update), _p(st), _p(it), nthreads)
+    assert rc == 0
+    return mu, P, st, it
+
+
+def usckf_step(pm, mm, nk, nl, mu, P, u, dt, Q, z, R, gate_dof=0, predict=True, update=True, nthreads=1):
+    mu, P = _d(mu).copy(), _d(P).copy()
+    B = mu.shape[0]
+    u = _d(u) if u is not None else np.zeros((B, 6))
+    z = _d(z) if z is not None else np.zeros((B, max(nk, 1)))
+    Q = _d(Q) if Q is not None else np.zeros((12, 12))
+    R = _d(R) if R is not None else np.zeros((max(nk, 1), max(nk, 1)))
+    st = np.zeros(B, np.int32)
+    it = np.zeros(B, np.int32)
+    rc = lib().slo_usckf_step(pm, mm, B, nk, nl, _p(mu), _p(P), _p(u), C.c_double(dt), _p(Q), _p(z), _p(R),
+                              gate_dof, int(predict), int(update), _p(st), _p(it), nthreads)
+    assert rc == 0
+    return mu, P, st, it
+
+
+def usckf_clone(mode, nk, nl, mu, P):
+    mu, P = _d(mu).copy(), _d(P).copy()
+    lib().slo_usckf_clone(mode, mu.shape[0], nk, nl, _p(mu), _p(P), 1)
+    return mu, P
+
+
+def usckf_ctor_single(mu_single, P_single):
+    mu_single, P_single = _d(mu_single), _d(P_single)
+    B = mu_single.shape[0]
+    mu = np.empty((B, 39))
+    P = np.empty((B, 36, 36))
+    lib().slo_usckf_ctor_single(B, _p(mu_single), _p(P_single), _p(mu), _p(P))
+    return mu, P
+
+
+def usckf_set_measurement(mode, nk, nl, mu, P, z, R):
+    mu, P, z, R = _d(mu), _d(P), _d(z), _d(R)
+    B, ln = z.shape
+    nk2 = ln if mode == STATEK else nk
+    nl2 = ln if mode == STATEK_L else nl
+    mu2 = np.empty((B, 39 + nk2 + nl2))
+    P2 = np.empty((B, 36 + nk2 + nl2, 36 + nk2 + nl2))
+    lib().slo_usckf_set_measurement(mode, B, nk, nl, _p(mu), _p(P), ln, _p(z), _p(R), _p(mu2), _p(P2))
+    return mu2, P2
+
+
+def msckf_predict(pm, k, mu, P, u, dt, Q, nthreads=1):
+    mu, P, u, Q = _d(mu).copy(), _d(P).copy(), _d(u), _d(Q)
+    B = mu.shape[0]
+    st = np.zeros(B, np.int32)
+    rc = lib().slo_msckf_predict(pm, B, k, _p(mu), _p(P), _p(u), C.c_double(dt), _p(Q), _p(st), nthreads)
+    assert rc == 0
+    return mu, P, st
+
+
+def msckf_update(mm, k, mu, P, landmarks, z, R, gate=True, nthreads=1):
+    mu, P, landmarks, z, R = _d(mu).copy(), _d(P).copy(), _d(landmarks), _d(z), _d(R)
+    B, m = z.shape
+    out = np.zeros(B, np.int32)
+    st = np.zeros(B, np.int32)
+    it = np.zeros(B, np.int32)
+    rc = lib().slo_msckf_update(mm, B, k, _p(mu), _p(P), _p(landmarks), m, _p(z), _p(R), int(gate), _p(out),
+                                _p(st), _p(it), nthreads)
+    assert rc == 0
+    return mu, P, out, st, it
+
+
+def msckf_remove_outliers(innov, S, N=12):
+    innov, S = _d(innov), _d(S)
+    m = innov.shape[0]
+    kept = np.zeros(m, np.int32)
+    nk = C.c_int(0)
+    o = lib().slo_msckf_remove_outliers(m, N, _p(innov), _p(S), _p(kept), C.byref(nk))
+    return int(o), kept[: nk.value].copy()
+
+
+def datamodel(op, x1, C1, x2, C2, nthreads=1):
+    x1, C1, x2, C2 = _d(x1), _d(C1), _d(x2), _d(C2)
+    n, d = x1.shape
+    xo, Co = np.empty_like(x1), np.empty_like(C1)
+    lib().slo_datamodel(int(op), d, C.c_longlong(n), _p(x1), _p(C1), _p(x2), _p(C2), _p(xo), _p(Co), nthreads)
+    return xo, Co
+
+
+def datamodel_default(d):
+    x, Cv = np.empty(d), np.empty((d, d))
+    lib().slo_datamodel_default(d, _p(x), _p(Cv))
+    return x, Cv

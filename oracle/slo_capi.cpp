@@ -1,0 +1,237 @@
+// oracle/slo_capi.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// extern "C" surface of the CPU oracle (restatement of the reference's Eigen/MTK algorithm;
+// PARITY UNPINNED for filter outputs, see slo_core.hpp).  Batches are instance-major dense
+// arrays; every entry point loops the single-instance restatement over the batch, optionally
+// on `nthreads` std::threads (instances are independent -- this is also how the CPU baseline
+// in bench.py uses all host cores).
+#include <algorithm>
+#include <thread>
+
+#include "slo_models.hpp"
+
+using namespace slo;
+
+namespace {
+
+template <typename F>
+void parallel_for(int B, int nthreads, F body) {
+    if (nthreads <= 1 || B <= 1) {
+        for (int i = 0; i < B; ++i) body(i);
+        return;
+    }
+    nthreads = std::min(nthreads, B);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([=]() {
+            const int lo = (int)((long long)B * t / nthreads), hi = (int)((long long)B * (t + 1) / nthreads);
+            for (int i = lo; i < hi; ++i) body(i);
+        });
+    for (auto &t : th) t.join();
+}
+
+Mat load_mat(const double *p, int r, int c) {
+    Mat m(r, c);
+    std::copy(p, p + (size_t)r * c, m.a.begin());
+    return m;
+}
+void store_mat(const Mat &m, double *p) { std::copy(m.a.begin(), m.a.end(), p); }
+
+Layout ukf_layout(int id) {
+    switch (id) {
+        case SLB_LAYOUT_POSE6: return Layout::pose6();
+        case SLB_LAYOUT_MTK9: return Layout::mtk9();
+        default: return Layout::state12();
+    }
+}
+int pm_nu(int pm) { return pm == SLB_PM_MSCKF_DELTAPOSE ? 13 : 6; }
+
+}  // namespace
+
+extern "C" {
+
+// ---- primitives (exposed for the algebra / linalg pin tests) --------------------------------
+void slo_so3_exp(const double *v, double scale, double *q) { so3_exp(v, scale, q); }
+void slo_so3_log(const double *q, double *v) { so3_log(q, v); }
+// layout given as an array of nblk flags (1 = SO3) plus nfeat
+static Layout mk(const int *so3, int nblk, int nfeat) {
+    Layout l;
+    for (int i = 0; i < nblk; ++i) l.so3.push_back((uint8_t)so3[i]);
+    l.nfeat = nfeat;
+    return l;
+}
+void slo_boxplus(const int *so3, int nblk, int nfeat, const double *x, const double *d, double *y) {
+    Layout l = mk(so3, nblk, nfeat);
+    Vec r = boxplus(l, Vec(x, x + l.qdim()), Vec(d, d + l.dof()));
+    std::copy(r.begin(), r.end(), y);
+}
+void slo_boxminus(const int *so3, int nblk, int nfeat, const double *a, const double *b, double *d) {
+    Layout l = mk(so3, nblk, nfeat);
+    Vec r = boxminus(l, Vec(a, a + l.qdim()), Vec(b, b + l.qdim()));
+    std::copy(r.begin(), r.end(), d);
+}
+void slo_set_from_vector(const int *so3, int nblk, int nfeat, const double *v, double *x) {
+    Layout l = mk(so3, nblk, nfeat);
+    Vec r = set_from_vector(l, Vec(v, v + l.dof()));
+    std::copy(r.begin(), r.end(), x);
+}
+void slo_get_vectorized(const int *so3, int nblk, int nfeat, const double *x, double *v) {
+    Layout l = mk(so3, nblk, nfeat);
+    Vec r = get_vectorized(l, Vec(x, x + l.qdim()));
+    std::copy(r.begin(), r.end(), v);
+}
+int slo_llt(int n, const double *P, double *L) {
+    Mat l;
+    int info = llt_lower(load_mat(P, n, n), l);
+    store_mat(l, L);
+    return info;
+}
+void slo_inverse(int n, const double *A, double *Ai, int fixed) {
+    Mat m = load_mat(A, n, n);
+    store_mat(fixed ? inverse_fixed(m) : inverse_lu(m), Ai);
+}
+int slo_accept_mahalanobis(double m2, int dof) { return accept_mahalanobis_distance(m2, dof) ? 1 : 0; }
+
+// ---- ukfom::ukf -----------------------------------------------------------------------------
+// mu: B x q, P: B x n x n, u: B x 6, z: B x 3; Q (n x n) and R (3 x 3) shared.
+int slo_ukf_step(int layout, int pm, int mm, int B, double *mu, double *P, const double *u, double dt,
+                 const double *Q, const double *z, const double *R, int gate_dof, int do_predict,
+                 int do_update, int *status, int *mean_iters, int nthreads) {
+    const Layout l = ukf_layout(layout);
+    const int n = l.dof(), q = l.qdim(), nu = pm_nu(pm), m = 3;
+    if (do_update && mm != SLB_MM_GPS_POS) return -1;
+    parallel_for(B, nthreads, [&](int i) {
+        Ukf f(l, Vec(mu + (size_t)i * q, mu + (size_t)(i + 1) * q), load_mat(P + (size_t)i * n * n, n, n));
+        if (do_predict) f.predict(make_process_model(pm, u + (size_t)i * nu, dt), load_mat(Q, n, n));
+        if (do_update) f.update(Vec(z + (size_t)i * m, z + (size_t)(i + 1) * m), mm_gps_pos, load_mat(R, m, m), gate_dof);
+        std::copy(f.mu.begin(), f.mu.end(), mu + (size_t)i * q);
+        store_mat(f.sigma, P + (size_t)i * n * n);
+        if (status) status[i] = f.status;
+        if (mean_iters) mean_iters[i] = f.last_mean_iters;
+    });
+    return 0;
+}
+
+// ---- localization::Usckf --------------------------------------------------------------------
+// mu: B x (39+nk+nl), P: B x N x N with N = 36+nk+nl
+int slo_usckf_step(int pm, int mm, int B, int nk, int nl, double *mu, double *P, const double *u,
+                   double dt, const double *Q, const double *z, const double *R, int gate_dof,
+                   int do_predict, int do_update, int *status, int *mean_iters, int nthreads) {
+    const int N = 36 + nk + nl, q = 39 + nk + nl, nu = pm_nu(pm), m = nk;
+    if (do_update && mm != SLB_MM_USCKF_VO) return -1;
+    parallel_for(B, nthreads, [&](int i) {
+        Usckf f(Vec(mu + (size_t)i * q, mu + (size_t)(i + 1) * q), nk, nl, load_mat(P + (size_t)i * N * N, N, N));
+        if (do_predict) f.predict(make_process_model(pm, u + (size_t)i * nu, dt), load_mat(Q, 12, 12));
+        if (do_update)
+            f.update(Vec(z + (size_t)i * m, z + (size_t)(i + 1) * m), [nk](const Vec &a) { return mm_usckf_vo(a, nk); },
+                     load_mat(R, m, m), gate_dof);
+        std::copy(f.mu.begin(), f.mu.end(), mu + (size_t)i * q);
+        store_mat(f.Pk, P + (size_t)i * N * N);
+        if (status) status[i] = f.status;
+        if (mean_iters) mean_iters[i] = f.last_mean_iters;
+    });
+    return 0;
+}
+int slo_usckf_clone(int mode, int B, int nk, int nl, double *mu, double *P, int nthreads) {
+    const int N = 36 + nk + nl, q = 39 + nk + nl;
+    parallel_for(B, nthreads, [&](int i) {
+        Usckf f(Vec(mu + (size_t)i * q, mu + (size_t)(i + 1) * q), nk, nl, load_mat(P + (size_t)i * N * N, N, N));
+        f.cloning(mode);
+        std::copy(f.mu.begin(), f.mu.end(), mu + (size_t)i * q);
+        store_mat(f.Pk, P + (size_t)i * N * N);
+    });
+    return 0;
+}
+// ctor #2 (Usckf.hpp:90-103): single-state in, 39-vector and 36x36 out
+int slo_usckf_ctor_single(int B, const double *mu_single, const double *P_single, double *mu, double *P) {
+    for (int i = 0; i < B; ++i) {
+        Usckf f(Vec(mu_single + (size_t)i * 13, mu_single + (size_t)(i + 1) * 13), load_mat(P_single + (size_t)i * 144, 12, 12));
+        std::copy(f.mu.begin(), f.mu.end(), mu + (size_t)i * 39);
+        store_mat(f.Pk, P + (size_t)i * 36 * 36);
+    }
+    return 0;
+}
+// setMeasurement: sizes change, so in/out arrays are separate.  len = z size; R: len x len shared
+int slo_usckf_set_measurement(int mode, int B, int nk, int nl, const double *mu_in, const double *P_in,
+                              int len, const double *z, const double *R, double *mu_out, double *P_out) {
+    const int N = 36 + nk + nl, q = 39 + nk + nl;
+    const int nk2 = mode == SLB_STATEK ? len : nk, nl2 = mode == SLB_STATEK_L ? len : nl;
+    const int N2 = 36 + nk2 + nl2, q2 = 39 + nk2 + nl2;
+    for (int i = 0; i < B; ++i) {
+        Usckf f(Vec(mu_in + (size_t)i * q, mu_in + (size_t)(i + 1) * q), nk, nl, load_mat(P_in + (size_t)i * N * N, N, N));
+        f.set_measurement(mode, Vec(z + (size_t)i * len, z + (size_t)(i + 1) * len), load_mat(R, len, len));
+        std::copy(f.mu.begin(), f.mu.end(), mu_out + (size_t)i * q2);
+        store_mat(f.Pk, P_out + (size_t)i * N2 * N2);
+    }
+    return 0;
+}
+
+// ---- localization::Msckf --------------------------------------------------------------------
+// mu: B x (13+7k), P: B x N x N, N = 12+6k; u: B x 13; z: B x m; landmarks: nfeat x 3 (m = 2 nfeat)
+int slo_msckf_predict(int pm, int B, int k, double *mu, double *P, const double *u, double dt,
+                      const double *Q, int *status, int nthreads) {
+    const int N = 12 + 6 * k, q = 13 + 7 * k, nu = pm_nu(pm);
+    parallel_for(B, nthreads, [&](int i) {
+        Msckf f(k, Vec(mu + (size_t)i * q, mu + (size_t)(i + 1) * q), load_mat(P + (size_t)i * N * N, N, N));
+        f.predict(make_process_model(pm, u + (size_t)i * nu, dt), load_mat(Q, 12, 12));
+        std::copy(f.mu.begin(), f.mu.end(), mu + (size_t)i * q);
+        store_mat(f.Pk, P + (size_t)i * N * N);
+        if (status) status[i] = f.status;
+    });
+    return 0;
+}
+int slo_msckf_update(int mm, int B, int k, double *mu, double *P, const double *landmarks, int m,
+                     const double *z, const double *R, int gate, int *outliers, int *status,
+                     int *mean_iters, int nthreads) {
+    const int N = 12 + 6 * k, q = 13 + 7 * k, nfeat = m / 2;
+    if (mm != SLB_MM_MSCKF_REPROJ) return -1;
+    parallel_for(B, nthreads, [&](int i) {
+        Msckf f(k, Vec(mu + (size_t)i * q, mu + (size_t)(i + 1) * q), load_mat(P + (size_t)i * N * N, N, N));
+        unsigned o = f.update(Vec(z + (size_t)i * m, z + (size_t)(i + 1) * m),
+                              [=](const Vec &s) { return mm_msckf_reproj(s, k, landmarks, nfeat); },
+                              load_mat(R, m, m), gate != 0);
+        std::copy(f.mu.begin(), f.mu.end(), mu + (size_t)i * q);
+        store_mat(f.Pk, P + (size_t)i * N * N);
+        if (outliers) outliers[i] = (int)o;
+        if (status) status[i] = f.status;
+        if (mean_iters) mean_iters[i] = f.last_mean_iters;
+    });
+    return 0;
+}
+// removeOutliers alone (Msckf.hpp:723-754, quirk Q6): returns the kept original row indices
+int slo_msckf_remove_outliers(int m, int N, const double *innov, const double *S, int *kept, int *nkept) {
+    Msckf f(0, Layout::state12().identity(), Mat(12, 12));
+    Vec in(innov, innov + m);
+    Mat s = load_mat(S, m, m), c(N, m);
+    std::vector<int> k;
+    unsigned o = f.remove_outliers(in, c, s, &k);
+    std::copy(k.begin(), k.end(), kept);
+    *nkept = (int)k.size();
+    return (int)o;
+}
+
+// ---- localization::DataModel ----------------------------------------------------------------
+// x*: n x d, C*: n x d x d; op: 0 fusion, +1 operator+, -1 operator-
+int slo_datamodel(int op, int d, long long n, const double *x1, const double *C1, const double *x2,
+                  const double *C2, double *xo, double *Co, int nthreads) {
+    parallel_for((int)n, nthreads, [&](int i) {
+        DataModel a(Vec(x1 + (size_t)i * d, x1 + (size_t)(i + 1) * d), load_mat(C1 + (size_t)i * d * d, d, d));
+        DataModel b(Vec(x2 + (size_t)i * d, x2 + (size_t)(i + 1) * d), load_mat(C2 + (size_t)i * d * d, d, d));
+        if (op == 0) a.fusion(b);
+        else if (op > 0) a = a.plus(b);
+        else a = a.minus(b);
+        std::copy(a.data.begin(), a.data.end(), xo + (size_t)i * d);
+        store_mat(a.Cov, Co + (size_t)i * d * d);
+    });
+    return 0;
+}
+// default constructor (DataModel.hpp:32-36)
+void slo_datamodel_default(int d, double *x, double *C) {
+    DataModel a(d);
+    std::copy(a.data.begin(), a.data.end(), x);
+    store_mat(a.Cov, C);
+}
+
+int slo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"
