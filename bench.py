@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- filter-steps/sec of the batched sigma-point filter hot path on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ukfom|usckf|msckf|fusion]
+                  [--impl reference]
+
+A "step" is one pass of the hot path (predict + update) over one batch of synthetic inputs.  The
+default workload is BASELINE.json configs[1]: batched UKFoM on the MTK pos/SO(3)/vel state, 65,536
+independent instances per GPU.  One process per GPU (torchrun for N > 1); instances shard by index
+with no collective on the step path ("weak" scaling: the per-GPU fleet is fixed); the only NCCL
+traffic is the end-of-run all-reduce of the ensemble statistics, reported separately.
+
+One JSON line is printed by rank 0; see the task contract for the keys.  `--impl reference` times
+the reference's CPU algorithm instead: the dependency-free oracle port (the reference itself needs
+Eigen/MTK/Boost, absent from this image) on all host cores, on a bounded sample of the same
+workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from slam_localization_b200 import synth  # noqa: E402
+
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------------
+class UkfomWorkload:
+    """BASELINE config 2: batched UKFoM (MTK9: pos, SO(3), vel), 65,536 instances per GPU, IMU predict +
+    GPS update fused in one launch.  Several independent fleets are rotated so that consecutive
+    steps never find their state in L2 (total resident footprint > 2x L2)."""
+    name = "ukfom"
+    metric = "filter-steps/sec (predict+update)"
+    unit = "filter-steps/s"
+    B = 65536
+    layout = 9
+    bytes_per_unit = 952            # 2*8*(45+10) + 72
+    flops_per_unit = 1.4e4
+    kernel = "slbd::ukf_kernel<MTK9, IMU, GPS, fused>"
+
+    def __init__(self, rank, seed=1234):
+        self.seed = seed + 1000 * rank
+        self.sc = synth.ukfom_scenario(self.B, seed=self.seed, layout=self.layout, p_scale=1e-4)
+        self.QD = 10
+
+    def describe(self):
+        return {"workload": "configs[1]: batched UKFoM, MTK9 pos/SO(3)/vel state, IMU predict + GPS update",
+                "instances_per_gpu": self.B, "n": 9, "sigma_points": 19, "m": 3}
+
+    def setup_gpu(self, engine, torch):
+        per_fleet = (45 + 10) * 8 * self.B
+        self.nfleets = max(2, int(np.ceil(2.2 * L2_BYTES / per_fleet)))
+        self.fleets = []
+        for _ in range(self.nfleets):
+            f = engine.Ukf(self.B, layout=self.layout)
+            f.set_state(self.sc["mu"], self.sc["P"])
+            self.fleets.append(f)
+        self.engine = engine
+        self.Q = engine.DeviceArray(self.sc["Q"])
+        self.R = engine.DeviceArray(self.sc["R"])
+        self.u = [engine.DeviceArray(self.sc["u"]) for _ in range(2)]
+        self.z = [engine.DeviceArray(self.sc["z"]) for _ in range(2)]
+        # host (pinned) buffers for the end-to-end arm
+        self.hu = torch.from_numpy(self.sc["u"].copy()).pin_memory()
+        self.hz = torch.from_numpy(self.sc["z"].copy()).pin_memory()
+        self.hQ = torch.from_numpy(self.sc["Q"].copy()).pin_memory()
+        self.hR = torch.from_numpy(self.sc["R"].copy()).pin_memory()
+        self.hmu = torch.empty((self.B, self.QD), dtype=torch.float64).pin_memory()
+        self.l2_policy = "rotating %d resident fleets (%.0f MB > L2)" % (self.nfleets, self.nfleets * per_fleet / 1e6)
+
+    def step(self, k):
+        e = self.engine
+        self.fleets[k % self.nfleets].step(e.PM_UKFOM_IMU, e.MM_GPS_POS, self.u[k & 1], self.sc["dt"], self.Q,
+                                           self.z[k & 1], self.R)
+
+    def step_e2e(self, k):
+        e = self.engine
+        self.fleets[k % self.nfleets].step_host(e.PM_UKFOM_IMU, e.MM_GPS_POS, self.hu, self.sc["dt"], self.hQ, self.hz,
+                                                self.hR, mu_out=self.hmu)
+
+    def e2e_bytes(self):
+        return (self.B * 9 + 81 + 9) * 8, self.B * self.QD * 8
+
+    def units_per_step(self):
+        return self.B
+
+    def launches_per_step(self):
+        return 1
+
+    def status_ok(self):
+        return all(sum(f.status_counts()) == 0 for f in self.fleets)
+
+    def stats_tensor(self):
+        return self.fleets[0].ensemble_stats().t
+
+    def cpu_step(self, slo, nsample, nthreads):
+        sc = self.sc
+        t0 = time.perf_counter()
+        slo.ukf_step(9, slo.PM_UKFOM_IMU, slo.MM_GPS_POS, sc["mu"][:nsample], sc["P"][:nsample], sc["u"][:nsample],
+                     sc["dt"], sc["Q"], sc["z"][:nsample], sc["R"], nthreads=nthreads)
+        return time.perf_counter() - t0
+
+
+class FusionWorkload:
+    """BASELINE config 5: DataModel covariance fusion, 1M 6-dof pairwise fusions per step."""
+    name = "fusion"
+    metric = "fusions/sec (DataModel::fusion, d=6)"
+    unit = "fusions/s"
+    B = 1 << 20
+    d = 6
+    bytes_per_unit = 648            # packed-symmetric accounting; dense traffic is 1008 B
+    flops_per_unit = 2.6e3
+    kernel = "slbd::datamodel_kernel<6, fusion>"
+
+    def __init__(self, rank, seed=99):
+        self.sc = synth.fusion_scenario(self.B, d=self.d, seed=seed + rank)
+
+    def describe(self):
+        return {"workload": "configs[4]: DataModel covariance fusion, 6-dof, pairwise", "fusions_per_step": self.B}
+
+    def setup_gpu(self, engine, torch):
+        self.engine = engine
+        self.a = [engine.DeviceArray(self.sc[k]) for k in ("x1", "C1", "x2", "C2")]
+        self.out = (engine.DeviceArray(shape=(self.B, self.d)), engine.DeviceArray(shape=(self.B, self.d, self.d)))
+        self.h = [torch.from_numpy(self.sc[k]).pin_memory() for k in ("x1", "C1", "x2", "C2")]
+        self.ho = (torch.empty((self.B, self.d), dtype=torch.float64).pin_memory(),
+                   torch.empty((self.B, self.d, self.d), dtype=torch.float64).pin_memory())
+        self.l2_policy = "inputs+outputs 1057 MB per step > L2"
+
+    def step(self, k):
+        self.engine.DataModel.fuse(*self.a, out=self.out)
+
+    def step_e2e(self, k):
+        e = self.engine
+        e.check(e.lib().slb_datamodel_fuse_host(self.d, self.B, *[e._ptr_of(t) for t in self.h],
+                                                e._ptr_of(self.ho[0]), e._ptr_of(self.ho[1])))
+
+    def e2e_bytes(self):
+        return 2 * self.B * (self.d + self.d * self.d) * 8, self.B * (self.d + self.d * self.d) * 8
+
+    def units_per_step(self):
+        return self.B
+
+    def launches_per_step(self):
+        return 1
+
+    def status_ok(self):
+        return True
+
+    def stats_tensor(self):
+        return None
+
+    def cpu_step(self, slo, nsample, nthreads):
+        sc = self.sc
+        t0 = time.perf_counter()
+        slo.datamodel(0, sc["x1"][:nsample], sc["C1"][:nsample], sc["x2"][:nsample], sc["C2"][:nsample], nthreads=nthreads)
+        return time.perf_counter() - t0
+
+
+WORKLOADS = {"ukfom": UkfomWorkload, "fusion": FusionWorkload}
+
+
+def register_workload(cls):
+    WORKLOADS[cls.name] = cls
+    return cls
+
+
+try:  # heavier workloads live next to the kernels they exercise
+    import bench_workloads  # noqa: F401,E402
+except ImportError:
+    pass
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_baseline(wl, steps=1, warmup=0, budget_s=12.0):
+    """Times the oracle (CPU restatement of the reference's algorithm) on all host threads over a
+    bounded sample of the same workload."""
+    from oracle import slo
+    slo.build()
+    cores = slo.hardware_threads()
+    n0 = min(wl.units_per_step(), 64 * cores)
+    t = wl.cpu_step(slo, n0, cores)
+    rate = n0 / t
+    nsample = int(min(wl.units_per_step(), max(n0, rate * budget_s / max(1, steps + warmup))))
+    for _ in range(warmup):
+        wl.cpu_step(slo, nsample, cores)
+    ts = [wl.cpu_step(slo, nsample, cores) for _ in range(max(1, steps))]
+    tot = sum(ts)
+    return {"value": nsample * len(ts) / tot, "unit": wl.unit, "cores": cores, "kind": "port",
+            "sample": "%d of %d units per step, %d step(s), oracle/libslo.so on %d threads" %
+                      (nsample, wl.units_per_step(), len(ts), cores)}, tot / len(ts) * 1e3
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload](0)
+    cb, ms = cpu_baseline(wl, steps=args.steps, warmup=args.warmup, budget_s=60.0)
+    line = {"impl": "reference", "metric": wl.metric, "value": cb["value"], "unit": wl.unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.describe(),
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference's own Eigen/MTK code cannot be built in this image; timed arm is the oracle port"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="ukfom", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; the engine has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from slam_localization_b200 import engine
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = WORKLOADS[args.workload](rank)
+    wl.setup_gpu(engine, torch)
+    hbm_peak, peak_src = measured_peaks()
+
+    # ---- device-resident arm -----------------------------------------------------------------------
+    for k in range(args.warmup):
+        wl.step(k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        wl.step(args.warmup + k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = engine.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    units = wl.units_per_step() * args.steps * world
+    value = units / (ms_max * 1e-3)
+    ok = wl.status_ok()
+
+    # ---- end-to-end arm: host buffers in, host result out, every step -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ke = max(3, min(args.steps, 50))
+        for k in range(3):
+            wl.step_e2e(k)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(ke):
+            wl.step_e2e(k)
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e = max(e0.elapsed_time(e1), wall)
+        t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d, d2h = wl.e2e_bytes()
+        e2e = {"value": wl.units_per_step() * ke * world / (float(t.item()) * 1e-3), "unit": wl.unit,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke}
+
+    # ---- end-of-run ensemble statistics (the only collective; not on the step path) -----------------
+    gather_ms = None
+    st = wl.stats_tensor()
+    if st is not None:
+        barrier()
+        e0.record()
+        st = wl.stats_tensor()
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        e1.record()
+        barrier()
+        gather_ms = e0.elapsed_time(e1)
+
+    if rank == 0:
+        ms_per_step = ms_max / args.steps
+        launch_ms = ms_per_step / wl.launches_per_step()
+        achieved = wl.bytes_per_unit * wl.units_per_step() / (launch_ms * 1e-3) / 1e9
+        fp64_peak = engine.fp64_peak_tflops()
+        fp64_ach = wl.flops_per_unit * wl.units_per_step() / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(wl.describe(), l2=wl.l2_policy, parallelism="instance-index shard x%d, no step-path collective" % world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": wl.kernel, "algorithmic_bytes_per_unit": wl.bytes_per_unit},
+            "roofline_fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": fp64_ach / fp64_peak if fp64_peak else None,
+                              "algorithmic_flops_per_unit": wl.flops_per_unit,
+                              "peak_source": "measured in this run (slb_bench_fp64_peak, DFMA)"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "status_clean": ok,
+            "ensemble_stats_allreduce_ms": gather_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline(wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -196,6 +196,9 @@ int slb_clear_status(slb_handle h, void *stream);
  * the SO3 log of every block of the q-vector; out_dev has 1 + nv + nv*nv doubles, nv = N.
  * Multi-GPU callers all-reduce out_dev (NCCL sum) -- see bench.py. */
 int slb_ensemble_stats(slb_handle h, double *out_dev, void *stream);
+/* Measures the device's FP64 FMA rate (TFLOP/s, FMA = 2) with a register-resident DFMA kernel:
+ * the roofline denominator for the FP64-bound configs (MEASURED_PEAKS.json has no FP64 entry). */
+int slb_bench_fp64_peak(double *tflops_out);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t slb_launch_count(void);
 

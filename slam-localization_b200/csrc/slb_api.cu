@@ -1,0 +1,596 @@
+// slb_api.cu -- the extern "C" surface declared in include/slb.h: batch lifetime, host<->device
+// state transfer (layout conversion kernels), dispatch to the filter kernels, diagnostics.
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <new>
+
+#include "slb_internal.h"
+#include "slb_math.cuh"
+
+namespace slb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char *what, cudaError_t ce) {
+    if (ce != cudaSuccess)
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(ce));
+    else
+        snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- layout conversion kernels ---------------------------------------------------------------------
+// UKF kind: instance-major host layout <-> SoA
+__global__ void aos_to_soa_mu(const double *aos, double *soa, int B0, int cnt, int QD, int stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt * QD) return;
+    const int i = t / QD, c = t - i * QD;
+    soa[(size_t)c * stride + B0 + i] = aos[t];
+}
+__global__ void soa_to_aos_mu(const double *soa, double *aos, int B0, int cnt, int QD, int stride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt * QD) return;
+    const int i = t / QD, c = t - i * QD;
+    aos[t] = soa[(size_t)c * stride + B0 + i];
+}
+__global__ void dense_to_soa_P(const double *dense, double *soa, int B0, int cnt, int N, int stride) {
+    const int NP = N * (N + 1) / 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)cnt * NP) return;
+    const int e = (int)(t / cnt), i = (int)(t - (int64_t)e * cnt);  // instance fastest: coalesced stores
+    int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while (r * (r + 1) / 2 > e) --r;
+    while ((r + 1) * (r + 2) / 2 <= e) ++r;
+    const int c = e - r * (r + 1) / 2;
+    soa[(size_t)e * stride + B0 + i] = dense[(size_t)i * N * N + r * N + c];
+}
+__global__ void soa_to_dense_P(const double *soa, double *dense, int B0, int cnt, int N, int stride) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)cnt * N * N) return;
+    const int i = (int)(t / (N * N)), rc = (int)(t - (int64_t)i * N * N);
+    int r = rc / N, c = rc - r * N;
+    if (c > r) { const int x = r; r = c; c = x; }
+    dense[t] = soa[(size_t)(r * (r + 1) / 2 + c) * stride + B0 + i];
+}
+// USCKF / MSCKF kinds: instance-major records, P packed lower
+__global__ void aos_to_rec_mu(const double *aos, double *rec, int B0, int cnt, int QD, int qstride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt * QD) return;
+    const int i = t / QD, c = t - i * QD;
+    rec[(size_t)(B0 + i) * qstride + c] = aos[t];
+}
+__global__ void rec_to_aos_mu(const double *rec, double *aos, int B0, int cnt, int QD, int qstride) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt * QD) return;
+    const int i = t / QD, c = t - i * QD;
+    aos[t] = rec[(size_t)(B0 + i) * qstride + c];
+}
+__global__ void dense_to_rec_P(const double *dense, double *rec, int B0, int cnt, int N, int pstride) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)cnt * N * N) return;
+    const int i = (int)(t / (N * N)), rc = (int)(t - (int64_t)i * N * N);
+    const int r = rc / N, c = rc - r * N;
+    if (c <= r) rec[(size_t)(B0 + i) * pstride + r * (r + 1) / 2 + c] = dense[t];
+}
+__global__ void rec_to_dense_P(const double *rec, double *dense, int B0, int cnt, int N, int pstride) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)cnt * N * N) return;
+    const int i = (int)(t / (N * N)), rc = (int)(t - (int64_t)i * N * N);
+    int r = rc / N, c = rc - r * N;
+    if (c > r) { const int x = r; r = c; c = x; }
+    dense[t] = rec[(size_t)(B0 + i) * pstride + r * (r + 1) / 2 + c];
+}
+
+__global__ void status_count(const int32_t *st, int B, unsigned long long *counts) {
+    unsigned long long c[4] = {0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+        const int s = st[i];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[b] += (s >> b) & 1;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        for (int o = 16; o > 0; o >>= 1) c[b] += __shfl_down_sync(0xffffffffu, c[b], o);
+        if ((threadIdx.x & 31) == 0 && c[b]) atomicAdd(counts + b, c[b]);
+    }
+}
+
+// Ensemble statistics: out = {count, sum x, sum x x^T}, x = vectorised mean (log of SO3 blocks).
+// Persistent CTAs, chunks of 64 instances staged in shared memory, register accumulators.
+struct StatLayout {
+    int nblk;
+    unsigned long long so3mask;
+    int nfeat, N, QD;
+    int soa;          // 1: mu is SoA with `stride`; 0: records with `qstride`
+    int stride, qstride;
+};
+constexpr int STAT_CHUNK = 64, STAT_TPB = 256, STAT_MAXACC = 24;
+__global__ void __launch_bounds__(STAT_TPB) ensemble_stats_kernel(const double *mu, int B, StatLayout l, double *out) {
+    extern __shared__ double xs[];  // [STAT_CHUNK][N]
+    const int N = l.N;
+    const int nent = N * N + N;
+    double acc[STAT_MAXACC];
+#pragma unroll
+    for (int k = 0; k < STAT_MAXACC; ++k) acc[k] = 0.0;
+    const int nchunks = (B + STAT_CHUNK - 1) / STAT_CHUNK;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int base = ch * STAT_CHUNK;
+        const int cnt = min(STAT_CHUNK, B - base);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            const int i = base + threadIdx.x;
+            double *x = xs + threadIdx.x * N;
+            int o = 0;
+            auto ld = [&](int c) { return l.soa ? mu[(size_t)c * l.stride + i] : mu[(size_t)i * l.qstride + c]; };
+            for (int b = 0; b < l.nblk; ++b) {
+                if ((l.so3mask >> b) & 1ull) {
+                    const double q[4] = {ld(o), ld(o + 1), ld(o + 2), ld(o + 3)};
+                    double v[3];
+                    slbd::so3_log(q, v);
+                    x[3 * b] = v[0]; x[3 * b + 1] = v[1]; x[3 * b + 2] = v[2];
+                    o += 4;
+                } else {
+                    x[3 * b] = ld(o); x[3 * b + 1] = ld(o + 1); x[3 * b + 2] = ld(o + 2);
+                    o += 3;
+                }
+            }
+            for (int f = 0; f < l.nfeat; ++f) x[3 * l.nblk + f] = ld(o + f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < STAT_MAXACC; ++k) {
+            const int e = threadIdx.x + k * STAT_TPB;
+            if (e < nent) {
+                double s = 0.0;
+                if (e < N) {
+                    for (int t = 0; t < cnt; ++t) s += xs[t * N + e];
+                } else {
+                    const int r = (e - N) / N, c = (e - N) - r * N;
+                    for (int t = 0; t < cnt; ++t) s += xs[t * N + r] * xs[t * N + c];
+                }
+                acc[k] += s;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < STAT_MAXACC; ++k) {
+        const int e = threadIdx.x + k * STAT_TPB;
+        if (e < nent && acc[k] != 0.0) atomicAdd(out + 1 + e, acc[k]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (double)B);
+}
+
+// FP64 FMA-rate microbenchmark (roofline denominator for the FP64-bound configs; not in
+// MEASURED_PEAKS.json).  16 independent DFMA chains per thread, every SM saturated.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, int iters, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = a + k + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = fma(x[k], b, a);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += x[k];
+    if (s == 12345.678) sink[0] = s;
+}
+
+static cudaStream_t S(void *p) { return (cudaStream_t)p; }
+
+static FilterArgs make_args(slb_handle h) {
+    FilterArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mu = h->mu; a.P = h->P; a.status = h->status; a.outliers = h->outliers;
+    a.B = h->B; a.stride = h->stride; a.pstride = h->pstride; a.qstride = h->qstride;
+    a.nk = h->cfg.nk; a.nl = h->cfg.nl; a.k = h->cfg.nclones;
+    return a;
+}
+
+static int pm_nu(int pm) { return pm == SLB_PM_MSCKF_DELTAPOSE ? 13 : 6; }
+
+}  // namespace slb
+
+using namespace slb;
+
+extern "C" {
+
+int slb_version(void) { return SLB_VERSION; }
+const char *slb_last_error(void) { return g_err; }
+int64_t slb_launch_count(void) { return g_launches.load(); }
+
+int slb_create(const slb_config *cfg, slb_handle *out) {
+    if (!cfg || !out) return set_error(SLB_ERR_INVALID, "slb_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_create: no CUDA device (this engine has no CPU fallback)");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return set_error(SLB_ERR_INVALID, "slb_create: bad device ordinal");
+    if (cfg->batch <= 0) return set_error(SLB_ERR_INVALID, "slb_create: batch must be positive");
+    SLB_CUDA(cudaSetDevice(cfg->device));
+    slb_batch_s *h = new (std::nothrow) slb_batch_s();
+    if (!h) return set_error(SLB_ERR_ALLOC, "slb_create: host allocation failed");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->B = cfg->batch;
+    switch (cfg->kind) {
+        case SLB_KIND_UKF:
+            if (cfg->layout != SLB_LAYOUT_POSE6 && cfg->layout != SLB_LAYOUT_MTK9) {
+                delete h;
+                return set_error(SLB_ERR_INVALID, "slb_create: UKF layout must be POSE6 or MTK9");
+            }
+            h->N = cfg->layout;
+            h->QD = cfg->layout + 1;
+            break;
+        case SLB_KIND_USCKF:
+            if (cfg->nk < 0 || cfg->nl < 0 || cfg->nk % 3 != 0 || cfg->nk + cfg->nl > 28) {
+                delete h;
+                return set_error(SLB_ERR_INVALID, "slb_create: USCKF needs nk % 3 == 0 and nk + nl <= 28");
+            }
+            h->N = 36 + cfg->nk + cfg->nl;
+            h->QD = 39 + cfg->nk + cfg->nl;
+            break;
+        case SLB_KIND_MSCKF:
+            if (cfg->nclones < 0 || cfg->nclones > 10) {
+                delete h;
+                return set_error(SLB_ERR_INVALID, "slb_create: MSCKF supports 0..10 clones");
+            }
+            h->N = 12 + 6 * cfg->nclones;
+            h->QD = 13 + 7 * cfg->nclones;
+            break;
+        default:
+            delete h;
+            return set_error(SLB_ERR_INVALID, "slb_create: unknown kind");
+    }
+    h->NP = h->N * (h->N + 1) / 2;
+    h->stride = (h->B + 31) / 32 * 32;
+    h->pstride = (h->NP + 15) / 16 * 16;
+    h->qstride = (h->QD + 1) / 2 * 2;
+    const bool soa = cfg->kind == SLB_KIND_UKF;
+    const size_t mu_bytes = soa ? (size_t)h->QD * h->stride * 8 : (size_t)h->B * h->qstride * 8;
+    const size_t P_bytes = soa ? (size_t)h->NP * h->stride * 8 : (size_t)h->B * h->pstride * 8;
+    h->stage_bytes = (size_t)64 << 20;
+    const size_t one = (size_t)h->N * h->N * 8;
+    if (h->stage_bytes < one * 32) h->stage_bytes = one * 32;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&h->mu, mu_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->P, P_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->status, (size_t)h->B * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->outliers, (size_t)h->B * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->stage, h->stage_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->shared_small, 64 * 1024);
+    if (e == cudaSuccess) e = cudaMalloc(&h->counts_dev, 4 * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemset(h->mu, 0, mu_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->P, 0, P_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->status, 0, (size_t)h->B * 4);
+    if (e == cudaSuccess) e = cudaMemset(h->outliers, 0, (size_t)h->B * 4);
+    if (e != cudaSuccess) {
+        slb_destroy(h);
+        return set_error(SLB_ERR_ALLOC, "slb_create: device allocation failed", e);
+    }
+    *out = h;
+    return SLB_OK;
+}
+
+int slb_destroy(slb_handle h) {
+    if (!h) return SLB_OK;
+    cudaFree(h->mu); cudaFree(h->P); cudaFree(h->status); cudaFree(h->outliers);
+    cudaFree(h->stage); cudaFree(h->shared_small); cudaFree(h->counts_dev);
+    delete h;
+    return SLB_OK;
+}
+
+int slb_dof(slb_handle h) { return h ? h->N : SLB_ERR_INVALID; }
+int slb_qdim(slb_handle h) { return h ? h->QD : SLB_ERR_INVALID; }
+
+int slb_device_ptr(slb_handle h, int field, void **dev) {
+    if (!h || !dev) return set_error(SLB_ERR_INVALID, "slb_device_ptr: null argument");
+    switch (field) {
+        case SLB_FIELD_MU: *dev = h->mu; return SLB_OK;
+        case SLB_FIELD_P: *dev = h->P; return SLB_OK;
+        case SLB_FIELD_STATUS: *dev = h->status; return SLB_OK;
+        case SLB_FIELD_OUTLIERS: *dev = h->outliers; return SLB_OK;
+    }
+    return set_error(SLB_ERR_INVALID, "slb_device_ptr: unknown field");
+}
+
+static int transfer(slb_handle h, int field, void *host, size_t count, cudaStream_t s, bool up) {
+    if (!h || !host) return set_error(SLB_ERR_INVALID, "slb_upload/download: null argument");
+    const bool soa = h->cfg.kind == SLB_KIND_UKF;
+    if (field == SLB_FIELD_STATUS || field == SLB_FIELD_OUTLIERS) {
+        if (up) return set_error(SLB_ERR_INVALID, "slb_upload: status fields are read-only");
+        if (count != (size_t)h->B) return set_error(SLB_ERR_INVALID, "slb_download: count must equal batch");
+        SLB_CUDA(cudaMemcpyAsync(host, field == SLB_FIELD_STATUS ? h->status : h->outliers, (size_t)h->B * 4,
+                                 cudaMemcpyDeviceToHost, s));
+        SLB_CUDA(cudaStreamSynchronize(s));
+        return SLB_OK;
+    }
+    size_t per;
+    if (field == SLB_FIELD_MU) per = h->QD;
+    else if (field == SLB_FIELD_P) per = (size_t)h->N * h->N;
+    else return set_error(SLB_ERR_INVALID, "slb_upload/download: unknown field");
+    if (count != per * h->B) return set_error(SLB_ERR_INVALID, "slb_upload/download: count must be batch * per-instance size");
+    const int chunk = (int)(h->stage_bytes / (per * 8));
+    double *hp = (double *)host;
+    for (int b0 = 0; b0 < h->B; b0 += chunk) {
+        const int cnt = (h->B - b0) < chunk ? (h->B - b0) : chunk;
+        const size_t bytes = (size_t)cnt * per * 8;
+        const int64_t work = (int64_t)cnt * (field == SLB_FIELD_MU ? h->QD : (up && soa ? h->NP : h->N * h->N));
+        const int tpb = 256;
+        const int grid = (int)((work + tpb - 1) / tpb);
+        if (up) {
+            SLB_CUDA(cudaMemcpyAsync(h->stage, hp + (size_t)b0 * per, bytes, cudaMemcpyHostToDevice, s));
+            if (field == SLB_FIELD_MU) {
+                if (soa) aos_to_soa_mu<<<grid, tpb, 0, s>>>(h->stage, h->mu, b0, cnt, h->QD, h->stride);
+                else aos_to_rec_mu<<<grid, tpb, 0, s>>>(h->stage, h->mu, b0, cnt, h->QD, h->qstride);
+            } else {
+                if (soa) dense_to_soa_P<<<grid, tpb, 0, s>>>(h->stage, h->P, b0, cnt, h->N, h->stride);
+                else dense_to_rec_P<<<grid, tpb, 0, s>>>(h->stage, h->P, b0, cnt, h->N, h->pstride);
+            }
+            count_launch();
+            SLB_CUDA(cudaGetLastError());
+        } else {
+            if (field == SLB_FIELD_MU) {
+                if (soa) soa_to_aos_mu<<<grid, tpb, 0, s>>>(h->mu, h->stage, b0, cnt, h->QD, h->stride);
+                else rec_to_aos_mu<<<grid, tpb, 0, s>>>(h->mu, h->stage, b0, cnt, h->QD, h->qstride);
+            } else {
+                if (soa) soa_to_dense_P<<<grid, tpb, 0, s>>>(h->P, h->stage, b0, cnt, h->N, h->stride);
+                else rec_to_dense_P<<<grid, tpb, 0, s>>>(h->P, h->stage, b0, cnt, h->N, h->pstride);
+            }
+            count_launch();
+            SLB_CUDA(cudaGetLastError());
+            SLB_CUDA(cudaMemcpyAsync(hp + (size_t)b0 * per, h->stage, bytes, cudaMemcpyDeviceToHost, s));
+        }
+        // the staging buffer is reused by the next chunk (and by later calls)
+        SLB_CUDA(cudaStreamSynchronize(s));
+    }
+    return SLB_OK;
+}
+
+int slb_upload(slb_handle h, int field, const void *host, size_t count, void *stream) {
+    return transfer(h, field, const_cast<void *>(host), count, S(stream), true);
+}
+int slb_download(slb_handle h, int field, void *host, size_t count, void *stream) {
+    return transfer(h, field, host, count, S(stream), false);
+}
+
+// ---- ukfom::ukf --------------------------------------------------------------------------------------
+static int ukf_call(slb_handle h, int pm, int mm, bool pred, bool upd, const double *u, double dt, const double *Q,
+                    const double *z, const double *R, int gate, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_UKF) return set_error(SLB_ERR_INVALID, "slb_ukf_*: handle is not a UKF batch");
+    if (pred && (!u || !Q)) return set_error(SLB_ERR_INVALID, "slb_ukf_predict: u and Q are required");
+    if (upd && (!z || !R)) return set_error(SLB_ERR_INVALID, "slb_ukf_update: z and R are required");
+    FilterArgs a = make_args(h);
+    a.u = u; a.dt = dt; a.Q = Q; a.z = z; a.R = R; a.gate = gate; a.m = 3;
+    return launch_ukf(h->cfg.layout, pm, mm, pred, upd, a, S(stream));
+}
+int slb_ukf_predict(slb_handle h, int pm, const double *u, double dt, const double *Q, void *stream) {
+    return ukf_call(h, pm, 0, true, false, u, dt, Q, nullptr, nullptr, 0, stream);
+}
+int slb_ukf_update(slb_handle h, int mm, const double *z, const double *R, int gate_dof, void *stream) {
+    return ukf_call(h, 0, mm, false, true, nullptr, 0.0, nullptr, z, R, gate_dof, stream);
+}
+int slb_ukf_step(slb_handle h, int pm, int mm, const double *u, double dt, const double *Q, const double *z,
+                 const double *R, int gate_dof, void *stream) {
+    return ukf_call(h, pm, mm, true, true, u, dt, Q, z, R, gate_dof, stream);
+}
+
+// Shared host-buffer step: stage u | z | Q | R on the device, run, return the posterior means.
+static int step_host(slb_handle h, int pm, int mm, int nu, int m, int nq, const double *u_host, double dt,
+                     const double *Q_host, const double *z_host, const double *R_host, int gate, double *mu_out,
+                     void *stream, bool usckf) {
+    if (!h || !u_host || !Q_host || !z_host || !R_host) return set_error(SLB_ERR_INVALID, "slb_*_step_host: null argument");
+    cudaStream_t s = S(stream);
+    const size_t ub = (size_t)h->B * nu * 8, zb = (size_t)h->B * m * 8;
+    const size_t mub = (size_t)h->B * h->QD * 8;
+    if (ub + zb + mub > h->stage_bytes) return set_error(SLB_ERR_INVALID, "slb_*_step_host: batch too large for the staging buffer");
+    double *du = h->stage, *dz = h->stage + (size_t)h->B * nu, *dmu = dz + (size_t)h->B * m;
+    double *dQ = h->shared_small, *dR = h->shared_small + nq * nq;
+    SLB_CUDA(cudaMemcpyAsync(du, u_host, ub, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dz, z_host, zb, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dQ, Q_host, (size_t)nq * nq * 8, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dR, R_host, (size_t)m * m * 8, cudaMemcpyHostToDevice, s));
+    int rc = usckf ? slb_usckf_step(h, pm, mm, du, dt, dQ, dz, dR, gate, stream)
+                   : slb_ukf_step(h, pm, mm, du, dt, dQ, dz, dR, gate, stream);
+    if (rc != SLB_OK) return rc;
+    if (mu_out) {
+        const int work = h->B * h->QD, tpb = 256;
+        if (usckf) rec_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, s>>>(h->mu, dmu, 0, h->B, h->QD, h->qstride);
+        else soa_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, s>>>(h->mu, dmu, 0, h->B, h->QD, h->stride);
+        count_launch();
+        SLB_CUDA(cudaGetLastError());
+        SLB_CUDA(cudaMemcpyAsync(mu_out, dmu, mub, cudaMemcpyDeviceToHost, s));
+    }
+    SLB_CUDA(cudaStreamSynchronize(s));
+    return SLB_OK;
+}
+int slb_ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                      const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_UKF) return set_error(SLB_ERR_INVALID, "slb_ukf_step_host: handle is not a UKF batch");
+    return step_host(h, pm, mm, pm_nu(pm), 3, h->N, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, false);
+}
+
+// ---- localization::Usckf -----------------------------------------------------------------------------
+static int usckf_call(slb_handle h, int pm, int mm, bool pred, bool upd, const double *u, double dt, const double *Q,
+                      const double *z, const double *R, int gate, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_*: handle is not a USCKF batch");
+    if (pred && (!u || !Q)) return set_error(SLB_ERR_INVALID, "slb_usckf_predict: u and Q are required");
+    if (upd && (!z || !R)) return set_error(SLB_ERR_INVALID, "slb_usckf_update: z and R are required");
+    FilterArgs a = make_args(h);
+    a.u = u; a.dt = dt; a.Q = Q; a.z = z; a.R = R; a.gate = gate; a.m = h->cfg.nk;
+    return launch_usckf(pm, mm, pred, upd, a, S(stream));
+}
+int slb_usckf_predict(slb_handle h, int pm, const double *u, double dt, const double *Q, void *stream) {
+    return usckf_call(h, pm, 0, true, false, u, dt, Q, nullptr, nullptr, 0, stream);
+}
+int slb_usckf_update(slb_handle h, int mm, const double *z, const double *R, int gate_dof, void *stream) {
+    return usckf_call(h, 0, mm, false, true, nullptr, 0.0, nullptr, z, R, gate_dof, stream);
+}
+int slb_usckf_step(slb_handle h, int pm, int mm, const double *u, double dt, const double *Q, const double *z,
+                   const double *R, int gate_dof, void *stream) {
+    return usckf_call(h, pm, mm, true, true, u, dt, Q, z, R, gate_dof, stream);
+}
+int slb_usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                        const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_step_host: handle is not a USCKF batch");
+    return step_host(h, pm, mm, pm_nu(pm), h->cfg.nk, 12, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, true);
+}
+int slb_usckf_clone(slb_handle h, int mode, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_clone: handle is not a USCKF batch");
+    FilterArgs a = make_args(h);
+    return launch_usckf_clone(mode, a, S(stream));
+}
+int slb_usckf_set_measurement(slb_handle h, int mode, const double *z, const double *R, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_set_measurement: handle is not a USCKF batch");
+    if (!z || !R) return set_error(SLB_ERR_INVALID, "slb_usckf_set_measurement: z and R are required");
+    FilterArgs a = make_args(h);
+    a.z = z; a.R = R;
+    return launch_usckf_set_measurement(mode, a, S(stream));
+}
+
+// ---- localization::Msckf -----------------------------------------------------------------------------
+int slb_msckf_predict(slb_handle h, int pm, const double *u, double dt, const double *Q, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_predict: handle is not an MSCKF batch");
+    if (!u || !Q) return set_error(SLB_ERR_INVALID, "slb_msckf_predict: u and Q are required");
+    FilterArgs a = make_args(h);
+    a.u = u; a.dt = dt; a.Q = Q;
+    return launch_msckf_predict(pm, a, S(stream));
+}
+int slb_msckf_update(slb_handle h, int mm, const double *params, int m, const double *z, const double *R, int gate,
+                     void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_update: handle is not an MSCKF batch");
+    if (!params || !z || !R || m <= 0 || (m & 1)) return set_error(SLB_ERR_INVALID, "slb_msckf_update: bad arguments");
+    FilterArgs a = make_args(h);
+    a.params = params; a.m = m; a.z = z; a.R = R; a.gate = gate;
+    return launch_msckf_update(mm, a, S(stream));
+}
+
+// ---- localization::DataModel -------------------------------------------------------------------------
+int slb_datamodel_fuse(int d, int64_t n, const double *x1, const double *C1, const double *x2, const double *C2,
+                       double *xo, double *Co, void *stream) {
+    if (!x1 || !C1 || !x2 || !C2 || !xo || !Co || n < 0) return set_error(SLB_ERR_INVALID, "slb_datamodel_fuse: bad arguments");
+    return launch_fusion(d, n, 0, x1, C1, x2, C2, xo, Co, S(stream));
+}
+int slb_datamodel_addsub(int d, int64_t n, int sign, const double *x1, const double *C1, const double *x2,
+                         const double *C2, double *xo, double *Co, void *stream) {
+    if (!x1 || !C1 || !x2 || !C2 || !xo || !Co || n < 0 || sign == 0) return set_error(SLB_ERR_INVALID, "slb_datamodel_addsub: bad arguments");
+    return launch_fusion(d, n, sign > 0 ? 1 : -1, x1, C1, x2, C2, xo, Co, S(stream));
+}
+int slb_datamodel_fuse_host(int d, int64_t n, const double *x1, const double *C1, const double *x2, const double *C2,
+                            double *xo, double *Co) {
+    if (!x1 || !C1 || !x2 || !C2 || !xo || !Co || n < 0) return set_error(SLB_ERR_INVALID, "slb_datamodel_fuse_host: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_datamodel_fuse_host: no CUDA device (no CPU fallback)");
+    }
+    if (n == 0) return SLB_OK;
+    const size_t xb = (size_t)n * d * 8, cb = (size_t)n * d * d * 8;
+    double *buf = nullptr;
+    SLB_CUDA(cudaMalloc(&buf, 2 * xb + 2 * cb));
+    double *dx1 = buf, *dx2 = dx1 + (size_t)n * d, *dC1 = dx2 + (size_t)n * d, *dC2 = dC1 + (size_t)n * d * d;
+    cudaError_t e = cudaMemcpyAsync(dx1, x1, xb, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx2, x2, xb, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dC1, C1, cb, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dC2, C2, cb, cudaMemcpyHostToDevice, 0);
+    int rc = SLB_OK;
+    if (e == cudaSuccess) rc = launch_fusion(d, n, 0, dx1, dC1, dx2, dC2, dx1, dC1, 0);
+    if (e == cudaSuccess && rc == SLB_OK) e = cudaMemcpyAsync(xo, dx1, xb, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess && rc == SLB_OK) e = cudaMemcpyAsync(Co, dC1, cb, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    cudaFree(buf);
+    if (e != cudaSuccess) return set_error(SLB_ERR_CUDA, "slb_datamodel_fuse_host", e);
+    return rc;
+}
+
+// ---- diagnostics -------------------------------------------------------------------------------------
+int slb_status(slb_handle h, int64_t counts[4], void *stream) {
+    if (!h || !counts) return set_error(SLB_ERR_INVALID, "slb_status: null argument");
+    cudaStream_t s = S(stream);
+    SLB_CUDA(cudaMemsetAsync(h->counts_dev, 0, 4 * sizeof(int64_t), s));
+    int grid = (h->B + 255) / 256;
+    if (grid > 1184) grid = 1184;
+    status_count<<<grid, 256, 0, s>>>(h->status, h->B, (unsigned long long *)h->counts_dev);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    SLB_CUDA(cudaMemcpyAsync(counts, h->counts_dev, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SLB_CUDA(cudaStreamSynchronize(s));
+    return SLB_OK;
+}
+int slb_clear_status(slb_handle h, void *stream) {
+    if (!h) return set_error(SLB_ERR_INVALID, "slb_clear_status: null argument");
+    SLB_CUDA(cudaMemsetAsync(h->status, 0, (size_t)h->B * 4, S(stream)));
+    SLB_CUDA(cudaMemsetAsync(h->outliers, 0, (size_t)h->B * 4, S(stream)));
+    return SLB_OK;
+}
+int slb_bench_fp64_peak(double *tflops_out) {
+    if (!tflops_out) return set_error(SLB_ERR_INVALID, "slb_bench_fp64_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_bench_fp64_peak: no CUDA device");
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *sink = nullptr;
+    SLB_CUDA(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, grid = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, 0);
+        fp64_peak_kernel<<<grid, 256, 0, 0>>>(sink, iters, 1.0000001, 0.9999999);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 16 * (double)iters * 256 * grid;
+        const double tf = fl / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    count_launch(5);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    SLB_CUDA(cudaGetLastError());
+    *tflops_out = best;
+    return SLB_OK;
+}
+
+int slb_ensemble_stats(slb_handle h, double *out_dev, void *stream) {
+    if (!h || !out_dev) return set_error(SLB_ERR_INVALID, "slb_ensemble_stats: null argument");
+    cudaStream_t s = S(stream);
+    StatLayout l;
+    memset(&l, 0, sizeof(l));
+    l.N = h->N; l.QD = h->QD; l.stride = h->stride; l.qstride = h->qstride;
+    l.soa = h->cfg.kind == SLB_KIND_UKF;
+    auto add_state12 = [&](int at) { l.so3mask |= 1ull << (at + 1); };
+    if (h->cfg.kind == SLB_KIND_UKF) {
+        l.nblk = h->N / 3; l.so3mask = 0x2; l.nfeat = 0;
+    } else if (h->cfg.kind == SLB_KIND_USCKF) {
+        l.nblk = 12; l.nfeat = h->cfg.nk + h->cfg.nl;
+        add_state12(0); add_state12(4); add_state12(8);
+    } else {
+        l.nblk = 4 + 2 * h->cfg.nclones; l.nfeat = 0;
+        add_state12(0);
+        for (int j = 0; j < h->cfg.nclones; ++j) l.so3mask |= 1ull << (4 + 2 * j + 1);
+    }
+    if (l.N * l.N + l.N > STAT_TPB * STAT_MAXACC) return set_error(SLB_ERR_INVALID, "slb_ensemble_stats: state too large");
+    SLB_CUDA(cudaMemsetAsync(out_dev, 0, (size_t)(1 + l.N + l.N * l.N) * 8, s));
+    const int nchunks = (h->B + STAT_CHUNK - 1) / STAT_CHUNK;
+    const int grid = nchunks < 296 ? nchunks : 296;
+    ensemble_stats_kernel<<<grid, STAT_TPB, (size_t)STAT_CHUNK * l.N * 8, s>>>(h->mu, h->B, l, out_dev);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// slb_internal.h -- shared declarations between the translation units of libslb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slb.h"
+
+struct slb_batch_s {
+    slb_config cfg;
+    int N;        // tangent dimension of the full filter state
+    int QD;       // q-vector length
+    int NP;       // packed lower-triangle length N(N+1)/2
+    int B;        // instances
+    int stride;   // UKF: SoA stride (B rounded up to 32); USCKF/MSCKF: unused
+    int pstride;  // USCKF/MSCKF: doubles per instance record of P (NP rounded up to 16 -> 128 B)
+    int qstride;  // USCKF/MSCKF: doubles per instance record of mu (QD rounded up to 2 -> 16 B)
+    double *mu;   // UKF: [QD][stride] SoA.  USCKF/MSCKF: [B][qstride]
+    double *P;    // UKF: [NP][stride] SoA packed lower.  USCKF/MSCKF: [B][pstride] packed lower
+    int32_t *status;
+    int32_t *outliers;
+    // staging for the *_host entry points and upload/download
+    double *stage;        // device scratch, stage_bytes long
+    size_t stage_bytes;
+    double *shared_small; // device copy of Q / R / params passed from host pointers
+    int64_t *counts_dev;  // 4 counters for slb_status
+};
+
+namespace slb {
+
+int set_error(int code, const char *what, cudaError_t ce = cudaSuccess);
+void count_launch(int n = 1);
+
+#define SLB_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return slb::set_error(SLB_ERR_CUDA, #call, e_); \
+    } while (0)
+
+struct FilterArgs {
+    double *mu;
+    double *P;
+    int32_t *status;
+    int32_t *outliers;
+    int B;
+    int stride, pstride, qstride;
+    const double *u;
+    double dt;
+    const double *Q;
+    const double *z;
+    const double *R;
+    const double *params;
+    int m;
+    int gate;
+    int nk, nl, k;
+};
+
+// slb_ukf.cu
+int launch_ukf(int layout, int pm, int mm, bool predict, bool update, const FilterArgs &a, cudaStream_t s);
+// slb_usckf.cu
+int launch_usckf(int pm, int mm, bool predict, bool update, const FilterArgs &a, cudaStream_t s);
+int launch_usckf_clone(int mode, const FilterArgs &a, cudaStream_t s);
+int launch_usckf_set_measurement(int mode, const FilterArgs &a, cudaStream_t s);
+// slb_msckf.cu
+int launch_msckf_predict(int pm, const FilterArgs &a, cudaStream_t s);
+int launch_msckf_update(int mm, const FilterArgs &a, cudaStream_t s);
+// slb_fusion.cu
+int launch_fusion(int d, int64_t n, int op, const double *x1, const double *C1, const double *x2,
+                  const double *C2, double *xo, double *Co, cudaStream_t s);
+
+}  // namespace slb

@@ -1,0 +1,313 @@
+"""ctypes binding of csrc/libslb.so -- the C ABI of include/slb.h -- plus thin host-side classes that
+mirror the reference's filter surface (Usckf / Msckf / ukfom::ukf / DataModel) for batches.
+
+torch is used for device memory and streams only.  There is NO CPU fallback: importing works
+anywhere (so the symbol table can be checked), but every compute call needs the CUDA library and
+a CUDA device and fails loudly otherwise."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libslb.so")
+
+# ---- ids of include/slb.h ------------------------------------------------------------------------
+KIND_UKF, KIND_USCKF, KIND_MSCKF = 1, 2, 3
+LAYOUT_POSE6, LAYOUT_MTK9, LAYOUT_STATE12 = 6, 9, 12
+PM_UKFOM_IMU, PM_UKFOM_IMU_REFBUG, PM_POSE6_ODOM, PM_USCKF_TEST, PM_MSCKF_DELTAPOSE = 1, 2, 3, 4, 5
+MM_GPS_POS, MM_USCKF_VO, MM_MSCKF_REPROJ = 101, 102, 103
+STATEK, STATEK_L, STATEK_I = 1, 2, 3
+FIELD_MU, FIELD_P, FIELD_STATUS, FIELD_OUTLIERS = 1, 2, 3, 4
+ST_CHOL_FAIL, ST_MEAN_NOCONV, ST_GATE_REJECT, ST_NONFINITE = 1, 2, 4, 8
+
+EXPORTS = [
+    "slb_version", "slb_last_error", "slb_create", "slb_destroy", "slb_dof", "slb_qdim", "slb_upload",
+    "slb_download", "slb_device_ptr", "slb_ukf_predict", "slb_ukf_update", "slb_ukf_step", "slb_ukf_step_host",
+    "slb_usckf_predict", "slb_usckf_update", "slb_usckf_step", "slb_usckf_step_host", "slb_usckf_clone",
+    "slb_usckf_set_measurement", "slb_msckf_predict", "slb_msckf_update", "slb_datamodel_fuse",
+    "slb_datamodel_addsub", "slb_datamodel_fuse_host", "slb_status", "slb_clear_status", "slb_ensemble_stats",
+    "slb_launch_count", "slb_bench_fp64_peak",
+]
+
+
+class SlbConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("layout", C.c_int32), ("batch", C.c_int32), ("nk", C.c_int32),
+                ("nl", C.c_int32), ("nclones", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 9)]
+
+
+class SlbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libslb.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SlbError("CUDA library %s is missing: run __graft_entry__.build() (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, dp, i32, i64, dbl = C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.slb_last_error.restype = C.c_char_p
+        L.slb_launch_count.restype = C.c_int64
+        L.slb_create.argtypes = [C.POINTER(SlbConfig), C.POINTER(vp)]
+        L.slb_destroy.argtypes = [vp]
+        L.slb_dof.argtypes = [vp]
+        L.slb_qdim.argtypes = [vp]
+        L.slb_upload.argtypes = [vp, i32, vp, C.c_size_t, vp]
+        L.slb_download.argtypes = [vp, i32, vp, C.c_size_t, vp]
+        L.slb_device_ptr.argtypes = [vp, i32, C.POINTER(vp)]
+        L.slb_ukf_predict.argtypes = [vp, i32, dp, dbl, dp, vp]
+        L.slb_ukf_update.argtypes = [vp, i32, dp, dp, i32, vp]
+        L.slb_ukf_step.argtypes = [vp, i32, i32, dp, dbl, dp, dp, dp, i32, vp]
+        L.slb_ukf_step_host.argtypes = [vp, i32, i32, dp, dbl, dp, dp, dp, i32, dp, vp]
+        L.slb_usckf_predict.argtypes = [vp, i32, dp, dbl, dp, vp]
+        L.slb_usckf_update.argtypes = [vp, i32, dp, dp, i32, vp]
+        L.slb_usckf_step.argtypes = [vp, i32, i32, dp, dbl, dp, dp, dp, i32, vp]
+        L.slb_usckf_step_host.argtypes = [vp, i32, i32, dp, dbl, dp, dp, dp, i32, dp, vp]
+        L.slb_usckf_clone.argtypes = [vp, i32, vp]
+        L.slb_usckf_set_measurement.argtypes = [vp, i32, dp, dp, vp]
+        L.slb_msckf_predict.argtypes = [vp, i32, dp, dbl, dp, vp]
+        L.slb_msckf_update.argtypes = [vp, i32, dp, i32, dp, dp, i32, vp]
+        L.slb_datamodel_fuse.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp, vp]
+        L.slb_datamodel_addsub.argtypes = [i32, i64, i32, dp, dp, dp, dp, dp, dp, vp]
+        L.slb_datamodel_fuse_host.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp]
+        L.slb_status.argtypes = [vp, C.POINTER(C.c_int64), vp]
+        L.slb_clear_status.argtypes = [vp, vp]
+        L.slb_ensemble_stats.argtypes = [vp, dp, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SlbError("slb error %d: %s" % (rc, lib().slb_last_error().decode()))
+
+
+def fp64_peak_tflops():
+    _torch()
+    v = C.c_double(0.0)
+    check(lib().slb_bench_fp64_peak(C.byref(v)))
+    return v.value
+
+
+def launch_count():
+    return int(lib().slb_launch_count())
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise SlbError("no CUDA device: the engine has no CPU fallback")
+    return torch
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _hp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _h(a, dtype=np.float64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class DeviceArray:
+    """A float64 torch tensor on the current device, passed to the C ABI as a raw pointer."""
+
+    def __init__(self, host=None, shape=None):
+        torch = _torch()
+        if host is not None:
+            self.t = torch.from_numpy(_h(host)).cuda()
+        else:
+            self.t = torch.empty(shape, dtype=torch.float64, device="cuda")
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.t.data_ptr())
+
+    def numpy(self):
+        return self.t.cpu().numpy()
+
+
+def dev(a):
+    return a if isinstance(a, DeviceArray) else DeviceArray(a)
+
+
+class Batch:
+    """A device-resident batch of filter instances (slb_handle)."""
+
+    def __init__(self, kind, batch, layout=0, nk=0, nl=0, nclones=0, device=None):
+        torch = _torch()
+        cfg = SlbConfig()
+        cfg.kind, cfg.layout, cfg.batch, cfg.nk, cfg.nl, cfg.nclones = kind, layout, batch, nk, nl, nclones
+        cfg.device = torch.cuda.current_device() if device is None else device
+        self.h = C.c_void_p()
+        check(lib().slb_create(C.byref(cfg), C.byref(self.h)))
+        self.B = batch
+        self.N = lib().slb_dof(self.h)
+        self.QD = lib().slb_qdim(self.h)
+        self.kind, self.nk, self.nl, self.k = kind, nk, nl, nclones
+
+    def close(self):
+        if self.h:
+            lib().slb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # state access: muState() / Pk (Usckf.hpp:518-526, Msckf.hpp:376-395)
+    def set_state(self, mu, P):
+        mu, P = _h(mu), _h(P)
+        assert mu.shape == (self.B, self.QD) and P.shape == (self.B, self.N, self.N), (mu.shape, P.shape)
+        check(lib().slb_upload(self.h, FIELD_MU, _hp(mu), mu.size, _stream()))
+        check(lib().slb_upload(self.h, FIELD_P, _hp(P), P.size, _stream()))
+
+    def mu(self):
+        out = np.empty((self.B, self.QD))
+        check(lib().slb_download(self.h, FIELD_MU, _hp(out), out.size, _stream()))
+        return out
+
+    def P(self):
+        out = np.empty((self.B, self.N, self.N))
+        check(lib().slb_download(self.h, FIELD_P, _hp(out), out.size, _stream()))
+        return out
+
+    def status(self):
+        out = np.empty(self.B, np.int32)
+        check(lib().slb_download(self.h, FIELD_STATUS, _hp(out), out.size, _stream()))
+        return out
+
+    def outliers(self):
+        out = np.empty(self.B, np.int32)
+        check(lib().slb_download(self.h, FIELD_OUTLIERS, _hp(out), out.size, _stream()))
+        return out
+
+    def status_counts(self):
+        c = (C.c_int64 * 4)()
+        check(lib().slb_status(self.h, c, _stream()))
+        return list(c)
+
+    def clear_status(self):
+        check(lib().slb_clear_status(self.h, _stream()))
+
+    def ensemble_stats(self, out=None):
+        out = out if out is not None else DeviceArray(shape=(1 + self.N + self.N * self.N,))
+        check(lib().slb_ensemble_stats(self.h, out.ptr, _stream()))
+        return out
+
+
+class Ukf(Batch):
+    """Batch of ukfom::ukf<state> (test/UKFoMUnitTest.cpp:104-117): predict(g,Q), update(z,h,R)."""
+
+    def __init__(self, batch, layout=LAYOUT_MTK9, device=None):
+        super().__init__(KIND_UKF, batch, layout=layout, device=device)
+
+    def predict(self, pm, u, dt, Q):
+        u, Q = dev(u), dev(Q)
+        check(lib().slb_ukf_predict(self.h, pm, u.ptr, dt, Q.ptr, _stream()))
+
+    def update(self, mm, z, R, gate_dof=0):
+        z, R = dev(z), dev(R)
+        check(lib().slb_ukf_update(self.h, mm, z.ptr, R.ptr, gate_dof, _stream()))
+
+    def step(self, pm, mm, u, dt, Q, z, R, gate_dof=0):
+        u, Q, z, R = dev(u), dev(Q), dev(z), dev(R)
+        check(lib().slb_ukf_step(self.h, pm, mm, u.ptr, dt, Q.ptr, z.ptr, R.ptr, gate_dof, _stream()))
+
+    def step_host(self, pm, mm, u, dt, Q, z, R, gate_dof=0, mu_out=None):
+        """u, z, Q, R are HOST arrays (numpy or pinned torch); returns/fills the posterior means."""
+        check(lib().slb_ukf_step_host(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(z), _ptr_of(R), gate_dof,
+                                      _ptr_of(mu_out) if mu_out is not None else None, _stream()))
+
+
+class Usckf(Batch):
+    """Batch of localization::Usckf<AugmentedState,State> (Usckf.hpp)."""
+
+    def __init__(self, batch, nk=3, nl=9, device=None):
+        super().__init__(KIND_USCKF, batch, nk=nk, nl=nl, device=device)
+
+    def predict(self, pm, u, dt, Q):
+        u, Q = dev(u), dev(Q)
+        check(lib().slb_usckf_predict(self.h, pm, u.ptr, dt, Q.ptr, _stream()))
+
+    def update(self, mm, z, R, gate_dof=0):
+        z, R = dev(z), dev(R)
+        check(lib().slb_usckf_update(self.h, mm, z.ptr, R.ptr, gate_dof, _stream()))
+
+    def step(self, pm, mm, u, dt, Q, z, R, gate_dof=0):
+        u, Q, z, R = dev(u), dev(Q), dev(z), dev(R)
+        check(lib().slb_usckf_step(self.h, pm, mm, u.ptr, dt, Q.ptr, z.ptr, R.ptr, gate_dof, _stream()))
+
+    def step_host(self, pm, mm, u, dt, Q, z, R, gate_dof=0, mu_out=None):
+        check(lib().slb_usckf_step_host(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(z), _ptr_of(R), gate_dof,
+                                        _ptr_of(mu_out) if mu_out is not None else None, _stream()))
+
+    def cloning(self, mode):
+        check(lib().slb_usckf_clone(self.h, mode, _stream()))
+
+    def set_measurement(self, mode, z, R):
+        z, R = dev(z), dev(R)
+        check(lib().slb_usckf_set_measurement(self.h, mode, z.ptr, R.ptr, _stream()))
+
+
+class Msckf(Batch):
+    """Batch of localization::Msckf<MultiState,State> (Msckf.hpp), UKF-flavoured update."""
+
+    def __init__(self, batch, nclones=10, device=None):
+        super().__init__(KIND_MSCKF, batch, nclones=nclones, device=device)
+
+    def predict(self, pm, u, dt, Q):
+        u, Q = dev(u), dev(Q)
+        check(lib().slb_msckf_predict(self.h, pm, u.ptr, dt, Q.ptr, _stream()))
+
+    def update(self, mm, params, z, R, gate=True):
+        params, z, R = dev(params), dev(z), dev(R)
+        m = z.t.shape[1]
+        check(lib().slb_msckf_update(self.h, mm, params.ptr, m, z.ptr, R.ptr, int(gate), _stream()))
+
+
+def _ptr_of(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return _hp(a)
+    return C.c_void_p(a.data_ptr())  # torch tensor (pinned host or device)
+
+
+class DataModel:
+    """localization::DataModel<double,D> over n independent estimates (DataModel.hpp)."""
+
+    @staticmethod
+    def fuse(x1, C1, x2, C2, out=None):
+        x1, C1, x2, C2 = dev(x1), dev(C1), dev(x2), dev(C2)
+        n, d = x1.t.shape
+        xo, Co = out if out is not None else (DeviceArray(shape=(n, d)), DeviceArray(shape=(n, d, d)))
+        check(lib().slb_datamodel_fuse(d, n, x1.ptr, C1.ptr, x2.ptr, C2.ptr, xo.ptr, Co.ptr, _stream()))
+        return xo, Co
+
+    @staticmethod
+    def addsub(sign, x1, C1, x2, C2):
+        x1, C1, x2, C2 = dev(x1), dev(C1), dev(x2), dev(C2)
+        n, d = x1.t.shape
+        xo, Co = DeviceArray(shape=(n, d)), DeviceArray(shape=(n, d, d))
+        check(lib().slb_datamodel_addsub(d, n, sign, x1.ptr, C1.ptr, x2.ptr, C2.ptr, xo.ptr, Co.ptr, _stream()))
+        return xo, Co
+
+    @staticmethod
+    def fuse_host(x1, C1, x2, C2):
+        x1, C1, x2, C2 = _h(x1), _h(C1), _h(x2), _h(C2)
+        n, d = x1.shape
+        xo, Co = np.empty_like(x1), np.empty_like(C1)
+        check(lib().slb_datamodel_fuse_host(d, n, _hp(x1), _hp(C1), _hp(x2), _hp(C2), _hp(xo), _hp(Co)))
+        return xo, Co

@@ -1,0 +1,152 @@
+"""GPU parity: batched ukfom::ukf (config 2 of BASELINE.json) through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import parity
+from slam_localization_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gpu(sc, layout, pm, fused, B):
+    f = engine.Ukf(B, layout=layout)
+    f.set_state(sc["mu"], sc["P"])
+    if fused:
+        f.step(pm, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"])
+        return f, None
+    f.predict(pm, sc["u"], sc["dt"], sc["Q"])
+    mid = (f.mu(), f.P())
+    f.update(engine.MM_GPS_POS, sc["z"], sc["R"])
+    return f, mid
+
+
+@pytest.mark.parametrize("layout,pm", [(9, engine.PM_UKFOM_IMU), (9, engine.PM_UKFOM_IMU_REFBUG), (6, engine.PM_POSE6_ODOM)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_ukf_step_parity(slo, layout, pm, fused):
+    B = 1000                                   # ragged: not a multiple of the CTA size
+    sc = synth.ukfom_scenario(B, seed=31, layout=layout)
+    blocks = synth.LAYOUT_BLOCKS[layout]
+    f, mid = _run_gpu(sc, layout, pm, fused, B)
+    mu1, P1, st1, _ = slo.ukf_step(layout, pm, slo.MM_GPS_POS, sc["mu"], sc["P"], sc["u"], sc["dt"], sc["Q"], None,
+                                   None, update=False)
+    if mid is not None:
+        parity.assert_parity(slo, blocks, mid[0], mid[1], mu1, P1)
+    mu2, P2, st2, _ = slo.ukf_step(layout, pm, slo.MM_GPS_POS, mu1, P1, None, 0.0, None, sc["z"], sc["R"], predict=False)
+    em, ec = parity.assert_parity(slo, blocks, f.mu(), f.P(), mu2, P2)
+    assert not f.status().any() and not st2.any()
+    P = f.P()
+    assert np.array_equal(P, P.transpose(0, 2, 1))
+    assert np.linalg.eigvalsh(P).min() > 0
+
+
+def test_ukf_reference_fixture(slo):
+    """The reference's own UKFOM test inputs (test/UKFoMUnitTest.cpp:95-114), batch of one."""
+    fx = synth.ukfom_fixture()
+    f = engine.Ukf(1)
+    f.set_state(fx["mu"], fx["P"])
+    f.predict(engine.PM_UKFOM_IMU_REFBUG, fx["u"], fx["dt"], fx["Q"])
+    f.update(engine.MM_GPS_POS, fx["z"], fx["R"])
+    mu, P, st, _ = slo.ukf_step(9, slo.PM_UKFOM_IMU_REFBUG, slo.MM_GPS_POS, fx["mu"], fx["P"], fx["u"], fx["dt"], fx["Q"],
+                                fx["z"], fx["R"])
+    parity.assert_parity(slo, [0, 1, 0], f.mu(), f.P(), mu, P)
+
+
+def test_ukf_golden_fixture(slo):
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "ukf_mtk9.npz"))
+    B = g["mu0"].shape[0]
+    f = engine.Ukf(B)
+    f.set_state(g["mu0"], g["P0"])
+    f.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, g["u"], float(g["dt"]), g["Q"], g["z"], g["R"])
+    parity.assert_parity(slo, [0, 1, 0], f.mu(), f.P(), g["mu1"], g["P1"])
+
+
+def test_ukf_gate_and_failure_flags(slo):
+    B = 64
+    sc = synth.ukfom_scenario(B, seed=32)
+    sc["z"][:8] += 50.0                         # far outside the 3-dof 5% gate
+    P = sc["P"].copy()
+    P[8, 4, 4] = -1.0                           # indefinite: LLT must flag, instance left untouched
+    f = engine.Ukf(B)
+    f.set_state(sc["mu"], P)
+    f.update(engine.MM_GPS_POS, sc["z"], sc["R"], gate_dof=3)
+    st = f.status()
+    assert np.all(st[:8] & engine.ST_GATE_REJECT)
+    assert st[8] & engine.ST_CHOL_FAIL
+    mu, Pg = f.mu(), f.P()
+    np.testing.assert_array_equal(mu[:9], sc["mu"][:9])                      # rejected: state untouched
+    np.testing.assert_array_equal(np.tril(Pg[:9]), np.tril(P[:9]))
+    mu_r, P_r, st_r, _ = slo.ukf_step(9, slo.PM_UKFOM_IMU, slo.MM_GPS_POS, sc["mu"], P, None, 0.0, None, sc["z"], sc["R"],
+                                      gate_dof=3, predict=False)
+    ok = st_r == 0
+    assert ok.sum() >= B - 9 - 4
+    np.testing.assert_array_equal(st[ok], 0)
+    parity.assert_parity(slo, [0, 1, 0], mu, Pg, mu_r, P_r, mask=ok)
+    assert f.status_counts()[0] == 1 and f.status_counts()[2] >= 8
+    f.clear_status()
+    assert not f.status().any()
+
+
+def test_ukf_free_running_1000_steps(slo):
+    """Drift of the GPU filter against the oracle over a free-running sequence (scaled-down version of
+    the 10k-step criterion: <= 1e-6 after the run)."""
+    B, steps = 64, 1000
+    sc = synth.ukfom_scenario(B, seed=33, p_scale=1e-4)
+    f = engine.Ukf(B)
+    f.set_state(sc["mu"], sc["P"])
+    mu, P = sc["mu"], sc["P"]
+    for k in range(steps):
+        u, z = synth.ukfom_inputs(B, k, seed=33, truth_pos=mu[:, :3])
+        f.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, u, sc["dt"], sc["Q"], z, sc["R"])
+        mu, P, st, _ = slo.ukf_step(9, slo.PM_UKFOM_IMU, slo.MM_GPS_POS, mu, P, u, sc["dt"], sc["Q"], z, sc["R"], nthreads=8)
+        assert not st.any()
+    parity.assert_parity(slo, [0, 1, 0], f.mu(), f.P(), mu, P, tol=parity.LONG_TOL)
+    assert not f.status().any()
+
+
+def test_ukf_large_batch_properties():
+    """BASELINE size (65,536 instances): size-independent properties instead of the oracle --
+    identity process model returns P + Q (checkSigmaPoints, Usckf.hpp:769-789), covariance stays
+    symmetric PSD, and instance i of a big batch equals instance i run alone (no cross-talk)."""
+    B = 65536
+    sc = synth.ukfom_scenario(B, seed=34, p_scale=1e-4)
+    f = engine.Ukf(B)
+    f.set_state(sc["mu"], sc["P"])
+    f.predict(engine.PM_UKFOM_IMU, np.zeros((B, 6)), 0.0, sc["Q"])
+    P = f.P()
+    assert np.max(np.abs(P - (sc["P"] + sc["Q"]))) / np.max(np.abs(sc["P"])) < 1e-9
+    f.set_state(sc["mu"], sc["P"])
+    f.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"])
+    mu_big, P_big = f.mu(), f.P()
+    assert not f.status().any()
+    assert np.linalg.eigvalsh(P_big[::97]).min() > 0
+    idx = np.array([0, 1, 31, 32, 127, 128, 4095, 65535])
+    g = engine.Ukf(len(idx))
+    g.set_state(sc["mu"][idx], sc["P"][idx])
+    g.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"][idx], sc["dt"], sc["Q"], sc["z"][idx], sc["R"])
+    np.testing.assert_array_equal(g.mu(), mu_big[idx])
+    np.testing.assert_array_equal(g.P(), P_big[idx])
+
+
+def test_ukf_step_host_matches_device_path():
+    B = 512
+    sc = synth.ukfom_scenario(B, seed=35)
+    a, b = engine.Ukf(B), engine.Ukf(B)
+    a.set_state(sc["mu"], sc["P"])
+    b.set_state(sc["mu"], sc["P"])
+    a.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"])
+    out = np.empty((B, 10))
+    b.step_host(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"], mu_out=out)
+    np.testing.assert_array_equal(out, a.mu())
+    np.testing.assert_array_equal(b.P(), a.P())
+
+
+def test_ensemble_stats_matches_host(slo):
+    B = 3000
+    sc = synth.ukfom_scenario(B, seed=36)
+    f = engine.Ukf(B)
+    f.set_state(sc["mu"], sc["P"])
+    out = f.ensemble_stats().numpy()
+    X = np.array([slo.get_vectorized([0, 1, 0], m) for m in sc["mu"]])
+    assert out[0] == B
+    np.testing.assert_allclose(out[1:10], X.sum(0), rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(out[10:].reshape(9, 9), X.T @ X, rtol=1e-10, atol=1e-9)
