@@ -1,7 +1,633 @@
-// placeholder until the USCKF kernels land
+// slb_usckf.cu -- localization::Usckf<AugmentedState,State>: predict, update, cloning,
+// setMeasurement (src/filters/Usckf.hpp), one filter instance per WARP.
+//
+// Instance record in HBM: mu[qstride] (statek 13 | statek_l 13 | statek_i 13 | featuresk | featuresk_l)
+// and the lower triangle of Pk packed row-major, P[T(i)+j], T(i) = i(i+1)/2, padded to 128 B.
+// A record is contiguous, so a warp streams it with one TMA bulk copy (cp.async.bulk -> UBLKCP).
+//
+// predict (Usckf.hpp:113-244) touches only statek_i: rows 24..35 of the packed triangle (one
+//   contiguous 366-double span) and the 12-wide segments of the feature rows.  Lane s evaluates sigma
+//   point s (25 of 32 lanes); Fk = Pxy^T Pii^-1 is obtained as W^T L^-1 with W = 0.5 (dY+ - dY-) by a
+//   triangular solve, because X_i [-] mu_old is +-L e_j by construction (same algebra as :152-154,
+//   without the explicit inverse).
+// update (Usckf.hpp:260-308): the 48x48 Cholesky runs left-looking with every lane owning rows
+//   (lane) and (lane+32) of the factor in REGISTERS; finished rows are published through shared
+//   memory and re-read as broadcasts, so the inner loop is 1 LDS per 2 DFMA.  Sigma points are
+//   evaluated lane-per-point for the columns that can move h (j < 36+nk); the rest equal Z0.
+//   P -= K S K^T is applied straight to the HBM record (re-read through L2), coalesced.
 #include "slb_internal.h"
-namespace slb {
-int launch_usckf(int, int, bool, bool, const FilterArgs &, cudaStream_t) { return set_error(SLB_ERR_INVALID, "usckf kernels not built"); }
-int launch_usckf_clone(int, const FilterArgs &, cudaStream_t) { return set_error(SLB_ERR_INVALID, "usckf kernels not built"); }
-int launch_usckf_set_measurement(int, const FilterArgs &, cudaStream_t) { return set_error(SLB_ERR_INVALID, "usckf kernels not built"); }
+#include "slb_models.cuh"
+
+namespace slbd {
+
+constexpr unsigned FULL = 0xffffffffu;
+SLB_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
 }
+SLB_DEV double bcast(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+// ---- TMA bulk copy helpers (global -> shared, completion on an mbarrier) ---------------------------
+SLB_DEV unsigned saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+SLB_DEV void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(saddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+SLB_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+SLB_DEV void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(saddr(dst)),
+                 "l"(src), "r"(bytes), "r"(saddr(bar))
+                 : "memory");
+}
+SLB_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(saddr(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// =====================================================================================================
+// predict
+// =====================================================================================================
+constexpr int PRED_PR = 366;           // packed rows 24..35: T(36) - T(24)
+constexpr int PRED_PF = 28 * 12;       // feature-row segments, nk + nl <= 28
+constexpr int PRED_SM = PRED_PR + PRED_PF + 78 + 25 * 13 + 144 + 144 + 1;  // doubles per warp (odd)
+
+template <int PM, int WPB>
+__global__ void __launch_bounds__(WPB * 32) usckf_predict_kernel(slb::FilterArgs a) {
+    typedef LayState12 L;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inst = blockIdx.x * WPB + w;
+    if (inst >= a.B) return;
+    double *Pr = smem + (size_t)w * PRED_SM, *Pf = Pr + PRED_PR, *Ls = Pf + PRED_PF, *D = Ls + 78, *W = D + 25 * 13,
+           *Fk = W + 144;
+    const int nf = a.nk + a.nl;
+    double *Pg = a.P + (size_t)inst * a.pstride;
+    double *mug = a.mu + (size_t)inst * a.qstride;
+    auto PR = [&](int r, int c) -> double & { return Pr[tri(24 + r, c) - 300]; };  // row 24+r, col c
+
+    for (int e = lane; e < PRED_PR; e += 32) Pr[e] = Pg[300 + e];
+    for (int e = lane; e < nf * 12; e += 32) {
+        const int r = e / 12, c = e - r * 12;
+        Pf[e] = Pg[tri(36 + r, 24 + c)];
+    }
+    double mu[13];
+#pragma unroll
+    for (int c = 0; c < 13; ++c) mu[c] = mug[26 + c];
+    __syncwarp();
+
+    // ---- Cholesky of Pk_i (12x12): lane l < 12 owns row l; rows are broadcast with shuffles -----------
+    double row[12];
+#pragma unroll
+    for (int p = 0; p < 12; ++p) row[p] = (lane < 12 && p <= lane) ? PR(lane, 24 + p) : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        double s = row[k];
+#pragma unroll
+        for (int p = 0; p < k; ++p) s -= row[p] * bcast(row[p], k);
+        const double x = bcast(s, k);
+        ok = ok && (x > 0.0);
+        const double sx = sqrt(x);
+        row[k] = (lane == k) ? sx : s / sx;
+    }
+    if (!ok) {
+        if (lane == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
+        return;
+    }
+    if (lane < 12) {
+#pragma unroll
+        for (int p = 0; p < 12; ++p)
+            if (p <= lane) Ls[tri(lane, p)] = row[p];
+    }
+    __syncwarp();
+
+    // ---- sigma point `lane` (Usckf.hpp:572-598), process model (:141) ---------------------------------
+    ProcessModel<PM> f;
+    {
+        double u[ProcessModel<PM>::NU];
+#pragma unroll
+        for (int c = 0; c < ProcessModel<PM>::NU; ++c) u[c] = a.u[(size_t)inst * ProcessModel<PM>::NU + c];
+        f.prepare(u, a.dt);
+    }
+    const bool act = lane < 25;
+    const int j = (lane - 1) >> 1;
+    const double sgn = (lane & 1) ? 1.0 : -1.0;
+    double Y[13];
+    {
+        double d[12], X[13];
+#pragma unroll
+        for (int r = 0; r < 12; ++r) d[r] = (act && lane >= 1 && r >= j) ? sgn * Ls[tri(r, j < 0 ? 0 : (j > r ? r : j))] : 0.0;
+        boxplus<L>(mu, d, 1.0, X);
+        f.apply(X, Y);
+    }
+    // ---- manifold mean (:601-627) --------------------------------------------------------------------
+    double ref[13];
+#pragma unroll
+    for (int c = 0; c < 13; ++c) ref[c] = bcast(Y[c], 0);
+    int it = 0;
+    double nrm2;
+    do {
+        double dd[12], md[12], nr[13];
+        boxminus<L>(Y, ref, dd);
+        nrm2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 12; ++r) {
+            md[r] = warp_sum(act ? dd[r] : 0.0) / 25.0;
+            nrm2 += md[r] * md[r];
+        }
+        boxplus<L>(ref, md, 1.0, nr);
+#pragma unroll
+        for (int c = 0; c < 13; ++c) ref[c] = nr[c];
+    } while (sqrt(nrm2) > 1e-6 && ++it < 10000);
+    int st = (it >= 10000) ? SLB_ST_MEAN_NOCONV : 0;
+
+    {
+        double dY[12];
+        boxminus<L>(Y, ref, dY);
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < 12; ++r) D[lane * 13 + r] = dY[r];
+        }
+    }
+    __syncwarp();
+    // ---- Pk_i = cov + Q (:178) and W = 0.5 (dY+ - dY-) -------------------------------------------------
+    for (int e = lane; e < 78; e += 32) {
+        int r = 0;
+        while (tri(r + 1, 0) <= e) ++r;
+        const int c = e - tri(r, 0);
+        double s = 0.0;
+#pragma unroll 5
+        for (int t = 0; t < 25; ++t) s += D[t * 13 + r] * D[t * 13 + c];
+        PR(r, 24 + c) = 0.5 * s + __ldg(a.Q + r * 12 + c);
+    }
+    for (int e = lane; e < 144; e += 32) {
+        const int jj = e / 12, c = e - jj * 12;
+        W[e] = 0.5 * (D[(1 + 2 * jj) * 13 + c] - D[(2 + 2 * jj) * 13 + c]);
+    }
+    __syncwarp();
+    // ---- Fk = W^T L^-1  <=>  L^T Fk^T = W: lane c back-substitutes column c (:154) --------------------
+    if (lane < 12) {
+        double x[12];
+#pragma unroll
+        for (int r = 11; r >= 0; --r) {
+            double s = W[r * 12 + lane];
+#pragma unroll
+            for (int p = r + 1; p < 12; ++p) s -= Ls[tri(p, r)] * x[p];
+            x[r] = s / Ls[tri(r, r)];
+        }
+#pragma unroll
+        for (int r = 0; r < 12; ++r) Fk[lane * 12 + r] = x[r];
+    }
+    __syncwarp();
+    // ---- cross-covariances with the clones (:191-208): rows 24..35 x cols 0..23  <- Fk * old ----------
+    double out[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int o = lane + 32 * t, r = o / 24, c = o - r * 24;
+        double s = 0.0;
+#pragma unroll
+        for (int p = 0; p < 12; ++p) s += Fk[r * 12 + p] * PR(p, c);
+        out[t] = s;
+    }
+    // ---- and with the features (:217-235): feature rows x cols 24..35  <- old * Fk^T -------------------
+    double of[11];
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {
+        const int o = lane + 32 * t;
+        double s = 0.0;
+        if (o < nf * 12) {
+            const int r = o / 12, c = o - r * 12;
+#pragma unroll
+            for (int p = 0; p < 12; ++p) s += Pf[r * 12 + p] * Fk[c * 12 + p];
+        }
+        of[t] = s;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int o = lane + 32 * t, r = o / 24, c = o - r * 24;
+        PR(r, c) = out[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 11; ++t) {
+        const int o = lane + 32 * t;
+        if (o < nf * 12) Pf[o] = of[t];
+    }
+    __syncwarp();
+    // ---- write back --------------------------------------------------------------------------------------
+    for (int e = lane; e < PRED_PR; e += 32) Pg[300 + e] = Pr[e];
+    for (int e = lane; e < nf * 12; e += 32) {
+        const int r = e / 12, c = e - r * 12;
+        Pg[tri(36 + r, 24 + c)] = Pf[e];
+    }
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < 13; ++c) {
+        finite = finite && isfinite(ref[c]);
+        if (lane == c) mug[26 + c] = ref[c];
+    }
+    if (!finite) st |= SLB_ST_NONFINITE;
+    if (st && lane == 0) a.status[inst] |= st;
+}
+
+// =====================================================================================================
+// update with the VO measurement model of test/UsckfUnitTest.cpp:62-86 (m = NK)
+// =====================================================================================================
+template <int NK, int NL>
+struct UpdCfg {
+    static constexpr int N = 36 + NK + NL;
+    static constexpr int NP = N * (N + 1) / 2;
+    static constexpr int NPPAD = (NP + 15) / 16 * 16;
+    static constexpr int JM = 36 + NK;          // columns j >= JM cannot move h
+    static constexpr int NSIG = 2 * JM + 1;     // sigma points that are actually evaluated
+    static constexpr int ZW = NSIG * NK + JM * NK;
+    static constexpr int KK = 2 * N * NK;
+    static constexpr int SCR = ZW > KK ? ZW : KK;  // Z|W, later overlaid by K|KS
+    static constexpr int SM = (NPPAD + SCR + N + 2 + 1) / 2 * 2;  // + delta + mbarrier slot; even: 16-B aligned warps
+};
+
+template <int NK, int NL, int WPB>
+__global__ void __launch_bounds__(WPB * 32) usckf_update_kernel(slb::FilterArgs a) {
+    typedef UpdCfg<NK, NL> C;
+    constexpr int N = C::N, JM = C::JM, NSIG = C::NSIG;
+    static_assert(NK == 3, "the 3x3 closed-form S^-1 is the only one wired so far");
+    static_assert(N > 32 && N <= 64, "two register rows per lane");
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inst = blockIdx.x * WPB + w;
+    if (inst >= a.B) return;
+    double *Ps = smem + (size_t)w * C::SM, *Zs = Ps + C::NPPAD, *Ws = Zs + NSIG * NK, *Ks = Zs, *KSs = Zs + N * NK,
+           *dl = Zs + C::SCR;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(dl + N);
+    double *Pg = a.P + (size_t)inst * a.pstride;
+    double *mug = a.mu + (size_t)inst * a.qstride;
+
+    // ---- stream the packed covariance record into shared memory with one TMA bulk copy -----------------
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, C::NPPAD * 8);
+        bulk_g2s(Ps, Pg, C::NPPAD * 8, bar);
+    }
+    // mean blocks that h needs (statek pos/orient, statek_i pos/orient, featuresk) while the copy flies
+    double pk[3], qk[4], pi[3], qi[4], ft[NK];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { pk[c] = mug[c]; pi[c] = mug[26 + c]; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { qk[c] = mug[3 + c]; qi[c] = mug[29 + c]; }
+#pragma unroll
+    for (int c = 0; c < NK; ++c) ft[c] = mug[39 + c];
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    // ---- Eigen::LLT of Pk (:537): lane owns rows `lane` (ra) and `lane+32` (rb) -----------------------
+    const bool hasB = lane + 32 < N;
+    const int iB = hasB ? lane + 32 : N - 1;
+    double ra[32], rb[N];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) ra[p] = (p <= lane) ? Ps[tri(lane, p)] : 0.0;
+#pragma unroll
+    for (int p = 0; p < N; ++p) rb[p] = (hasB && p <= lane + 32) ? Ps[tri(iB, p > iB ? iB : p)] : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double sA = (k < 32) ? ra[k < 32 ? k : 0] : 0.0, sB = rb[k];
+#pragma unroll
+        for (int p = 0; p < k; ++p) {
+            const double bk = Ps[tri(k, p)];  // finished entry of row k: broadcast read
+            if (k < 32 && p < 32) sA -= ra[p] * bk;
+            sB -= rb[p] * bk;
+        }
+        const double x = (k < 32) ? bcast(sA, k) : bcast(sB, k - 32);
+        ok = ok && (x > 0.0);
+        const double sx = sqrt(x);
+        if (k < 32) {
+            const double v = (lane == k) ? sx : sA / sx;
+            ra[k < 32 ? k : 0] = v;
+            if (lane >= k) Ps[tri(lane, k)] = v;
+        }
+        {
+            const double v = (k >= 32 && lane == k - 32) ? sx : sB / sx;
+            rb[k] = v;
+            if (hasB && lane + 32 >= k) Ps[tri(iB, k)] = v;
+        }
+        __syncwarp();
+    }
+    if (!ok) {
+        if (lane == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < 32; ++p) ra[p] = (p <= lane) ? ra[p] : 0.0;
+#pragma unroll
+    for (int p = 0; p < N; ++p) rb[p] = (hasB && p <= lane + 32) ? rb[p] : 0.0;
+
+    // ---- sigma points through h (:275-278), lane per point ---------------------------------------------
+    constexpr int NPASS = (NSIG + 31) / 32;
+    double zr[NPASS][NK];
+#pragma unroll
+    for (int t = 0; t < NPASS; ++t) {
+        const int s = lane + 32 * t;
+        const bool act = s < NSIG;
+        const int j = act && s >= 1 ? (s - 1) >> 1 : 0;
+        const double sgn = (s & 1) ? 1.0 : -1.0;
+        auto Lc = [&](int r) -> double { return (act && s >= 1 && r >= j) ? sgn * Ps[tri(r, j)] : 0.0; };
+        double xpk[3], xqk[4], xpi[3], xqi[4], xf[NK];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { xpk[c] = pk[c] + Lc(c); xpi[c] = pi[c] + Lc(24 + c); }
+        {
+            const double v[3] = {Lc(3), Lc(4), Lc(5)};
+            double e[4];
+            so3_exp(v, 1.0, e);
+            quat_mul(qk, e, xqk);
+        }
+        {
+            const double v[3] = {Lc(27), Lc(28), Lc(29)};
+            double e[4];
+            so3_exp(v, 1.0, e);
+            quat_mul(qi, e, xqi);
+        }
+#pragma unroll
+        for (int c = 0; c < NK; ++c) xf[c] = ft[c] + Lc(36 + c);
+        // h: delta = statek [-] statek_i as a transform, applied to every 3-D feature of featuresk
+        double dq[4];
+        quat_cmul(xqi, xqk, dq);
+#pragma unroll
+        for (int c = 0; c < NK; c += 3) {
+            double rz[3];
+            rotmat_apply(dq, xf + c, rz);
+            zr[t][c] = rz[0] + (xpk[0] - xpi[0]);
+            zr[t][c + 1] = rz[1] + (xpk[1] - xpi[1]);
+            zr[t][c + 2] = rz[2] + (xpk[2] - xpi[2]);
+        }
+        if (act) {
+#pragma unroll
+            for (int c = 0; c < NK; ++c) Zs[s * NK + c] = zr[t][c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < NK; ++c) zr[t][c] = 0.0;
+        }
+    }
+    // ---- mean / innovation covariance (:280-282); the 2(N-JM) untouched points all equal Z0 ------------
+    constexpr double NREST = 2.0 * (N - JM);
+    double z0[NK], zbar[NK];
+#pragma unroll
+    for (int c = 0; c < NK; ++c) {
+        z0[c] = bcast(zr[0][c], 0);
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < NPASS; ++t) s += zr[t][c];
+        zbar[c] = (warp_sum(s) + NREST * z0[c]) / (double)(2 * N + 1);
+    }
+    double S[NK * (NK + 1) / 2];
+#pragma unroll
+    for (int r = 0; r < NK; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < NPASS; ++t)
+                if (lane + 32 * t < NSIG) s += (zr[t][r] - zbar[r]) * (zr[t][c] - zbar[c]);
+            s = warp_sum(s) + NREST * (z0[r] - zbar[r]) * (z0[c] - zbar[c]);
+            S[tri(r, c)] = 0.5 * s + __ldg(a.R + r * NK + c);
+        }
+    __syncwarp();
+    // W[j] = 0.5 (Z+_j - Z-_j): the only part of covXZ's right factor that survives the +- pairing
+    for (int e = lane; e < JM * NK; e += 32) {
+        const int jj = e / NK, c = e - jj * NK;
+        Ws[e] = 0.5 * ((Zs[(1 + 2 * jj) * NK + c] - zbar[c]) - (Zs[(2 + 2 * jj) * NK + c] - zbar[c]));
+    }
+    __syncwarp();
+    // ---- covXZ = L W (:283, :714-737), rows from registers ---------------------------------------------
+    double pxA[NK], pxB[NK];
+#pragma unroll
+    for (int c = 0; c < NK; ++c) pxA[c] = pxB[c] = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < JM; ++jj) {
+#pragma unroll
+        for (int c = 0; c < NK; ++c) {
+            const double wv = Ws[jj * NK + c];
+            if (jj < 32) pxA[c] += ra[jj < 32 ? jj : 0] * wv;
+            pxB[c] += rb[jj] * wv;
+        }
+    }
+    // ---- K = covXZ S^-1 (:286-288), innovation, Mahalanobis gate (:290-294) ----------------------------
+    double Si[6];
+    sym3_inverse(S, Si);
+    auto SiAt = [&](int r, int c) { return r >= c ? Si[tri(r, c)] : Si[tri(c, r)]; };
+    auto SAt = [&](int r, int c) { return r >= c ? S[tri(r, c)] : S[tri(c, r)]; };
+    double nu[NK], m2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < NK; ++c) nu[c] = a.z[(size_t)inst * NK + c] - zbar[c];
+#pragma unroll
+    for (int r = 0; r < NK; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < NK; ++c) s += SiAt(r, c) * nu[c];
+        m2 += nu[r] * s;
+    }
+    const bool accept = chi2_accept(m2, a.gate);
+    __syncwarp();  // Z | W are dead from here: K | KS overlay them
+    auto finish_row = [&](const double *px, int i) {
+        double K[NK], dsum = 0.0;
+#pragma unroll
+        for (int c = 0; c < NK; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int p = 0; p < NK; ++p) s += px[p] * SiAt(p, c);
+            K[c] = s;
+            dsum += s * nu[c];
+        }
+#pragma unroll
+        for (int c = 0; c < NK; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int p = 0; p < NK; ++p) s += K[p] * SAt(p, c);
+            Ks[i * NK + c] = K[c];
+            KSs[i * NK + c] = s;
+        }
+        dl[i] = dsum;
+    };
+    finish_row(pxA, lane);
+    if (hasB) finish_row(pxB, lane + 32);
+    __syncwarp();
+    if (!accept) {
+        if (lane == 0) a.status[inst] |= SLB_ST_GATE_REJECT;
+        return;
+    }
+    // ---- mu = mu [+] K nu (:299-301): lane b < 12 owns block b, lanes 12.. own the feature scalars -----
+    bool finite = true;
+    if (lane < 12) {
+        const int sidx = lane >> 2, bw = lane & 3;
+        const int qo = 13 * sidx + (bw == 0 ? 0 : bw == 1 ? 3 : bw == 2 ? 7 : 10);
+        const double v[3] = {dl[3 * lane], dl[3 * lane + 1], dl[3 * lane + 2]};
+        if (bw == 1) {
+            const double q[4] = {mug[qo], mug[qo + 1], mug[qo + 2], mug[qo + 3]};
+            double e[4], o[4];
+            so3_exp(v, 1.0, e);
+            quat_mul(q, e, o);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { mug[qo + c] = o[c]; finite = finite && isfinite(o[c]); }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double o = mug[qo + c] + v[c];
+                mug[qo + c] = o;
+                finite = finite && isfinite(o);
+            }
+        }
+    } else if (lane - 12 < NK + NL) {
+        const double o = mug[39 + lane - 12] + dl[36 + lane - 12];
+        mug[39 + lane - 12] = o;
+        finite = finite && isfinite(o);
+    }
+    // ---- Pk -= K S K^T (:296) on the HBM record (lower triangle), coalesced per row ---------------------
+#pragma unroll 2
+    for (int i = 0; i < N; ++i) {
+        const double k0 = KSs[i * NK], k1 = KSs[i * NK + 1], k2 = KSs[i * NK + 2];
+        for (int c = lane; c <= i; c += 32) {
+            const int e = tri(i, c);
+            Pg[e] = Pg[e] - (k0 * Ks[c * NK] + k1 * Ks[c * NK + 1] + k2 * Ks[c * NK + 2]);
+        }
+    }
+    if (!__all_sync(FULL, finite) && lane == 0) a.status[inst] |= SLB_ST_NONFINITE;
+}
+
+// =====================================================================================================
+// cloning (Usckf.hpp:391-433) and setMeasurement (:322-389): pure data movement, thread per element
+// =====================================================================================================
+__global__ void usckf_clone_kernel(slb::FilterArgs a, int mode) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = 13 + 12 * 12 * 2;  // 13 mean scalars + two 12x12 blocks' worth of work items
+    if (t >= (int64_t)a.B * per) return;
+    const int inst = (int)(t / per), e = (int)(t - (int64_t)inst * per);
+    double *P = a.P + (size_t)inst * a.pstride, *mu = a.mu + (size_t)inst * a.qstride;
+    auto sym = [&](int r, int c) { return r >= c ? P[tri(r, c)] : P[tri(c, r)]; };
+    if (e < 13) {
+        if (mode == SLB_STATEK_I) mu[13 + e] = mu[26 + e];   // statek_l = statek_i (:401)
+        else mu[e] = mu[13 + e];                              // statek = statek_l (:419)
+        return;
+    }
+    const int q = e - 13, blk = q / 144, rc = q - blk * 144, r = rc / 12, c = rc - r * 12;
+    if (mode == SLB_STATEK_I) {
+        if (blk == 0) {
+            // Pk+l = Pk+i (:405) and Pk+i|k+l = Pk+i (:406-407)
+            const double v = sym(24 + r, 24 + c);
+            if (c <= r) P[tri(12 + r, 12 + c)] = v;
+            P[tri(24 + r, 12 + c)] = v;
+        } else {
+            // cross blocks with statek zeroed (:410-413)
+            P[tri(24 + r, c)] = 0.0;
+            P[tri(12 + r, c)] = 0.0;
+        }
+    } else if (blk == 0) {
+        // Pk = Pk+l, Pk|k+l = Pk+l (:422-425)
+        const double v = sym(12 + r, 12 + c);
+        if (c <= r) P[tri(r, c)] = v;
+        P[tri(12 + r, c)] = v;
+    }
+}
+// The cloning kernel reads blocks other threads overwrite only in STATEK_I blk 0 (reads P_ii, writes
+// P_ll / P_il) and STATEK_L blk 0 (reads P_ll, writes P_kk / P_lk): sources and destinations are disjoint.
+
+__global__ void usckf_set_measurement_kernel(slb::FilterArgs a, int mode) {
+    const int N = 36 + a.nk + a.nl, NP = N * (N + 1) / 2;
+    const int nfe = NP - 666;  // packed entries of rows 36..N-1
+    const int per = nfe + (mode == SLB_STATEK ? a.nk : a.nl);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)a.B * per) return;
+    const int inst = (int)(t / per), e = (int)(t - (int64_t)inst * per);
+    double *P = a.P + (size_t)inst * a.pstride, *mu = a.mu + (size_t)inst * a.qstride;
+    const int len = mode == SLB_STATEK ? a.nk : a.nl;
+    const int f0 = mode == SLB_STATEK ? 0 : a.nk;  // first feature index being replaced
+    if (e >= nfe) {
+        const int c = e - nfe;
+        mu[39 + f0 + c] = a.z[(size_t)inst * len + c];  // featuresk / featuresk_l = z (:335,:362)
+        return;
+    }
+    int r = 36;
+    while (tri(r + 1, 0) - 666 <= e) ++r;
+    const int c = e - (tri(r, 0) - 666);
+    const int fr = r - 36, fc = c - 36;
+    double v = 0.0;  // Pk.setZero() (:348,:376): every state<->feature and k<->k+l cross term
+    if (c >= 36) {
+        const bool rin = fr >= f0 && fr < f0 + len, cin = fc >= f0 && fc < f0 + len;
+        if (rin && cin) v = a.R[(fr - f0) * len + (fc - f0)];      // new block = R (:353,:381)
+        else if (!rin && !cin) v = P[tri(r, c)];                    // the block that stays (:355,:383)
+    }
+    P[tri(r, c)] = v;
+}
+
+}  // namespace slbd
+
+namespace slb {
+
+template <int PM>
+static int launch_predict_t(const FilterArgs &a, cudaStream_t s) {
+    constexpr int WPB = 8;
+    constexpr size_t smem = (size_t)WPB * slbd::PRED_SM * sizeof(double);
+    auto kern = slbd::usckf_predict_kernel<PM, WPB>;
+    SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(a.B + WPB - 1) / WPB, WPB * 32, smem, s>>>(a);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+template <int NK, int NL>
+static int launch_update_t(const FilterArgs &a, cudaStream_t s) {
+    constexpr int WPB = 4;
+    constexpr size_t smem = (size_t)WPB * slbd::UpdCfg<NK, NL>::SM * sizeof(double);
+    auto kern = slbd::usckf_update_kernel<NK, NL, WPB>;
+    SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(a.B + WPB - 1) / WPB, WPB * 32, smem, s>>>(a);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+int launch_usckf(int pm, int mm, bool predict, bool update, const FilterArgs &a, cudaStream_t s) {
+    if (predict) {
+        if (pm != SLB_PM_USCKF_TEST) return set_error(SLB_ERR_INVALID, "usckf: unsupported process model");
+        int rc = launch_predict_t<SLB_PM_USCKF_TEST>(a, s);
+        if (rc != SLB_OK) return rc;
+    }
+    if (update) {
+        if (mm != SLB_MM_USCKF_VO) return set_error(SLB_ERR_INVALID, "usckf: unsupported measurement model");
+        if (a.nk == 3 && a.nl == 9) return launch_update_t<3, 9>(a, s);
+        if (a.nk == 3 && a.nl == 0) return launch_update_t<3, 0>(a, s);
+        return set_error(SLB_ERR_INVALID, "usckf update: built for (nk,nl) = (3,9) and (3,0)");
+    }
+    return SLB_OK;
+}
+
+int launch_usckf_clone(int mode, const FilterArgs &a, cudaStream_t s) {
+    if (mode != SLB_STATEK_I && mode != SLB_STATEK_L) return SLB_OK;  // default: break (Usckf.hpp:428)
+    const int64_t work = (int64_t)a.B * (13 + 288);
+    slbd::usckf_clone_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s>>>(a, mode);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+int launch_usckf_set_measurement(int mode, const FilterArgs &a, cudaStream_t s) {
+    if (mode != SLB_STATEK && mode != SLB_STATEK_L) return SLB_OK;
+    const int N = 36 + a.nk + a.nl;
+    const int len = mode == SLB_STATEK ? a.nk : a.nl;
+    if (len == 0) return SLB_OK;
+    const int64_t work = (int64_t)a.B * (N * (N + 1) / 2 - 666 + len);
+    slbd::usckf_set_measurement_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s>>>(a, mode);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+}  // namespace slb

@@ -1,0 +1,198 @@
+"""GPU parity: localization::Usckf (BASELINE configs 1/4: n=12, N=36+3+9=48, m=3) through the C ABI
+vs the CPU oracle.  The engine keeps the lower triangle of Pk (what the reference's LLT reads, Q8),
+so oracle covariances are compared through their lower triangle."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from slam_localization_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+AUG = synth.STATE_BLOCKS * 3
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _oracle_predict(slo, sc, mu, P):
+    return slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, sc["nk"], sc["nl"], mu, P, sc["u"], sc["dt"], sc["Q"], None,
+                          None, update=False, nthreads=8)
+
+
+def _oracle_update(slo, sc, mu, P, gate=0):
+    return slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, sc["nk"], sc["nl"], mu, P, None, 0.0, None, sc["z"], sc["R"],
+                          gate_dof=gate, predict=False, nthreads=8)
+
+
+@pytest.mark.parametrize("nk,nl", [(3, 9), (3, 0)])
+def test_usckf_predict_then_update_parity(slo, nk, nl):
+    B = 203                                       # ragged against the 4- and 8-warp CTAs
+    sc = synth.usckf_scenario(B, seed=41, nk=nk, nl=nl)
+    f = engine.Usckf(B, nk=nk, nl=nl)
+    f.set_state(sc["mu"], sc["P"])
+    f.predict(engine.PM_USCKF_TEST, sc["u"], sc["dt"], sc["Q"])
+    mu1, P1, st1, it1 = _oracle_predict(slo, sc, sc["mu"], sc["P"])
+    assert not st1.any()
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mu1, parity.symmetrize_lower(P1), nfeat=nk + nl)
+    f.update(engine.MM_USCKF_VO, sc["z"], sc["R"])
+    mu2, P2, st2, _ = _oracle_update(slo, sc, mu1, P1)
+    assert not st2.any() and not f.status().any()
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mu2, parity.symmetrize_lower(P2), nfeat=nk + nl)
+
+
+def test_usckf_fused_step_and_golden(slo):
+    g = np.load(os.path.join(G, "usckf_n48.npz"))
+    B = g["mu0"].shape[0]
+    f = engine.Usckf(B, nk=3, nl=9)
+    f.set_state(g["mu0"], g["P0"])
+    f.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, g["u"], float(g["dt"]), g["Q"], g["z"], g["R"])
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), g["mu2"], parity.symmetrize_lower(g["P2"]), nfeat=12)
+
+
+def test_usckf_update_only_touches_what_it_should(slo):
+    """Columns j >= 36+nk cannot move h: the kernel skips them; the result must not notice."""
+    B = 64
+    sc = synth.usckf_scenario(B, seed=42)
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], sc["P"])
+    f.update(engine.MM_USCKF_VO, sc["z"], sc["R"])
+    mu2, P2, st2, _ = _oracle_update(slo, sc, sc["mu"], sc["P"])
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mu2, parity.symmetrize_lower(P2), nfeat=12)
+    P = f.P()
+    assert np.linalg.eigvalsh(P).min() > 0
+
+
+def test_usckf_gate_and_indefinite_covariance(slo):
+    B = 32
+    sc = synth.usckf_scenario(B, seed=43)
+    sc["z"][:5] += 100.0
+    P = sc["P"].copy()
+    P[5, 40, 40] = -1.0
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], P)
+    f.update(engine.MM_USCKF_VO, sc["z"], sc["R"], gate_dof=3)
+    st = f.status()
+    assert np.all(st[:5] & engine.ST_GATE_REJECT) and (st[5] & engine.ST_CHOL_FAIL)
+    np.testing.assert_array_equal(f.mu()[:6], sc["mu"][:6])
+    np.testing.assert_array_equal(np.tril(f.P()[:6]), np.tril(P[:6]))
+    mu2, P2, st2, _ = _oracle_update(slo, dict(sc), sc["mu"], P, gate=3)
+    ok = st2 == 0
+    np.testing.assert_array_equal(st[ok], 0)
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mu2, parity.symmetrize_lower(P2), nfeat=12, mask=ok)
+
+
+def test_usckf_reference_unit_test_sequence(slo):
+    """USCKF_DYNAMIC (test/UsckfUnitTest.cpp:175-284) through the engine: ctor #2 = cloning(I), cloning(L);
+    three setMeasurement calls; two predicts; update on the resulting INDEFINITE covariance (quirk Q13),
+    which the engine flags instead of continuing with a broken factor (Q8)."""
+    fx = synth.usckf_unit_test_fixture()
+    # engine batches have fixed feature sizes: start at (3, 9) with zero feature blocks
+    mu = np.r_[synth.identity_q(AUG), np.zeros(12)][None]
+    P = np.zeros((1, 48, 48))
+    P[0, 24:36, 24:36] = fx["P0_single"]
+    f = engine.Usckf(1, nk=3, nl=9)
+    f.set_state(mu, P)
+    f.cloning(engine.STATEK_I)
+    f.cloning(engine.STATEK_L)
+    f.set_measurement(engine.STATEK, fx["featuresVO"][None], fx["featuresVOCov"])
+    f.set_measurement(engine.STATEK_L, fx["featuresICP"][None], fx["featuresICPCov"])
+    f.set_measurement(engine.STATEK, fx["featuresVO2"][None], fx["featuresVO2Cov"])
+    # oracle: the reference's own call sequence with growing P
+    single = synth.identity_q(synth.STATE_BLOCKS)[None]
+    mo, Po = slo.usckf_ctor_single(single, fx["P0_single"][None])
+    mo, Po = slo.usckf_set_measurement(slo.STATEK, 0, 0, mo, Po, fx["featuresVO"][None], fx["featuresVOCov"])
+    mo, Po = slo.usckf_set_measurement(slo.STATEK_L, 3, 0, mo, Po, fx["featuresICP"][None], fx["featuresICPCov"])
+    mo, Po = slo.usckf_set_measurement(slo.STATEK, 3, 9, mo, Po, fx["featuresVO2"][None], fx["featuresVO2Cov"])
+    np.testing.assert_array_equal(f.mu(), mo)
+    np.testing.assert_array_equal(f.P(), Po)
+    u = np.r_[fx["velo"], fx["angvelo"]][None]
+    Q = synth.usckf_process_noise(fx["dt"])
+    for _ in range(2):
+        f.predict(engine.PM_USCKF_TEST, u, fx["dt"], Q)
+        mo, Po, st, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, mo, Po, u, fx["dt"], Q, None, None,
+                                       update=False)
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mo, parity.symmetrize_lower(Po), nfeat=12)
+    f.update(engine.MM_USCKF_VO, fx["z"][None], fx["R"])
+    assert f.status()[0] & engine.ST_CHOL_FAIL
+
+
+@pytest.mark.parametrize("mode", [engine.STATEK_I, engine.STATEK_L])
+def test_usckf_cloning(slo, mode):
+    B = 50
+    sc = synth.usckf_scenario(B, seed=44)
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], sc["P"])
+    f.cloning(mode)
+    mo, Po = slo.usckf_clone(mode, 3, 9, sc["mu"], sc["P"])
+    np.testing.assert_array_equal(f.mu(), mo)
+    np.testing.assert_array_equal(f.P(), parity.symmetrize_lower(Po))
+
+
+@pytest.mark.parametrize("mode", [engine.STATEK, engine.STATEK_L])
+def test_usckf_set_measurement(slo, mode):
+    B = 50
+    sc = synth.usckf_scenario(B, seed=45)
+    ln = 3 if mode == engine.STATEK else 9
+    rng = np.random.default_rng(46)
+    z = rng.normal(size=(B, ln))
+    R = synth.random_spd(rng, 1, ln, 0.01, 5.0)[0]
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], sc["P"])
+    f.set_measurement(mode, z, R)
+    mo, Po = slo.usckf_set_measurement(mode, 3, 9, sc["mu"], sc["P"], z, R)
+    np.testing.assert_array_equal(f.mu(), mo)
+    np.testing.assert_array_equal(f.P(), parity.symmetrize_lower(Po))
+
+
+def test_usckf_sliding_window_sequence(slo):
+    """A realistic cycle: predict x3, update, cloning(L), cloning(I), setMeasurement, ... for 60 steps,
+    free-running on both sides (no re-synchronisation)."""
+    B = 40
+    sc = synth.usckf_scenario(B, seed=47)
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], sc["P"])
+    mo, Po = sc["mu"], sc["P"]
+    rng = np.random.default_rng(48)
+    for k in range(60):
+        u = np.concatenate([rng.normal(size=(B, 3)), rng.normal(size=(B, 3)) * 0.2], axis=1)
+        f.predict(engine.PM_USCKF_TEST, u, sc["dt"], sc["Q"])
+        mo, Po, st, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, mo, Po, u, sc["dt"], sc["Q"], None, None,
+                                       update=False, nthreads=8)
+        assert not st.any()
+        if k % 3 == 2:
+            z = mo[:, 39:42] + rng.normal(size=(B, 3)) * 0.1
+            f.update(engine.MM_USCKF_VO, z, sc["R"])
+            mo, Po, st, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, mo, Po, None, 0.0, None, z, sc["R"],
+                                           predict=False, nthreads=8)
+            assert not st.any()
+        if k % 12 == 11:
+            for mode in (engine.STATEK_L, engine.STATEK_I):
+                f.cloning(mode)
+                mo, Po = slo.usckf_clone(mode, 3, 9, mo, Po)
+            zk = 3.3 + 0.1 * rng.normal(size=(B, 3))
+            f.set_measurement(engine.STATEK, zk, 0.008 * np.eye(3))
+            mo, Po = slo.usckf_set_measurement(slo.STATEK, 3, 9, mo, Po, zk, 0.008 * np.eye(3))
+    assert not f.status().any()
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mo, parity.symmetrize_lower(Po), nfeat=12, tol=parity.LONG_TOL)
+
+
+def test_usckf_fleet_properties():
+    """Fleet-size run (65,536 instances here; config 4 shards 4M of these over 8 GPUs): instance i of the
+    fleet equals instance i run alone, bit for bit (no cross-instance arithmetic => results independent of
+    the sharding), covariances stay PSD, no status flags."""
+    B = 65536
+    sc = synth.usckf_scenario(2048, seed=49)
+    rep = B // 2048
+    tile = lambda x: np.tile(x, (rep,) + (1,) * (x.ndim - 1))
+    f = engine.Usckf(B)
+    f.set_state(tile(sc["mu"]), tile(sc["P"]))
+    f.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, tile(sc["u"]), sc["dt"], sc["Q"], tile(sc["z"]), sc["R"])
+    assert sum(f.status_counts()) == 0
+    mu, P = f.mu(), f.P()
+    g = engine.Usckf(2048)
+    g.set_state(sc["mu"], sc["P"])
+    g.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"])
+    for r in (0, 7, rep - 1):
+        np.testing.assert_array_equal(mu[r * 2048:(r + 1) * 2048], g.mu())
+        np.testing.assert_array_equal(P[r * 2048:(r + 1) * 2048], g.P())
+    assert np.linalg.eigvalsh(P[::511]).min() > 0
