@@ -41,18 +41,25 @@ def test_addsub(slo, d):
 
 def test_fusion_full_size_properties():
     """1M 6-dof fusions (BASELINE config 5): fusing an estimate with itself halves the covariance and
-    keeps the mean; fusion is symmetric in its arguments up to rounding; three-way chaining is
-    bounded by conditioning (explicit inverses lose ~cond*eps; cond <~ 1e4 here)."""
+    keeps the mean; fusion is symmetric in its arguments.  Explicit inverses (DataModel.hpp:54) lose
+    ~cond*eps, and among 1M random covariances a few are nearly singular, so the bound is per instance:
+    1e-12 * cond."""
     n = 1 << 20
     sc = synth.fusion_scenario(n, d=6, log_spread=0.5)
+    kap = np.maximum(np.linalg.cond(sc["C1"]), np.linalg.cond(sc["C2"]))
     x1, C1, x2, C2 = (engine.DeviceArray(sc[k]) for k in ("x1", "C1", "x2", "C2"))
+
+    def close(a, b, scale):
+        err = np.max(np.abs(a - b).reshape(n, -1), axis=1)
+        assert np.all(err <= 1e-12 * kap * scale), float(np.max(err / (kap * scale)))
+
     xs, Cs = engine.DataModel.fuse(x1, C1, x1, C1)
-    np.testing.assert_allclose(xs.numpy(), sc["x1"], rtol=1e-7, atol=1e-8)
-    np.testing.assert_allclose(Cs.numpy(), 0.5 * sc["C1"], rtol=1e-7, atol=1e-9)
+    close(xs.numpy(), sc["x1"], 1.0 + np.max(np.abs(sc["x1"]), axis=1))
+    close(Cs.numpy(), 0.5 * sc["C1"], np.max(np.abs(sc["C1"]).reshape(n, -1), axis=1))
     xa, Ca = engine.DataModel.fuse(x1, C1, x2, C2)
     xb, Cb = engine.DataModel.fuse(x2, C2, x1, C1)
-    np.testing.assert_allclose(xa.numpy(), xb.numpy(), rtol=1e-7, atol=1e-8)
-    np.testing.assert_allclose(Ca.numpy(), Cb.numpy(), rtol=1e-7, atol=1e-9)
+    close(xa.numpy(), xb.numpy(), 1.0 + np.max(np.abs(xb.numpy()), axis=1))
+    close(Ca.numpy(), Cb.numpy(), np.max(np.abs(Cb.numpy()).reshape(n, -1), axis=1))
     # in-place form, like data1.fusion(data2)
     engine.DataModel.fuse(x1, C1, x2, C2, out=(x1, C1))
     np.testing.assert_array_equal(x1.numpy(), xa.numpy())
