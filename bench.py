@@ -234,7 +234,78 @@ class FusionWorkload:
         return time.perf_counter() - t0
 
 
-WORKLOADS = {"ukfom": UkfomWorkload, "fusion": FusionWorkload}
+class UsckfWorkload:
+    """BASELINE configs 1/4: Monte-Carlo USCKF fleet (n=12, N=36+3+9=48, m=3), 4M instances over 8 GPUs =
+    524,288 per GPU, predict (IMU-style process model) + update (VO features) per step, two launches.
+    The fleet is 2048 distinct seeded priors replicated on the device; inputs differ per instance."""
+    name = "usckf"
+    metric = "filter-steps/sec (predict+update)"
+    unit = "filter-steps/s"
+    B = 524288
+    NPRIOR = 2048
+    bytes_per_unit = 19704          # SURVEY 8(d): 2*8*(1176+51) + 72
+    flops_per_unit = 1.5e5
+    kernel = "slbd::usckf_update_kernel<3,9> (+ usckf_predict_kernel)"
+
+    def __init__(self, rank, seed=4321):
+        self.sc = synth.usckf_scenario(self.NPRIOR, seed=seed + 1000 * rank)
+        rng = np.random.default_rng(seed + 1000 * rank + 1)
+        rep = self.B // self.NPRIOR
+        self.u = np.concatenate([rng.normal(size=(self.B, 3)), rng.normal(size=(self.B, 3)) * 0.2], axis=1)
+        self.z = np.tile(self.sc["mu"][:, 39:42], (rep, 1)) + rng.normal(size=(self.B, 3)) * 0.1
+
+    def describe(self):
+        return {"workload": "configs[3]/[0]: Monte-Carlo USCKF fleet, 12-dof state + 2 clones + 3+9 features (N=48), "
+                            "IMU-style predict + 3-D VO update", "instances_per_gpu": self.B, "n": 12, "N": 48, "m": 3}
+
+    def setup_gpu(self, engine, torch):
+        self.engine = engine
+        self.f = engine.Usckf(self.B, nk=3, nl=9)
+        self.f.set_state(self.sc["mu"], self.sc["P"], replicate=True)
+        self.Q = engine.DeviceArray(self.sc["Q"])
+        self.R = engine.DeviceArray(self.sc["R"])
+        self.du = engine.DeviceArray(self.u)
+        self.dz = engine.DeviceArray(self.z)
+        self.hu = torch.from_numpy(self.u).pin_memory()
+        self.hz = torch.from_numpy(self.z).pin_memory()
+        self.hQ = torch.from_numpy(self.sc["Q"].copy()).pin_memory()
+        self.hR = torch.from_numpy(self.sc["R"].copy()).pin_memory()
+        self.hmu = torch.empty((self.B, 51), dtype=torch.float64).pin_memory()
+        self.l2_policy = "fleet state %.0f MB per step > L2" % (self.B * (1184 + 52) * 8 / 1e6)
+
+    def step(self, k):
+        e = self.engine
+        self.f.step(e.PM_USCKF_TEST, e.MM_USCKF_VO, self.du, self.sc["dt"], self.Q, self.dz, self.R)
+
+    def step_e2e(self, k):
+        e = self.engine
+        self.f.step_host(e.PM_USCKF_TEST, e.MM_USCKF_VO, self.hu, self.sc["dt"], self.hQ, self.hz, self.hR, mu_out=self.hmu)
+
+    def e2e_bytes(self):
+        return (self.B * 9 + 144 + 9) * 8, self.B * 51 * 8
+
+    def units_per_step(self):
+        return self.B
+
+    def launches_per_step(self):
+        return 2
+
+    def status_ok(self):
+        return sum(self.f.status_counts()) == 0
+
+    def stats_tensor(self):
+        return self.f.ensemble_stats().t
+
+    def cpu_step(self, slo, nsample, nthreads):
+        sc = self.sc
+        n = min(nsample, self.NPRIOR)
+        t0 = time.perf_counter()
+        slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, sc["mu"][:n], sc["P"][:n], self.u[:n], sc["dt"], sc["Q"],
+                       self.z[:n], sc["R"], nthreads=nthreads)
+        return (time.perf_counter() - t0) * nsample / n
+
+
+WORKLOADS = {"ukfom": UkfomWorkload, "fusion": FusionWorkload, "usckf": UsckfWorkload}
 
 
 def register_workload(cls):

@@ -119,8 +119,12 @@ int slb_qdim(slb_handle h);  /* length of a q-vector                    */
 
 /* ---- state access: muState()/PkAugmentedState() (Usckf.hpp:518-526), getPk()/setPk()
  *      (Msckf.hpp:386-395), ukf::mu()/sigma() ------------------------------------------------ */
+/* count = k * (per-instance size): the first k instances are transferred (k = batch for all). */
 int slb_upload(slb_handle h, int field, const void *host, size_t count, void *stream);
 int slb_download(slb_handle h, int field, void *host, size_t count, void *stream);
+/* Fleet initialisation: instance i <- instance (i % count) for i >= count, i.e. Monte-Carlo
+ * replicas of the first `count` priors (new; the reference constructs one filter at a time). */
+int slb_replicate(slb_handle h, int count, void *stream);
 /* Raw device storage (engine-native layout) for zero-copy consumers. */
 int slb_device_ptr(slb_handle h, int field, void **dev);
 

@@ -84,6 +84,20 @@ __global__ void rec_to_dense_P(const double *rec, double *dense, int B0, int cnt
     dense[t] = rec[(size_t)(B0 + i) * pstride + r * (r + 1) / 2 + c];
 }
 
+// fleet initialisation: instance i <- instance i % count (Monte-Carlo replicas of `count` priors)
+__global__ void replicate_soa(double *a, int rows, int stride, int B, int count) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)rows * B) return;
+    const int r = (int)(t / B), i = (int)(t - (int64_t)r * B);
+    if (i >= count) a[(size_t)r * stride + i] = a[(size_t)r * stride + i % count];
+}
+__global__ void replicate_rec(double *a, int per, int B, int count) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)per * B) return;
+    const int i = (int)(t / per), e = (int)(t - (int64_t)i * per);
+    if (i >= count) a[(size_t)i * per + e] = a[(size_t)(i % count) * per + e];
+}
+
 __global__ void status_count(const int32_t *st, int B, unsigned long long *counts) {
     unsigned long long c[4] = {0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
@@ -257,6 +271,9 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
     h->stage_bytes = (size_t)64 << 20;
     const size_t one = (size_t)h->N * h->N * 8;
     if (h->stage_bytes < one * 32) h->stage_bytes = one * 32;
+    // the *_step_host entry points stage u | z | mu_out for the whole batch
+    const size_t io = (size_t)h->B * (h->QD + 16 + (cfg->kind == SLB_KIND_MSCKF ? 104 : 4)) * 8;
+    if (h->stage_bytes < io) h->stage_bytes = io;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&h->mu, mu_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->P, P_bytes);
@@ -314,11 +331,13 @@ static int transfer(slb_handle h, int field, void *host, size_t count, cudaStrea
     if (field == SLB_FIELD_MU) per = h->QD;
     else if (field == SLB_FIELD_P) per = (size_t)h->N * h->N;
     else return set_error(SLB_ERR_INVALID, "slb_upload/download: unknown field");
-    if (count != per * h->B) return set_error(SLB_ERR_INVALID, "slb_upload/download: count must be batch * per-instance size");
+    if (count == 0 || count % per != 0 || count > per * h->B)
+        return set_error(SLB_ERR_INVALID, "slb_upload/download: count must be k * per-instance size, 1 <= k <= batch");
+    const int nin = (int)(count / per);  // the first `nin` instances are transferred
     const int chunk = (int)(h->stage_bytes / (per * 8));
     double *hp = (double *)host;
-    for (int b0 = 0; b0 < h->B; b0 += chunk) {
-        const int cnt = (h->B - b0) < chunk ? (h->B - b0) : chunk;
+    for (int b0 = 0; b0 < nin; b0 += chunk) {
+        const int cnt = (nin - b0) < chunk ? (nin - b0) : chunk;
         const size_t bytes = (size_t)cnt * per * 8;
         const int64_t work = (int64_t)cnt * (field == SLB_FIELD_MU ? h->QD : (up && soa ? h->NP : h->N * h->N));
         const int tpb = 256;
@@ -357,6 +376,27 @@ int slb_upload(slb_handle h, int field, const void *host, size_t count, void *st
 }
 int slb_download(slb_handle h, int field, void *host, size_t count, void *stream) {
     return transfer(h, field, host, count, S(stream), false);
+}
+
+int slb_replicate(slb_handle h, int count, void *stream) {
+    if (!h || count <= 0 || count > h->B) return set_error(SLB_ERR_INVALID, "slb_replicate: bad count");
+    cudaStream_t s = S(stream);
+    if (count == h->B) return SLB_OK;
+    const int tpb = 256;
+    if (h->cfg.kind == SLB_KIND_UKF) {
+        int64_t w = (int64_t)h->QD * h->B;
+        replicate_soa<<<(unsigned)((w + tpb - 1) / tpb), tpb, 0, s>>>(h->mu, h->QD, h->stride, h->B, count);
+        w = (int64_t)h->NP * h->B;
+        replicate_soa<<<(unsigned)((w + tpb - 1) / tpb), tpb, 0, s>>>(h->P, h->NP, h->stride, h->B, count);
+    } else {
+        int64_t w = (int64_t)h->qstride * h->B;
+        replicate_rec<<<(unsigned)((w + tpb - 1) / tpb), tpb, 0, s>>>(h->mu, h->qstride, h->B, count);
+        w = (int64_t)h->pstride * h->B;
+        replicate_rec<<<(unsigned)((w + tpb - 1) / tpb), tpb, 0, s>>>(h->P, h->pstride, h->B, count);
+    }
+    count_launch(2);
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
 }
 
 // ---- ukfom::ukf --------------------------------------------------------------------------------------

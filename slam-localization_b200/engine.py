@@ -27,7 +27,7 @@ EXPORTS = [
     "slb_usckf_predict", "slb_usckf_update", "slb_usckf_step", "slb_usckf_step_host", "slb_usckf_clone",
     "slb_usckf_set_measurement", "slb_msckf_predict", "slb_msckf_update", "slb_datamodel_fuse",
     "slb_datamodel_addsub", "slb_datamodel_fuse_host", "slb_status", "slb_clear_status", "slb_ensemble_stats",
-    "slb_launch_count", "slb_bench_fp64_peak",
+    "slb_launch_count", "slb_bench_fp64_peak", "slb_replicate",
 ]
 
 
@@ -60,6 +60,7 @@ def lib():
         L.slb_upload.argtypes = [vp, i32, vp, C.c_size_t, vp]
         L.slb_download.argtypes = [vp, i32, vp, C.c_size_t, vp]
         L.slb_device_ptr.argtypes = [vp, i32, C.POINTER(vp)]
+        L.slb_replicate.argtypes = [vp, i32, vp]
         L.slb_ukf_predict.argtypes = [vp, i32, dp, dbl, dp, vp]
         L.slb_ukf_update.argtypes = [vp, i32, dp, dp, i32, vp]
         L.slb_ukf_step.argtypes = [vp, i32, i32, dp, dbl, dp, dp, dp, i32, vp]
@@ -166,19 +167,27 @@ class Batch:
             pass
 
     # state access: muState() / Pk (Usckf.hpp:518-526, Msckf.hpp:376-395)
-    def set_state(self, mu, P):
+    def set_state(self, mu, P, replicate=False):
+        """Upload means / covariances.  With replicate=True only the first len(mu) instances are given and
+        the rest of the batch is filled with copies (instance i <- i % len(mu))."""
         mu, P = _h(mu), _h(P)
-        assert mu.shape == (self.B, self.QD) and P.shape == (self.B, self.N, self.N), (mu.shape, P.shape)
+        k = mu.shape[0]
+        assert (k == self.B or replicate) and k <= self.B
+        assert mu.shape == (k, self.QD) and P.shape == (k, self.N, self.N), (mu.shape, P.shape)
         check(lib().slb_upload(self.h, FIELD_MU, _hp(mu), mu.size, _stream()))
         check(lib().slb_upload(self.h, FIELD_P, _hp(P), P.size, _stream()))
+        if k < self.B:
+            check(lib().slb_replicate(self.h, k, _stream()))
 
-    def mu(self):
-        out = np.empty((self.B, self.QD))
+    def mu(self, first=None):
+        k = self.B if first is None else first
+        out = np.empty((k, self.QD))
         check(lib().slb_download(self.h, FIELD_MU, _hp(out), out.size, _stream()))
         return out
 
-    def P(self):
-        out = np.empty((self.B, self.N, self.N))
+    def P(self, first=None):
+        k = self.B if first is None else first
+        out = np.empty((k, self.N, self.N))
         check(lib().slb_download(self.h, FIELD_P, _hp(out), out.size, _stream()))
         return out
 
