@@ -1,0 +1,111 @@
+"""GPU parity: localization::Msckf (BASELINE config 3: 10 clones, N=72, 50 features, m=100) through the
+C ABI vs the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from slam_localization_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def blocks(k):
+    return synth.STATE_BLOCKS + [0, 1] * k
+
+
+@pytest.mark.parametrize("pm", [engine.PM_MSCKF_DELTAPOSE, engine.PM_USCKF_TEST])
+def test_msckf_predict_parity(slo, pm):
+    B, k = 77, 10
+    sc = synth.msckf_scenario(B, seed=51, k=k)
+    u = sc["u"] if pm == engine.PM_MSCKF_DELTAPOSE else sc["u"][:, [0, 1, 2, 10, 11, 12]]
+    f = engine.Msckf(B, nclones=k)
+    f.set_state(sc["mu"], sc["P"])
+    f.predict(pm, u, 0.01, sc["Q"])
+    mu, P, st = slo.msckf_predict(pm, k, sc["mu"], sc["P"], u, 0.01, sc["Q"], nthreads=8)
+    assert not st.any() and not f.status().any()
+    parity.assert_parity(slo, blocks(k), f.mu(), f.P(), mu, parity.symmetrize_lower(P))
+    # cross blocks are left stale (quirk Q5): only the 12x12 corner may change
+    Pg = f.P()
+    np.testing.assert_array_equal(Pg[:, 12:, :], sc["P"][:, 12:, :])
+
+
+@pytest.mark.parametrize("k,nfeat", [(10, 50), (3, 6), (4, 7), (1, 1)])
+def test_msckf_update_parity_no_outliers(slo, k, nfeat):
+    B = 37
+    sc = synth.msckf_scenario(B, seed=52, k=k, nfeat=nfeat)
+    f = engine.Msckf(B, nclones=k)
+    f.set_state(sc["mu"], sc["P"])
+    f.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"], gate=False)
+    mu, P, out, st, _ = slo.msckf_update(slo.MM_MSCKF_REPROJ, k, sc["mu"], sc["P"], sc["landmarks"], sc["z"], sc["R"],
+                                        gate=False, nthreads=8)
+    assert not st.any() and not f.status().any()
+    parity.assert_parity(slo, blocks(k), f.mu(), f.P(), mu, P)
+    Pg = f.P()
+    assert np.array_equal(Pg, Pg.transpose(0, 2, 1)) and np.linalg.eigvalsh(Pg).min() > 0
+
+
+def test_msckf_update_with_outliers_matches_reference_quirk(slo):
+    """5% gross outliers: the per-feature 2-dof gate fires and rows are deleted with the reference's index
+    quirk (Q6: rows {2i, 2i+2}); the engine must delete the same rows and report the same count."""
+    B, k, nfeat = 64, 10, 50
+    sc = synth.msckf_scenario(B, seed=53, k=k, nfeat=nfeat, outlier_frac=0.05)
+    f = engine.Msckf(B, nclones=k)
+    f.set_state(sc["mu"], sc["P"])
+    f.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"], gate=True)
+    mu, P, out, st, _ = slo.msckf_update(slo.MM_MSCKF_REPROJ, k, sc["mu"], sc["P"], sc["landmarks"], sc["z"], sc["R"],
+                                        gate=True, nthreads=8)
+    assert out.sum() > 20
+    np.testing.assert_array_equal(f.outliers(), out)
+    ok = st == 0
+    assert ok.sum() > B // 2
+    np.testing.assert_array_equal(f.status()[ok], 0)
+    parity.assert_parity(slo, blocks(k), f.mu(), f.P(), mu, P, mask=ok)
+
+
+def test_msckf_golden_fixture(slo):
+    g = np.load(os.path.join(G, "msckf_k10_f50.npz"))
+    B = g["mu0"].shape[0]
+    f = engine.Msckf(B, nclones=10)
+    f.set_state(g["mu0"], g["P0"])
+    f.predict(engine.PM_MSCKF_DELTAPOSE, g["u"], 0.0, g["Q"])
+    parity.assert_parity(slo, blocks(10), f.mu(), f.P(), g["mu_pred"], parity.symmetrize_lower(g["P_pred"]))
+    f.set_state(g["mu0"], g["P0"])
+    f.update(engine.MM_MSCKF_REPROJ, g["landmarks"], g["z"], g["R"], gate=True)
+    parity.assert_parity(slo, blocks(10), f.mu(), f.P(), g["mu_upd"], g["P_upd"])
+    np.testing.assert_array_equal(f.outliers(), g["outliers"])
+
+
+def test_msckf_indefinite_covariance_is_flagged():
+    B, k = 8, 10
+    sc = synth.msckf_scenario(B, seed=54, k=k)
+    P = sc["P"].copy()
+    P[3, 20, 20] = -1.0
+    f = engine.Msckf(B, nclones=k)
+    f.set_state(sc["mu"], P)
+    f.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"])
+    st = f.status()
+    assert st[3] & engine.ST_CHOL_FAIL and not st[[0, 1, 2, 4, 5, 6, 7]].any()
+    np.testing.assert_array_equal(f.mu()[3], sc["mu"][3])
+
+
+def test_msckf_full_size_properties():
+    """16,384 instances (BASELINE config 3): batch results are independent of the batch (instance i equals
+    instance i run in a small batch, bit for bit), covariances stay symmetric PSD, status clean."""
+    B, k = 16384, 10
+    sc = synth.msckf_scenario(512, seed=55, k=k)
+    rep = B // 512
+    f = engine.Msckf(B, nclones=k)
+    f.set_state(sc["mu"], sc["P"], replicate=True)
+    f.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], np.tile(sc["z"], (rep, 1)), sc["R"])
+    assert sum(f.status_counts()) == 0
+    g = engine.Msckf(512, nclones=k)
+    g.set_state(sc["mu"], sc["P"])
+    g.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"])
+    mu, P = f.mu(), f.P()
+    for r in (0, 13, rep - 1):
+        np.testing.assert_array_equal(mu[r * 512:(r + 1) * 512], g.mu())
+        np.testing.assert_array_equal(P[r * 512:(r + 1) * 512], g.P())
+    assert np.linalg.eigvalsh(P[::257]).min() > 0
