@@ -191,6 +191,12 @@ int slb_datamodel_addsub(int d, int64_t n, int sign, const double *x1, const dou
 int slb_datamodel_fuse_host(int d, int64_t n, const double *x1, const double *C1,
                             const double *x2, const double *C2, double *xo, double *Co);
 
+/* ---- device buffers for callers without a CUDA binding (cgo / JNI / ctypes, the C++ facade) ---- */
+int slb_dev_alloc(size_t bytes, void **dev);
+int slb_dev_free(void *dev);
+/* kind: 1 host->device, 2 device->host, 3 device->device; synchronises the stream for kind 2. */
+int slb_dev_copy(void *dst, const void *src, size_t bytes, int kind, void *stream);
+
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* counts[0..3] = instances with CHOL_FAIL / MEAN_NOCONV / GATE_REJECT / NONFINITE set. */
 int slb_status(slb_handle h, int64_t counts[4], void *stream);

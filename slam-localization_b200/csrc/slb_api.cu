@@ -548,6 +548,29 @@ int slb_datamodel_fuse_host(int d, int64_t n, const double *x1, const double *C1
     return rc;
 }
 
+// ---- device buffers ----------------------------------------------------------------------------------
+int slb_dev_alloc(size_t bytes, void **dev) {
+    if (!dev) return set_error(SLB_ERR_INVALID, "slb_dev_alloc: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_dev_alloc: no CUDA device (this engine has no CPU fallback)");
+    }
+    SLB_CUDA(cudaMalloc(dev, bytes ? bytes : 8));
+    return SLB_OK;
+}
+int slb_dev_free(void *dev) {
+    if (dev) SLB_CUDA(cudaFree(dev));
+    return SLB_OK;
+}
+int slb_dev_copy(void *dst, const void *src, size_t bytes, int kind, void *stream) {
+    if (!dst || !src) return set_error(SLB_ERR_INVALID, "slb_dev_copy: null argument");
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    SLB_CUDA(cudaMemcpyAsync(dst, src, bytes, k, S(stream)));
+    if (kind == 2) SLB_CUDA(cudaStreamSynchronize(S(stream)));
+    return SLB_OK;
+}
+
 // ---- diagnostics -------------------------------------------------------------------------------------
 int slb_status(slb_handle h, int64_t counts[4], void *stream) {
     if (!h || !counts) return set_error(SLB_ERR_INVALID, "slb_status: null argument");

@@ -1,0 +1,103 @@
+// facade_test.cpp -- the reference's own test flows (test/DataModelUnitTest.cpp:30-67,
+// test/UKFoMUnitTest.cpp:93-117, test/UsckfUnitTest.cpp:175-284, test/MsckfUnitTest.cpp:151-213)
+// re-written against the host C++ facade.  Prints `key v0 v1 ...` lines that tests/test_facade.py
+// compares with the CPU oracle.  Exits 3 with "NO_DEVICE" when there is no GPU (no CPU fallback).
+#include <cmath>
+#include <cstdio>
+
+#include "../slam-localization_b200/facade/localization_b200.hpp"
+
+using namespace slb200;
+
+static void print(const char *key, const Vec &v, size_t n) {
+    std::printf("%s", key);
+    for (size_t i = 0; i < n && i < v.size(); ++i) std::printf(" %.17g", v[i]);
+    std::printf("\n");
+}
+
+int main() {
+    try {
+        const double D2R = M_PI / 180.0;
+        {   // DATAMODEL
+            DataModel<3> data1, data2;
+            data1.data = {0.0124889, 0.00171945, -0.0138983};
+            data2.data = {0.0168381, 0.000632167, -0.0235605};
+            DataModel<3> data3 = data1 + data2;
+            print("dm_plus_x", data3.data, 3);
+            print("dm_plus_C", data3.Cov, 9);
+            data3 = data1 - data2;
+            print("dm_minus_x", data3.data, 3);
+            print("dm_minus_C", data3.Cov, 9);
+            data3 = data1;
+            data3.fusion(data2);
+            print("dm_fusion_x", data3.data, 3);
+            print("dm_fusion_C", data3.Cov, 9);
+        }
+        {   // UKFOM
+            Vec mu0 = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0}, P0(81, 0.0), Q(81, 0.0), R(9, 0.0);
+            for (int i = 0; i < 9; ++i) P0[i * 9 + i] = 0.001;
+            const double dt = 0.01;
+            for (int i = 3; i < 6; ++i) Q[i * 9 + i] = 0.0001 * dt;
+            for (int i = 6; i < 9; ++i) Q[i * 9 + i] = 0.0002 * dt;
+            for (int i = 0; i < 3; ++i) R[i * 3 + i] = 0.00000001;
+            Ukf filter(1, SLB_LAYOUT_MTK9, mu0, P0);
+            Vec u = {0.0, 0.0, 0.0, 10.0 * D2R, 0.0, 0.0}, gps = {1.0, 0.0, 0.0};
+            filter.predict(SLB_PM_UKFOM_IMU_REFBUG, u, dt, Q);
+            filter.update(gps, SLB_MM_GPS_POS, R);
+            print("ukfom_mu", filter.mu(), 10);
+            print("ukfom_sigma", filter.sigma(), 81);
+        }
+        {   // USCKF_DYNAMIC
+            Vec single = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0}, P0(144, 0.0);
+            for (int i = 0; i < 12; ++i) P0[i * 12 + i] = 0.0025;
+            Usckf filter(1, 3, 9, single, P0, true);
+            Vec vo(3, 3.34), voC(9, 0.0), icp(9, 1.34), icpC(81, 0.0), vo2(3, 3.35), vo2C(9, 0.0);
+            for (int i = 0; i < 3; ++i) { voC[i * 3 + i] = 0.008; vo2C[i * 3 + i] = 0.05; }
+            for (int i = 0; i < 9; ++i) icpC[i * 9 + i] = 0.008;
+            filter.setMeasurement(STATEK, vo, voC);
+            filter.setMeasurement(STATEK_L, icp, icpC);
+            filter.setMeasurement(STATEK, vo2, vo2C);
+            const double dt = 0.01;
+            Vec Q(144, 0.0);
+            for (int i = 0; i < 12; ++i) Q[i * 12 + i] = 0.1 * dt;
+            Vec u = {100.0, 0.0, 0.0, 100.0 * D2R, 100.0 * D2R, 100.0 * D2R};
+            for (int i = 0; i < 2; ++i) {
+                filter.predict(SLB_PM_USCKF_TEST, u, dt, Q);
+                Vec Pi = filter.PkSingleState(STATEK_I);
+                double tr = 0;
+                for (int d = 0; d < 12; ++d) tr += Pi[d * 12 + d];
+                print("usckf_trace", Vec{tr}, 1);
+            }
+            print("usckf_mu", filter.muState(), 51);
+            Vec z = {2.33, 3.35, 3.35}, R(9, 0.0);
+            for (int i = 0; i < 3; ++i) R[i * 3 + i] = 0.01;
+            filter.update(z, SLB_MM_USCKF_VO, R);
+            std::printf("usckf_status %d\n", filter.status()[0]);
+        }
+        {   // MSCKF: ctor + two predicts with the delta-pose process model
+            const int k = 4, N = 12 + 6 * k, QD = 13 + 7 * k;
+            Vec mu(QD, 0.0), P((size_t)N * N, 0.0), Q(144, 0.0);
+            mu[3] = 1.0;
+            for (int c = 0; c < k; ++c) mu[13 + 7 * c + 3] = 1.0;
+            for (int i = 0; i < N; ++i) P[(size_t)i * N + i] = 0.025;
+            for (int i = 0; i < 12; ++i) Q[i * 12 + i] = 0.01;
+            Msckf filter(1, k, mu, P);
+            // delta orientation Rz(1 deg) Ry(1 deg) Rx(1 deg) as (w,x,y,z)
+            const double h = 0.5 * D2R, c = std::cos(h), s = std::sin(h);
+            Vec u = {0.1, 0.1, 0.1, c * c * c + s * s * s, s * c * c - c * s * s, c * s * c + s * c * s, c * c * s - s * s * c,
+                     0.1, 0.1, 0.1, 0.1, 0.1, 0.1};
+            for (int i = 0; i < 2; ++i) filter.predict(SLB_PM_MSCKF_DELTAPOSE, u, 0.0, Q);
+            print("msckf_mu", filter.muSingleState(), 13);
+            print("msckf_P", filter.getPkSingleState(), 144);
+        }
+        std::printf("OK\n");
+        return 0;
+    } catch (const Error &e) {
+        if (e.code == SLB_ERR_NO_DEVICE) {
+            std::printf("NO_DEVICE %s\n", e.what());
+            return 3;
+        }
+        std::printf("ERROR %d %s\n", e.code, e.what());
+        return 1;
+    }
+}
