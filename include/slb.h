@@ -178,6 +178,14 @@ int slb_msckf_predict(slb_handle h, int pm, const double *u_dev, double dt, cons
 int slb_msckf_update(slb_handle h, int mm, const double *params_dev, int m, const double *z_dev,
                      const double *R_dev, int gate, void *stream);
 
+/* predict + update with HOST buffers: u (batch x nu), z (batch x m) and the shared Q (12x12),
+ * params (nparams doubles), R (m x m) are copied to the device, both kernels run, the posterior
+ * q-vectors are copied back (mu_out_host: batch x qdim, may be NULL) and the stream is synchronised. */
+int slb_msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt,
+                        const double *Q_host, const double *params_host, int nparams, int m,
+                        const double *z_host, const double *R_host, int gate, double *mu_out_host,
+                        void *stream);
+
 /* ---- localization::DataModel<double,D> ---------------------------------------------------
  * fusion(data2) DataModel.hpp:48-60 over n independent pairs.  Instance-major device arrays:
  * x*: n x d, C*: n x d x d row-major.  d in {3, 6}.  Output may alias input 1 (in-place, like

@@ -280,7 +280,7 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->status, (size_t)h->B * 4);
     if (e == cudaSuccess) e = cudaMalloc(&h->outliers, (size_t)h->B * 4);
     if (e == cudaSuccess) e = cudaMalloc(&h->stage, h->stage_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&h->shared_small, 64 * 1024);
+    if (e == cudaSuccess) e = cudaMalloc(&h->shared_small, 128 * 1024);
     if (e == cudaSuccess) e = cudaMalloc(&h->counts_dev, 4 * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMemset(h->mu, 0, mu_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->P, 0, P_bytes);
@@ -508,6 +508,41 @@ int slb_msckf_update(slb_handle h, int mm, const double *params, int m, const do
     FilterArgs a = make_args(h);
     a.params = params; a.m = m; a.z = z; a.R = R; a.gate = gate;
     return launch_msckf_update(mm, a, S(stream));
+}
+
+// predict + update with HOST buffers (the end-to-end arm of bench.py): u | z staged on the device, the
+// posterior means copied back.  Q, R and the landmark parameters are small shared inputs.
+int slb_msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                        const double *params_host, int nparams, int m, const double *z_host, const double *R_host,
+                        int gate, double *mu_out_host, void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: handle is not an MSCKF batch");
+    if (!u_host || !Q_host || !params_host || !z_host || !R_host || m <= 0 || nparams <= 0)
+        return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: null argument");
+    cudaStream_t s = S(stream);
+    const int nu = pm_nu(pm);
+    const size_t ub = (size_t)h->B * nu * 8, zb = (size_t)h->B * m * 8, mub = (size_t)h->B * h->QD * 8;
+    const size_t small = (size_t)(144 + m * m + nparams) * 8;
+    if (ub + zb + mub > h->stage_bytes || small > 128 * 1024)
+        return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: batch / shared inputs too large for the staging buffers");
+    double *du = h->stage, *dz = du + (size_t)h->B * nu, *dmu = dz + (size_t)h->B * m;
+    double *dQ = h->shared_small, *dp = dQ + 144, *dR = dp + nparams;
+    SLB_CUDA(cudaMemcpyAsync(du, u_host, ub, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dz, z_host, zb, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dQ, Q_host, 144 * 8, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dp, params_host, (size_t)nparams * 8, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dR, R_host, (size_t)m * m * 8, cudaMemcpyHostToDevice, s));
+    int rc = slb_msckf_predict(h, pm, du, dt, dQ, stream);
+    if (rc == SLB_OK) rc = slb_msckf_update(h, mm, dp, m, dz, dR, gate, stream);
+    if (rc != SLB_OK) return rc;
+    if (mu_out_host) {
+        const int work = h->B * h->QD, tpb = 256;
+        rec_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, s>>>(h->mu, dmu, 0, h->B, h->QD, h->qstride);
+        count_launch();
+        SLB_CUDA(cudaGetLastError());
+        SLB_CUDA(cudaMemcpyAsync(mu_out_host, dmu, mub, cudaMemcpyDeviceToHost, s));
+    }
+    SLB_CUDA(cudaStreamSynchronize(s));
+    return SLB_OK;
 }
 
 // ---- localization::DataModel -------------------------------------------------------------------------

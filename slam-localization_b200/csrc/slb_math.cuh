@@ -34,23 +34,34 @@ typedef Layout<4, 0x2> LayState12;  // pos, orient, velo, angvelo       (State)
 SLB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
 
 // ---- SO3 -----------------------------------------------------------------------------------------
-// MTK cos_sinc_sqrt: cos(sqrt(x)), sin(sqrt(x))/sqrt(x); 3-term Taylor pair below eps^(1/4).
+// Sigma-point deviations are small rotations, so exp / log almost always see small arguments.  Both
+// have a branch-free polynomial fast path (minimax fits, relative error < 5e-18 before rounding) that
+// replaces sqrt + sincos + div (exp) and sqrt + atan + 2 div (log) by ~15 DFMA; large arguments fall
+// back to the libm formulation of MTK.  Either path is within a few ulp of the CPU oracle's glibc
+// result -- far inside the 1e-9 parity tolerance.
+// 1/w for finite, normal, non-zero w: MUFU.RCP64H seed + two Newton steps (full double accuracy,
+// not correctly rounded; never used where the oracle comparison is bit-exact).
+SLB_DEV double rcp_fast(double w) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+    double e = fma(-w, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-w, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+// MTK cos_sinc_sqrt: c = cos(sqrt(x)), s = sin(sqrt(x))/sqrt(x)
 SLB_DEV void cos_sinc_sqrt(double x, double &c, double &s) {
-    const double taylor_n = 1.220703125e-4;  // sqrt(sqrt(DBL_EPSILON)) = 2^-13
-    if (x >= taylor_n) {
+    if (x < 1.0) {  // |rotation| < 2 rad
+        // minimax fits on [0, 1], Horner form
+        c = fma(fma(fma(fma(fma(fma(fma(fma(4.70967686713015879e-14, x, -1.14694398696376668e-11), x, 2.08767438008076401e-09), x, -2.75573191463304794e-07), x, 2.48015873013186193e-05), x, -1.38888888888883668e-03), x, 4.16666666666666644e-02), x, -5.00000000000000000e-01), x, 1.00000000000000000e+00);
+        s = fma(fma(fma(fma(fma(fma(fma(-7.53548806448761316e-13, x, 1.60572333370398622e-10), x, -2.50520930836997243e-08), x, 2.75573191523091937e-06), x, -1.98412698410874757e-04), x, 8.33333333333310597e-03), x, -1.66666666666666657e-01), x, 1.00000000000000000e+00);
+    } else {
         const double sx = sqrt(x);
         double sn, cs;
         sincos(sx, &sn, &cs);
         c = cs;
         s = sn / sx;
-    } else {
-        double cosi = 1.0, sinc = 1.0;
-        double term = -0.5 * x;
-        cosi += term; term *= (1.0 / 3.0); sinc += term; term *= -(1.0 / 4.0) * x;
-        cosi += term; term *= (1.0 / 5.0); sinc += term; term *= -(1.0 / 6.0) * x;
-        cosi += term; term *= (1.0 / 7.0); sinc += term;
-        c = cosi;
-        s = sinc;
     }
 }
 // exp(v, scale): (w,x,y,z) of a rotation by scale*|v| about v/|v|
@@ -64,9 +75,19 @@ SLB_DEV void so3_exp(const double v[3], double scale, double q[4]) {
 }
 // log(q) = 2 atan(|qv|/qw)/|qv| qv   (atan: +-q identified; |qv| clamped at 1e-11)
 SLB_DEV void so3_log(const double q[4], double v[3]) {
-    double nv = sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    nv = nv < 1e-11 ? 1e-11 : nv;
-    const double s = 2.0 / nv * atan(nv / q[0]);
+    const double nv2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const double w = q[0];
+    double s;
+    if (nv2 <= 0.16 * (w * w)) {  // |qv|/|qw| <= 0.4: rotation below ~43 degrees
+        // 2 atan(t)/(t |qw|) sign(qw) = (2/qw) f(t^2),  f(x) = atan(sqrt x)/sqrt x
+        const double r = rcp_fast(w);
+        const double x = nv2 * (r * r);  // minimax fit of f on [0, 0.16], Horner form
+        s = (r + r) * fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(-1.88731700307688370e-02, x, 3.88960642020704864e-02), x, -5.07008289291807218e-02), x, 5.85429330706751586e-02), x, -6.66392574614696059e-02), x, 7.69212730997153177e-02), x, -9.09090122859413791e-02), x, 1.11111108929975527e-01), x, -1.42857142821344346e-01), x, 1.99999999999695866e-01), x, -3.33333333333332316e-01), x, 1.00000000000000000e+00);
+    } else {
+        double nv = sqrt(nv2);
+        nv = nv < 1e-11 ? 1e-11 : nv;
+        s = 2.0 / nv * atan(nv / w);
+    }
     v[0] = s * q[1]; v[1] = s * q[2]; v[2] = s * q[3];
 }
 SLB_DEV void quat_mul(const double a[4], const double b[4], double o[4]) {

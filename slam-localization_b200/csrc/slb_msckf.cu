@@ -339,9 +339,11 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         for (int e = tid; e < QD; e += MS_T) ref[e] = RB[e];
         if (tid == 0) flags[4] = 0;
         __syncthreads();
+        // per-warp partial sums go to region C (Y is dead) and are added in warp order: the result of an
+        // instance must not depend on scheduling (bitwise reproducible across batch sizes and GPUs)
+        double *part = RC;
+        const int nwa = (NS + 31) / 32;
         while (true) {
-            for (int e = tid; e < N; e += MS_T) acc[e] = 0.0;
-            __syncthreads();
             for (int b = 0; b < NB; ++b) {
                 double d[3] = {0.0, 0.0, 0.0};
                 if (tid < NS) {
@@ -355,13 +357,19 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                         d[0] = X[qo] - ref[qo]; d[1] = X[qo + 1] - ref[qo + 1]; d[2] = X[qo + 2] - ref[qo + 2];
                     }
                 }
-                if (warp * 32 < NS) {
+                if (warp < nwa) {
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         const double s = warp_sum(d[r]);
-                        if (lane == 0) atomicAdd(acc + 3 * b + r, s);
+                        if (lane == 0) part[warp * MS_NMAX + 3 * b + r] = s;
                     }
                 }
+            }
+            __syncthreads();
+            if (tid < N) {
+                double s = 0.0;
+                for (int w2 = 0; w2 < nwa; ++w2) s += part[w2 * MS_NMAX + tid];
+                acc[tid] = s;
             }
             __syncthreads();
             if (tid < NB) {

@@ -28,6 +28,7 @@ EXPORTS = [
     "slb_usckf_set_measurement", "slb_msckf_predict", "slb_msckf_update", "slb_datamodel_fuse",
     "slb_datamodel_addsub", "slb_datamodel_fuse_host", "slb_status", "slb_clear_status", "slb_ensemble_stats",
     "slb_launch_count", "slb_bench_fp64_peak", "slb_replicate", "slb_dev_alloc", "slb_dev_free", "slb_dev_copy",
+    "slb_msckf_step_host",
 ]
 
 
@@ -73,6 +74,7 @@ def lib():
         L.slb_usckf_set_measurement.argtypes = [vp, i32, dp, dp, vp]
         L.slb_msckf_predict.argtypes = [vp, i32, dp, dbl, dp, vp]
         L.slb_msckf_update.argtypes = [vp, i32, dp, i32, dp, dp, i32, vp]
+        L.slb_msckf_step_host.argtypes = [vp, i32, i32, dp, dbl, dp, dp, i32, i32, dp, dp, i32, dp, vp]
         L.slb_datamodel_fuse.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp, vp]
         L.slb_datamodel_addsub.argtypes = [i32, i64, i32, dp, dp, dp, dp, dp, dp, vp]
         L.slb_datamodel_fuse_host.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp]
@@ -283,6 +285,14 @@ class Msckf(Batch):
         params, z, R = dev(params), dev(z), dev(R)
         m = z.t.shape[1]
         check(lib().slb_msckf_update(self.h, mm, params.ptr, m, z.ptr, R.ptr, int(gate), _stream()))
+
+    def step_host(self, pm, mm, u, dt, Q, params, z, R, gate=True, mu_out=None):
+        """predict + update with HOST arrays (numpy or pinned torch); fills the posterior means."""
+        m = z.shape[1]
+        nparams = int(np.prod(params.shape))
+        check(lib().slb_msckf_step_host(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(params), nparams, m,
+                                        _ptr_of(z), _ptr_of(R), int(gate),
+                                        _ptr_of(mu_out) if mu_out is not None else None, _stream()))
 
 
 def _ptr_of(a):
