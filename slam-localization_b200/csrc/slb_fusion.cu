@@ -18,14 +18,25 @@
 
 namespace slbd {
 
-// Eigen PartialPivLU inverse restated (oracle/slo_core.hpp inverse_lu), rows swapped with
-// predicated moves so everything stays in registers.
-template <int D>
-SLB_DEV void inverse_lu(const double *A, double *X) {
-    double LU[D * D];
+// IEEE-rounded a / d from r = RN(1/d): q0 = RN(a r), exact remainder by FMA, one correction (Markstein:
+// with a correctly rounded reciprocal the corrected quotient is the correctly rounded a/d for normal,
+// non-overflowing operands -- the same final step div.rn.f64 itself performs).  An LU inverse divides by
+// each pivot 2D-1-k times, so the reciprocal (the expensive part of a division) is computed once per pivot.
+SLB_DEV double div_by(double a, double d, double r) {
+    const double q = __dmul_rn(a, r);
+    const double rem = __fma_rn(-d, q, a);
+    return __fma_rn(rem, r, q);
+}
+
+// Eigen PartialPivLU inverse restated (oracle/slo_core.hpp inverse_lu): same pivot choice, same
+// operation order, no FMA contraction, so the result is bit-identical to the CPU oracle.  Rows are
+// swapped with predicated moves so LU stays in registers; each finished column of the inverse is handed
+// to `sink(col, x)` instead of being kept (the caller stores or accumulates it), which keeps the live
+// state at LU + two D-vectors.
+template <int D, class Sink>
+SLB_DEV void inverse_lu_cols(double *LU, Sink sink) {
     int perm[D];
-#pragma unroll
-    for (int e = 0; e < D * D; ++e) LU[e] = A[e];
+    double rd[D];  // RN(1 / U_kk)
 #pragma unroll
     for (int i = 0; i < D; ++i) perm[i] = i;
 #pragma unroll
@@ -33,49 +44,65 @@ SLB_DEV void inverse_lu(const double *A, double *X) {
         int piv = k;
         double best = fabs(LU[k * D + k]);
 #pragma unroll
-        for (int i = k + 1; i < D; ++i) {
-            const double v = fabs(LU[i * D + k]);
-            if (v > best) { best = v; piv = i; }
+        for (int i = 0; i < D; ++i) {
+            if (i > k) {
+                const double v = fabs(LU[i * D + k]);
+                if (v > best) { best = v; piv = i; }
+            }
         }
 #pragma unroll
-        for (int i = k + 1; i < D; ++i) {
-            if (piv == i) {
+        for (int i = 0; i < D; ++i) {
+            if (i > k) {
+                const bool sw = piv == i;
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    const double t = LU[k * D + j];
-                    LU[k * D + j] = LU[i * D + j];
-                    LU[i * D + j] = t;
+                    const double t = LU[k * D + j], u = LU[i * D + j];
+                    LU[k * D + j] = sw ? u : t;
+                    LU[i * D + j] = sw ? t : u;
                 }
-                const int tp = perm[k]; perm[k] = perm[i]; perm[i] = tp;
+                const int tp = perm[k], up = perm[i];
+                perm[k] = sw ? up : tp;
+                perm[i] = sw ? tp : up;
             }
         }
         const double d = LU[k * D + k];
+        const double r = __drcp_rn(d);
+        rd[k] = r;
 #pragma unroll
-        for (int i = k + 1; i < D; ++i) LU[i * D + k] = LU[i * D + k] / d;
+        for (int i = 0; i < D; ++i)
+            if (i > k) LU[i * D + k] = div_by(LU[i * D + k], d, r);
 #pragma unroll
-        for (int i = k + 1; i < D; ++i) {
-            const double lik = LU[i * D + k];
+        for (int i = 0; i < D; ++i) {
+            if (i > k) {
+                const double lik = LU[i * D + k];
 #pragma unroll
-            for (int j = k + 1; j < D; ++j) LU[i * D + j] = LU[i * D + j] - lik * LU[k * D + j];
+                for (int j = 0; j < D; ++j)
+                    if (j > k) LU[i * D + j] = LU[i * D + j] - lik * LU[k * D + j];
+            }
         }
     }
-#pragma unroll
+    // one column at a time (rolled): the six solves unrolled side by side need > 200 registers, and the
+    // kernel is HBM-bound, so the shorter schedule buys nothing
+#pragma unroll 1
     for (int col = 0; col < D; ++col) {
-        double y[D];
+        double y[D], x[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             double s = (perm[i] == col) ? 1.0 : 0.0;
 #pragma unroll
-            for (int p = 0; p < i; ++p) s = s - LU[i * D + p] * y[p];
+            for (int p = 0; p < D; ++p)
+                if (p < i) s = s - LU[i * D + p] * y[p];
             y[i] = s;
         }
 #pragma unroll
         for (int i = D - 1; i >= 0; --i) {
             double s = y[i];
 #pragma unroll
-            for (int p = i + 1; p < D; ++p) s = s - LU[i * D + p] * X[p * D + col];
-            X[i * D + col] = s / LU[i * D + i];
+            for (int p = 0; p < D; ++p)
+                if (p > i) s = s - LU[i * D + p] * x[p];
+            x[i] = div_by(s, LU[i * D + i], rd[i]);
         }
+        sink(col, x);
     }
 }
 
@@ -93,20 +120,28 @@ SLB_DEV void inverse_3x3(const double *A, double *C) {
 #undef SLB_COF
 }
 
+// v[col] for a runtime col without indexing the register array (that would spill it to local memory)
 template <int D>
-SLB_DEV void inverse_fixed(const double *A, double *X) {
-    if (D == 3) inverse_3x3(A, X);
-    else inverse_lu<D>(A, X);
+SLB_DEV double pick(const double *v, int col) {
+    double r = v[0];
+#pragma unroll
+    for (int i = 1; i < D; ++i) r = (col == i) ? v[i] : r;
+    return r;
 }
 
-template <int D>
-SLB_DEV void matvec(const double *A, const double *x, double *y) {
+// inverse of the DxD matrix held row-major in registers A (destroyed for D > 3); columns go to sink
+template <int D, class Sink>
+SLB_DEV void inverse_fixed_cols(double *A, Sink sink) {
+    if (D == 3) {
+        double X[9];
+        inverse_3x3(A, X);
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) s = s + A[i * D + j] * x[j];
-        y[i] = s;
+        for (int col = 0; col < 3; ++col) {
+            const double x[3] = {X[col], X[3 + col], X[6 + col]};
+            sink(col, x);
+        }
+    } else {
+        inverse_lu_cols<D>(A, sink);
     }
 }
 
@@ -159,40 +194,72 @@ __global__ void __launch_bounds__(FUSE_WARPS * 32) datamodel_kernel(int64_t n, c
                 cp_async8(s2 + r * RS + c, g2 + e);
             }
         }
-        double A[DD], Bm[DD], a[D], b[D], xr[D];
+        double a[D], b[D], xr[D];
         const bool act = lane < cnt;
         if (act) {
 #pragma unroll
-            for (int e = 0; e < D; ++e) { a[e] = x1[(base + lane) * D + e]; b[e] = x2[(base + lane) * D + e]; }
+            for (int e = 0; e < D; ++e) a[e] = x1[(base + lane) * D + e];
+            if (OP != 0) {
+#pragma unroll
+                for (int e = 0; e < D; ++e) b[e] = x2[(base + lane) * D + e];
+            }
         }
         cp_async_wait_all();
         __syncwarp();
+        double *r1 = s1 + lane * RS, *r2 = s2 + lane * RS;  // this lane's padded rows
         if (act) {
-#pragma unroll
-            for (int e = 0; e < DD; ++e) { A[e] = s1[lane * RS + e]; Bm[e] = s2[lane * RS + e]; }
             if (OP == 0) {
-                double I1[DD], I2[DD], Sm[DD], ya[D], yb[D], ys[D];
-                inverse_fixed<D>(A, I1);
-                inverse_fixed<D>(Bm, I2);
+                // fusion (DataModel.hpp:48-60) in the oracle's order: I1 = C1^-1, I2 = C2^-1, P = (I1 + I2)^-1,
+                // x = P (I1 x1 + I2 x2).  The mat-vecs accumulate column by column as the inverses are produced
+                // (the same left-to-right sums as a row-wise mat-vec), I1 and I1 + I2 are parked in the row of C1.
+                double M[DD], ya[D], yb[D];
 #pragma unroll
-                for (int e = 0; e < DD; ++e) Sm[e] = I1[e] + I2[e];
-                inverse_fixed<D>(Sm, A);  // A <- P
-                matvec<D>(I1, a, ya);
-                matvec<D>(I2, b, yb);
+                for (int e = 0; e < DD; ++e) M[e] = r1[e];
 #pragma unroll
-                for (int e = 0; e < D; ++e) ys[e] = ya[e] + yb[e];
-                matvec<D>(A, ys, xr);
+                for (int i = 0; i < D; ++i) ya[i] = 0.0;
+                inverse_fixed_cols<D>(M, [&](int col, const double *x) {
+                    const double ac = pick<D>(a, col);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        r1[i * D + col] = x[i];
+                        ya[i] = ya[i] + x[i] * ac;
+                    }
+                });
+#pragma unroll
+                for (int e = 0; e < DD; ++e) M[e] = r2[e];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {  // x2 is fetched only now: fewer live registers during inverse 1
+                    yb[i] = 0.0;
+                    b[i] = x2[(base + lane) * D + i];
+                }
+                inverse_fixed_cols<D>(M, [&](int col, const double *x) {
+                    const double bc = pick<D>(b, col);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        r1[i * D + col] = r1[i * D + col] + x[i];
+                        yb[i] = yb[i] + x[i] * bc;
+                    }
+                });
+#pragma unroll
+                for (int e = 0; e < DD; ++e) M[e] = r1[e];
+#pragma unroll
+                for (int i = 0; i < D; ++i) { ya[i] = ya[i] + yb[i]; xr[i] = 0.0; }
+                inverse_fixed_cols<D>(M, [&](int col, const double *x) {
+                    const double yc = pick<D>(ya, col);
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        r1[i * D + col] = x[i];
+                        xr[i] = xr[i] + x[i] * yc;
+                    }
+                });
             } else {
 #pragma unroll
-                for (int e = 0; e < DD; ++e) A[e] = A[e] + Bm[e];  // operator- ALSO adds (:149)
+                for (int e = 0; e < DD; ++e) r1[e] = r1[e] + r2[e];  // operator- ALSO adds (:149)
 #pragma unroll
                 for (int e = 0; e < D; ++e) xr[e] = OP > 0 ? a[e] + b[e] : a[e] - b[e];
             }
         }
-        __syncwarp();
         if (act) {
-#pragma unroll
-            for (int e = 0; e < DD; ++e) s1[lane * RS + e] = A[e];
 #pragma unroll
             for (int e = 0; e < D; ++e) xo[(base + lane) * D + e] = xr[e];
         }

@@ -53,9 +53,19 @@ SLB_DEV double rcp_fast(double w) {
 // MTK cos_sinc_sqrt: c = cos(sqrt(x)), s = sin(sqrt(x))/sqrt(x)
 SLB_DEV void cos_sinc_sqrt(double x, double &c, double &s) {
     if (x < 1.0) {  // |rotation| < 2 rad
-        // minimax fits on [0, 1], Horner form
-        c = fma(fma(fma(fma(fma(fma(fma(fma(4.70967686713015879e-14, x, -1.14694398696376668e-11), x, 2.08767438008076401e-09), x, -2.75573191463304794e-07), x, 2.48015873013186193e-05), x, -1.38888888888883668e-03), x, 4.16666666666666644e-02), x, -5.00000000000000000e-01), x, 1.00000000000000000e+00);
-        s = fma(fma(fma(fma(fma(fma(fma(-7.53548806448761316e-13, x, 1.60572333370398622e-10), x, -2.50520930836997243e-08), x, 2.75573191523091937e-06), x, -1.98412698410874757e-04), x, 8.33333333333310597e-03), x, -1.66666666666666657e-01), x, 1.00000000000000000e+00);
+        // minimax fits on [0, 1], Estrin form (short dependency chains: the kernels are latency-, not issue-bound)
+        const double cx2 = x * x;
+        const double ct1_0 = fma(fma(-1.38888888888883668e-03, x, 4.16666666666666644e-02), cx2, fma(-5.00000000000000000e-01, x, 1.00000000000000000e+00));
+        const double ct1_1 = fma(fma(-1.14694398696376668e-11, x, 2.08767438008076401e-09), cx2, fma(-2.75573191463304794e-07, x, 2.48015873013186193e-05));
+        const double cx4 = cx2 * cx2;
+        const double ct2_0 = fma(ct1_1, cx4, ct1_0);
+        const double cx8 = cx4 * cx4;
+        const double ct3_0 = fma(4.70967686713015879e-14, cx8, ct2_0);
+        const double st1_0 = fma(fma(-1.98412698410874757e-04, x, 8.33333333333310597e-03), cx2, fma(-1.66666666666666657e-01, x, 1.00000000000000000e+00));
+        const double st1_1 = fma(fma(-7.53548806448761316e-13, x, 1.60572333370398622e-10), cx2, fma(-2.50520930836997243e-08, x, 2.75573191523091937e-06));
+        const double st2_0 = fma(st1_1, cx4, st1_0);
+        c = ct3_0;
+        s = st2_0;
     } else {
         const double sx = sqrt(x);
         double sn, cs;
@@ -81,8 +91,16 @@ SLB_DEV void so3_log(const double q[4], double v[3]) {
     if (nv2 <= 0.16 * (w * w)) {  // |qv|/|qw| <= 0.4: rotation below ~43 degrees
         // 2 atan(t)/(t |qw|) sign(qw) = (2/qw) f(t^2),  f(x) = atan(sqrt x)/sqrt x
         const double r = rcp_fast(w);
-        const double x = nv2 * (r * r);  // minimax fit of f on [0, 0.16], Horner form
-        s = (r + r) * fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(fma(-1.88731700307688370e-02, x, 3.88960642020704864e-02), x, -5.07008289291807218e-02), x, 5.85429330706751586e-02), x, -6.66392574614696059e-02), x, 7.69212730997153177e-02), x, -9.09090122859413791e-02), x, 1.11111108929975527e-01), x, -1.42857142821344346e-01), x, 1.99999999999695866e-01), x, -3.33333333333332316e-01), x, 1.00000000000000000e+00);
+        const double x = nv2 * (r * r);  // minimax fit of f on [0, 0.16], Estrin form
+        const double ax2 = x * x;
+        const double at1_0 = fma(fma(-1.42857142821344346e-01, x, 1.99999999999695866e-01), ax2, fma(-3.33333333333332316e-01, x, 1.00000000000000000e+00));
+        const double at1_1 = fma(fma(-6.66392574614696059e-02, x, 7.69212730997153177e-02), ax2, fma(-9.09090122859413791e-02, x, 1.11111108929975527e-01));
+        const double at1_2 = fma(fma(-1.88731700307688370e-02, x, 3.88960642020704864e-02), ax2, fma(-5.07008289291807218e-02, x, 5.85429330706751586e-02));
+        const double ax4 = ax2 * ax2;
+        const double at2_0 = fma(at1_1, ax4, at1_0);
+        const double ax8 = ax4 * ax4;
+        const double at3_0 = fma(at1_2, ax8, at2_0);
+        s = (r + r) * at3_0;
     } else {
         double nv = sqrt(nv2);
         nv = nv < 1e-11 ? 1e-11 : nv;
@@ -194,11 +212,12 @@ SLB_DEV void sym3_inverse(const double *S, double *Si) {
 }
 
 SLB_DEV bool chi2_accept(double m2, int dof) {
-    // 5% table, Usckf.hpp:794-855; dof 0 = accept_any_mahalanobis_distance
+    // 5% table, Usckf.hpp:794-855; dof 0 = accept_any_mahalanobis_distance; other dof reject.
+    // (select chain, not an indexed array: a runtime-indexed table would live in local memory)
     if (dof == 0) return true;
-    const double th[10] = {0, 3.84, 5.99, 7.81, 9.49, 11.07, 12.59, 14.07, 15.51, 16.92};
-    if (dof < 1 || dof > 9) return false;
-    return m2 < th[dof];
+    const double th = dof == 1 ? 3.84 : dof == 2 ? 5.99 : dof == 3 ? 7.81 : dof == 4 ? 9.49 : dof == 5 ? 11.07
+                    : dof == 6 ? 12.59 : dof == 7 ? 14.07 : dof == 8 ? 15.51 : dof == 9 ? 16.92 : -1.0;
+    return m2 < th;
 }
 
 }  // namespace slbd

@@ -1,4 +1,4 @@
-// slb_ukf.cu -- ukfom::ukf<state> predict / update / fused step, one filter instance per thread.
+// slb_ukf.cu -- ukfom::ukf<state> predict / update / fused step, G lanes per filter instance.
 //
 // Replaces (per instance) ukfom::ukf::predict / update / apply_delta as exercised at
 // test/UKFoMUnitTest.cpp:104-117, whose skeleton is the single-state path of Msckf.hpp
@@ -6,365 +6,482 @@
 // :668-675 applyDelta).
 //
 // Mapping (see DESIGN.md "UKF kernel"):
-//   * state is SoA in HBM: mu[c][stride], P[e][stride] with P packed lower-triangular, so the 32
-//     lanes of a warp read 256 contiguous bytes per field;
-//   * mean and covariance live in registers (all loops over compile-time layouts are unrolled);
-//   * the 2n+1 propagated sigma points of one instance live in a private column of shared memory
-//     (element e of thread t at sm[e*TPB + t]: conflict-free), with the Cholesky factor parked in
-//     the not-yet-written tail of the same column;
+//   * G = 4 consecutive lanes own one instance, a warp owns 32/G = 8 instances and never talks to
+//     another warp (only __syncwarp / shuffles): the on-chip footprint of an instance (its 2n+1
+//     propagated sigma points, P, L) bounds how many instances an SM can hold (~100), so the lanes
+//     per instance -- not the instances -- supply the warps that hide FP64 latency;
+//   * state is SoA in HBM: mu[c][stride], P[e][stride] with P packed lower-triangular; a warp reads
+//     8 consecutive instances of G fields per load (64-byte segments);
+//   * sigma point s of an instance is handled by lane s % G: drawn from the Cholesky column, pushed
+//     through the model and parked in shared memory as Y[c][s] (component-major: the G lanes of a
+//     group touch consecutive doubles, groups sit 4 banks apart, so the traffic is conflict-free);
+//   * manifold mean: per-lane partial sums of X_s [-] ref, xor-shuffle inside the group, every lane
+//     applies the same [+]; covariance: per-lane 0.5 sum d d^T partials in registers, reduced through
+//     shared scratch in fixed lane order (bitwise reproducible whatever the batch size);
+//   * the 9x9 Cholesky runs redundantly on the G lanes in registers (same issue slots as one lane
+//     doing it, no exchange), pivots through MUFU.RSQ64H + Newton;
 //   * predict+update fused in one launch moves each instance through HBM exactly once.
 #include "slb_internal.h"
 #include "slb_models.cuh"
 
 namespace slbd {
 
-template <class L, int TPB>
-struct Col {
-    static constexpr int N = L::N, QD = L::QD, NP = L::NP, NS = 2 * L::N + 1;
-    static constexpr int NSQ = NS * QD;  // doubles per thread column
-    double *sm;
-    int tid;
-    SLB_DEV double &at(int e) const { return sm[e * TPB + tid]; }
-    // sigma point s, component c
-    SLB_DEV double &Y(int s, int c) const { return at(s * QD + c); }
-    // Cholesky factor, column-major packed from the END of the column (col N-1 last)
-    SLB_DEV double &Lt(int r, int j) const { return at(NSQ - (N - j) * (N - j + 1) / 2 + (r - j)); }
-};
+constexpr unsigned UKF_FULL = 0xffffffffu;
 
-// y = x [+] sign*d, knowing d[r] == 0 for r < j0 (column j0 of a lower-triangular factor)
-template <class L>
-SLB_DEV void boxplus_from(const double *x, const double *d, int j0, double sign, double *y) {
+template <int G>
+SLB_DEV double gsum(double v) {
 #pragma unroll
-    for (int b = 0; b < L::NB; ++b) {
-        const int o = L::qoff(b);
-        if (3 * b + 2 < j0) {
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(UKF_FULL, v, o);
+    return v;
+}
+
+// sqrt(x) and 1/sqrt(x) for x > 0 from the MUFU.RSQ64H seed and two Newton steps (full double
+// accuracy, ~1 ulp; not the IEEE-rounded sqrt/div pair of the CPU oracle -- parity is at 1e-9).
+SLB_DEV void sqrt_rsqrt(double x, double &s, double &rs) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    double r = x * y;
+    r = fma(fma(-r, r, x), 0.5 * y, r);
+    s = r;
+    rs = y;
+}
+
+// In-register packed Cholesky (lower, row-major packed), pivots through sqrt_rsqrt.  Every loop has the
+// constant trip count N with compile-time predicates: nvcc then unrolls all three levels and the
+// matrix stays in registers (data-dependent bounds left a rolled loop over a local-memory array).
+template <int N>
+SLB_DEV bool chol_packed_fast(double *A) {
+    bool ok = true;
 #pragma unroll
-            for (int i = 0; i < (L::so3(b) ? 4 : 3); ++i) y[o + i] = x[o + i];
-        } else if (L::so3(b)) {
-            const double v[3] = {sign * d[3 * b], sign * d[3 * b + 1], sign * d[3 * b + 2]};
-            double e[4];
-            so3_exp(v, 1.0, e);
-            quat_mul(x + o, e, y + o);
-        } else {
+    for (int k = 0; k < N; ++k) {
+        double x = A[tri(k, k)];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) y[o + i] = x[o + i] + sign * d[3 * b + i];
+        for (int p = 0; p < N; ++p)
+            if (p < k) x = fma(-A[tri(k, p)], A[tri(k, p)], x);
+        ok = ok && (x > 0.0);
+        double sx, inv;
+        sqrt_rsqrt(x, sx, inv);
+        A[tri(k, k)] = sx;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i > k) {
+                double s = A[tri(i, k)];
+#pragma unroll
+                for (int p = 0; p < N; ++p)
+                    if (p < k) s = fma(-A[tri(i, p)], A[tri(k, p)], s);
+                A[tri(i, k)] = s * inv;
+            }
         }
     }
+    return ok;
+}
+
+// Shared-memory record of one instance (doubles).  IS = G (mod 16) keeps the G-lane groups of a
+// half-warp on disjoint banks for the Y[c][s] accesses.
+template <class L, int M, int G>
+struct Rec {
+    static constexpr int N = L::N, QD = L::QD, NP = L::NP, NS = 2 * L::N + 1;
+    static constexpr int UPD_SCR = NS * M + 3 * N * M + N;  // Z | DZ | K | KS | delta
+    static constexpr int A0 = NS * QD > UPD_SCR ? NS * QD : UPD_SCR;
+    static constexpr int SIGSZ = A0 > G * NP ? A0 : G * NP;  // also the covariance reduction scratch
+    static constexpr int SIG = 0, LF = SIGSZ, PS = LF + NP, MU = PS + NP, FLAG = MU + QD;
+    static constexpr int RAW = FLAG + 1;
+    static constexpr int IS = RAW + ((G - RAW % 16) % 16 + 16) % 16;
+    // update scratch inside SIG
+    static constexpr int ZO = 0, DZO = NS * M, KO = DZO + N * M, KSO = KO + N * M, DLO = KSO + N * M;
+};
+
+// Cholesky of the packed P at `ps` into `lf` (both in this instance's record); every lane of the
+// group factors redundantly in registers, lane 0 of the group publishes.  Returns pivot success.
+template <int N>
+SLB_DEV bool group_chol(const double *ps, double *lf, int sub) {
+    constexpr int NP = N * (N + 1) / 2;
+    double A[NP];
+#pragma unroll
+    for (int e = 0; e < NP; ++e) A[e] = ps[e];
+    const bool ok = chol_packed_fast<N>(A);
+    if (sub == 0) {
+#pragma unroll
+        for (int e = 0; e < NP; ++e) lf[e] = A[e];
+    }
+    __syncwarp();
+    return ok;
+}
+
+// column j of the factor scaled by sgn (zero above the diagonal); s = 0 gives the zero vector
+template <int N>
+SLB_DEV void sigma_offset(const double *lf, int s, double *d) {
+    const int j = s >= 1 ? (s - 1) >> 1 : 0;
+    const double sgn = (s & 1) ? 1.0 : -1.0;
+#pragma unroll
+    for (int r = 0; r < N; ++r) d[r] = (s >= 1 && r >= j) ? sgn * lf[tri(r, j)] : 0.0;
 }
 
 // Msckf.hpp:471-496 / Usckf.hpp:601-627: reference = X0; do { d = mean(Xi [-] ref); ref [+]= d }
-// while (|d| > 1e-6 && ++i < 10000).  Returns false if the cap was hit.
-template <class L, int TPB>
-SLB_DEV bool manifold_mean(const Col<L, TPB> &col, double *ref) {
-    constexpr int N = L::N, QD = L::QD, NS = 2 * N + 1;
+// while (|d| > 1e-6 && ++i < 10000).  Sigma points in `sig` as Y[c*NS + s].  `go` = this group takes
+// part; groups of a warp that finish early idle through the remaining rounds.  Returns false when the
+// iteration cap was hit.
+template <class L, int G>
+SLB_DEV bool group_mean(const double *sig, int sub, bool go, double *ref) {
+    constexpr int N = L::N, QD = L::QD, NS = 2 * N + 1, ROUNDS = (NS + G - 1) / G;
 #pragma unroll
-    for (int c = 0; c < QD; ++c) ref[c] = col.Y(0, c);
+    for (int c = 0; c < QD; ++c) ref[c] = sig[c * NS];
     int it = 0;
-    double nrm2;
-    do {
+    while (__any_sync(UKF_FULL, go)) {
         double md[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) md[r] = 0.0;
 #pragma unroll 2
-        for (int s = 0; s < NS; ++s) {
-            double y[QD], d[N];
+        for (int t = 0; t < ROUNDS; ++t) {
+            const int s = sub + G * t;
+            if (s < NS) {
+                double y[QD], d[N];
 #pragma unroll
-            for (int c = 0; c < QD; ++c) y[c] = col.Y(s, c);
-            boxminus<L>(y, ref, d);
+                for (int c = 0; c < QD; ++c) y[c] = sig[c * NS + s];
+                boxminus<L>(y, ref, d);
 #pragma unroll
-            for (int r = 0; r < N; ++r) md[r] += d[r];
+                for (int r = 0; r < N; ++r) md[r] += d[r];
+            }
         }
-        nrm2 = 0.0;
+        double nrm2 = 0.0;
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-            md[r] = md[r] / (double)NS;
+            md[r] = gsum<G>(md[r]) / (double)NS;
             nrm2 += md[r] * md[r];
         }
         double nr[QD];
         boxplus<L>(ref, md, 1.0, nr);
+        if (go) {
 #pragma unroll
-        for (int c = 0; c < QD; ++c) ref[c] = nr[c];
-    } while (sqrt(nrm2) > 1e-6 && ++it < 10000);
+            for (int c = 0; c < QD; ++c) ref[c] = nr[c];
+            if (sqrt(nrm2) > 1e-6) {
+                ++it;
+                go = it < 10000;
+            } else {
+                go = false;
+            }
+        }
+    }
     return it < 10000;
 }
 
-// Msckf.hpp:554-570: 0.5 * sum (Yi [-] mean)(Yi [-] mean)^T, packed lower
-template <class L, int TPB>
-SLB_DEV void manifold_cov(const Col<L, TPB> &col, const double *mean, double *C) {
-    constexpr int N = L::N, QD = L::QD, NP = L::NP, NS = 2 * N + 1;
+// Msckf.hpp:554-570: P = 0.5 * sum (Yi [-] mean)(Yi [-] mean)^T (+ Qp), packed lower, written to `ps`.
+// `sig` is consumed: it becomes the reduction scratch.
+template <class L, int G, bool ADDQ>
+SLB_DEV void group_cov(double *sig, double *ps, const double *Qp, int sub, const double *mean) {
+    constexpr int N = L::N, QD = L::QD, NP = L::NP, NS = 2 * N + 1, ROUNDS = (NS + G - 1) / G;
+    double acc[NP];
 #pragma unroll
-    for (int e = 0; e < NP; ++e) C[e] = 0.0;
+    for (int e = 0; e < NP; ++e) acc[e] = 0.0;
 #pragma unroll 1
-    for (int s = 0; s < NS; ++s) {
-        double y[QD], d[N];
+    for (int t = 0; t < ROUNDS; ++t) {
+        const int s = sub + G * t;
+        if (s < NS) {
+            double y[QD], d[N];
 #pragma unroll
-        for (int c = 0; c < QD; ++c) y[c] = col.Y(s, c);
-        boxminus<L>(y, mean, d);
+            for (int c = 0; c < QD; ++c) y[c] = sig[c * NS + s];
+            boxminus<L>(y, mean, d);
 #pragma unroll
-        for (int i = 0; i < N; ++i)
+            for (int i = 0; i < N; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) C[tri(i, j)] += d[i] * d[j];
+                for (int j = 0; j <= i; ++j) acc[tri(i, j)] = fma(d[i], d[j], acc[tri(i, j)]);
+        }
     }
+    __syncwarp();  // every lane is done with the sigma points: the area becomes scratch
 #pragma unroll
-    for (int e = 0; e < NP; ++e) C[e] *= 0.5;
+    for (int e = 0; e < NP; ++e) sig[sub * NP + e] = acc[e];
+    __syncwarp();
+    for (int e = sub; e < NP; e += G) {
+        double v = sig[e];
+#pragma unroll
+        for (int l = 1; l < G; ++l) v += sig[l * NP + e];
+        v *= 0.5;
+        if (ADDQ) v += Qp[e];
+        ps[e] = v;
+    }
+    __syncwarp();
 }
 
-// Factor P (registers, destroyed) and park L in the column tail.
-template <class L, int TPB>
-SLB_DEV bool factor_to_tail(const Col<L, TPB> &col, double *P) {
-    constexpr int N = L::N;
-    const bool ok = chol_packed<N>(P);
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-        for (int r = j; r < N; ++r) col.Lt(r, j) = P[tri(r, j)];
-    return ok;
-}
-
-template <class L, int TPB>
-SLB_DEV void load_col(const Col<L, TPB> &col, int j, double *d) {
-#pragma unroll
-    for (int r = 0; r < L::N; ++r) d[r] = (r >= j) ? col.Lt(r < j ? j : r, j) : 0.0;
-}
-
-template <class L, int PM, class MM, int TPB, bool PRED, bool UPD>
-__global__ void __launch_bounds__(TPB) ukf_kernel(slb::FilterArgs a) {
+template <class L, int PM, class MM, int G, int TPB, int MINB, bool PRED, bool UPD>
+__global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
+    typedef Rec<L, MM::M, G> R;
     constexpr int N = L::N, QD = L::QD, NP = L::NP, NS = 2 * N + 1, M = MM::M, MP = M * (M + 1) / 2;
-    static_assert(NS * M + 2 * NP <= NS * QD, "column too small for the update scratch");
+    constexpr int IPW = 32 / G, WPB = TPB / 32, ROUNDS = (NS + G - 1) / G, RROWS = (N + G - 1) / G;
+    constexpr int WSZ = IPW * R::IS + NP;  // per-warp shared memory: IPW records + packed Q
+    static_assert(M == 3, "only 3-dof measurement models are wired to the UKF kernel");
     extern __shared__ double sm[];
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x * TPB + tid;
-    if (i >= a.B) return;
-    Col<L, TPB> col{sm, tid};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % G, grp = lane / G;
+    double *wsm = sm + (size_t)warp * WSZ;
+    double *rec = wsm + grp * R::IS;
+    double *Qp = wsm + IPW * R::IS;
+    const int wbase = (blockIdx.x * WPB + warp) * IPW;  // first instance of this warp
+    if (wbase >= a.B) return;
+    const int inst = wbase + grp;
+    const bool valid = inst < a.B;
 
-    double mu[QD], P[NP];
+    // ---- stage the 8 records of this warp: lane -> (instance lane % IPW, fields lane / IPW + G k) ----
+    {
+        const int li = lane % IPW, e0 = lane / IPW;
+        const bool lv = wbase + li < a.B;
+        double *dst = wsm + li * R::IS;
+#pragma unroll 4
+        for (int e = e0; e < QD + NP; e += G) {
+            double v = 0.0;
+            if (lv) v = e < QD ? a.mu[(size_t)e * a.stride + wbase + li] : a.P[(size_t)(e - QD) * a.stride + wbase + li];
+            dst[e < QD ? R::MU + e : R::PS + (e - QD)] = v;
+        }
+        if (PRED) {
+            for (int e = lane; e < NP; e += 32) {
+                int r = 0;
+                while (tri(r + 1, 0) <= e) ++r;
+                Qp[e] = __ldg(a.Q + r * N + (e - tri(r, 0)));
+            }
+        }
+    }
+    __syncwarp();
+    double *sig = rec + R::SIG, *lf = rec + R::LF, *ps = rec + R::PS;
+    if (!valid && sub == 0) {  // tail of the batch: a benign identity prior keeps the idle lanes finite
 #pragma unroll
-    for (int c = 0; c < QD; ++c) mu[c] = a.mu[(size_t)c * a.stride + i];
+        for (int r = 0; r < N; ++r) ps[tri(r, r)] = 1.0;
 #pragma unroll
-    for (int e = 0; e < NP; ++e) P[e] = a.P[(size_t)e * a.stride + i];
+        for (int b = 0; b < L::NB; ++b)
+            if (L::so3(b)) rec[R::MU + L::qoff(b)] = 1.0;
+    }
+    __syncwarp();
+    double mu[QD];
+#pragma unroll
+    for (int c = 0; c < QD; ++c) mu[c] = rec[R::MU + c];
     int st = 0;
-    bool alive = true;
+    bool alive = valid;
 
     if (PRED) {
         // ---- predict(g, Q): sigma points -> g -> manifold mean -> cov + Q ------------------------
-        if (!factor_to_tail(col, P)) { st |= SLB_ST_CHOL_FAIL; alive = false; }
-        if (alive) {
-            ProcessModel<PM> g;
-            {
-                double u[ProcessModel<PM>::NU];
+        if (!group_chol<N>(ps, lf, sub) && alive) { st |= SLB_ST_CHOL_FAIL; alive = false; }
+        ProcessModel<PM> g;
+        {
+            double u[ProcessModel<PM>::NU];
 #pragma unroll
-                for (int c = 0; c < ProcessModel<PM>::NU; ++c) u[c] = a.u[(size_t)i * ProcessModel<PM>::NU + c];
-                g.prepare(u, a.dt);
-            }
-            {
-                double y[QD];
-                g.apply(mu, y);
-#pragma unroll
-                for (int c = 0; c < QD; ++c) col.Y(0, c) = y[c];
-            }
-#pragma unroll 1
-            for (int j = 0; j < N; ++j) {
-                double d[N];
-                load_col(col, j, d);
-                double xp[QD], xm[QD], yp[QD], ym[QD];
-                boxplus_from<L>(mu, d, j, 1.0, xp);
-                boxplus_from<L>(mu, d, j, -1.0, xm);
-                g.apply(xp, yp);
-                g.apply(xm, ym);
-#pragma unroll
-                for (int c = 0; c < QD; ++c) { col.Y(1 + 2 * j, c) = yp[c]; col.Y(2 + 2 * j, c) = ym[c]; }
-            }
-            if (!manifold_mean(col, mu)) st |= SLB_ST_MEAN_NOCONV;
-            manifold_cov(col, mu, P);
-#pragma unroll
-            for (int r = 0; r < N; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c) P[tri(r, c)] += __ldg(a.Q + r * N + c);
+            for (int c = 0; c < ProcessModel<PM>::NU; ++c) u[c] = valid ? a.u[(size_t)inst * ProcessModel<PM>::NU + c] : 0.0;
+            g.prepare(u, a.dt);
         }
+#pragma unroll 1
+        for (int t = 0; t < ROUNDS; ++t) {
+            const int s = sub + G * t;
+            if (s < NS) {
+                double d[N], x[QD], y[QD];
+                sigma_offset<N>(lf, s, d);
+                boxplus<L>(mu, d, 1.0, x);
+                g.apply(x, y);
+#pragma unroll
+                for (int c = 0; c < QD; ++c) sig[c * NS + s] = y[c];
+            }
+        }
+        __syncwarp();
+        if (!group_mean<L, G>(sig, sub, alive, mu) && alive) st |= SLB_ST_MEAN_NOCONV;
+        group_cov<L, G, true>(sig, ps, Qp, sub, mu);
     }
 
-    if (UPD && alive) {
+    if (UPD) {
         // ---- update(z, h, R, mt) ----------------------------------------------------------------
-        constexpr int ZOFF = 0, PSOFF = NS * M;
+        if (!group_chol<N>(ps, lf, sub) && alive) { st |= SLB_ST_CHOL_FAIL; alive = false; }
+        double *Z = sig + R::ZO, *DZ = sig + R::DZO, *Ks = sig + R::KO, *KSs = sig + R::KSO, *DL = sig + R::DLO;
+        double zsum[M];
 #pragma unroll
-        for (int e = 0; e < NP; ++e) col.at(PSOFF + e) = P[e];  // stash P: needed for P -= K S K^T
-        if (!factor_to_tail(col, P)) { st |= SLB_ST_CHOL_FAIL; alive = false; }
-        if (alive) {
-            double zsum[M];
-            {
-                double z0[M];
-                MM::apply(mu, z0);
-#pragma unroll
-                for (int c = 0; c < M; ++c) { col.at(ZOFF + c) = z0[c]; zsum[c] = z0[c]; }
-            }
+        for (int c = 0; c < M; ++c) zsum[c] = 0.0;
 #pragma unroll 1
-            for (int j = 0; j < N; ++j) {
-                double d[N];
-                load_col(col, j, d);
-                double xp[QD], xm[QD], zp[M], zm[M];
-                boxplus_from<L>(mu, d, j, 1.0, xp);
-                boxplus_from<L>(mu, d, j, -1.0, xm);
-                MM::apply(xp, zp);
-                MM::apply(xm, zm);
+        for (int t = 0; t < ROUNDS; ++t) {
+            const int s = sub + G * t;
+            if (s < NS) {
+                double d[N], x[QD], z[M];
+                sigma_offset<N>(lf, s, d);
+                boxplus<L>(mu, d, 1.0, x);
+                MM::apply(x, z);
 #pragma unroll
-                for (int c = 0; c < M; ++c) {
-                    col.at(ZOFF + (1 + 2 * j) * M + c) = zp[c];
-                    col.at(ZOFF + (2 + 2 * j) * M + c) = zm[c];
-                    zsum[c] += zp[c];
-                    zsum[c] += zm[c];
-                }
+                for (int c = 0; c < M; ++c) { Z[c * NS + s] = z[c]; zsum[c] += z[c]; }
             }
-            double zbar[M];
+        }
+        double zbar[M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) zbar[c] = zsum[c] / (double)NS;
-            // S = 0.5 sum (Zi - zbar)(Zi - zbar)^T + R   (packed lower)
-            double S[MP];
+        for (int c = 0; c < M; ++c) zbar[c] = gsum<G>(zsum[c]) / (double)NS;
+        __syncwarp();
+        // S = 0.5 sum (Zi - zbar)(Zi - zbar)^T + R   (packed lower)
+        double S[MP];
 #pragma unroll
-            for (int e = 0; e < MP; ++e) S[e] = 0.0;
+        for (int e = 0; e < MP; ++e) S[e] = 0.0;
 #pragma unroll 1
-            for (int s = 0; s < NS; ++s) {
+        for (int t = 0; t < ROUNDS; ++t) {
+            const int s = sub + G * t;
+            if (s < NS) {
                 double dz[M];
 #pragma unroll
-                for (int c = 0; c < M; ++c) dz[c] = col.at(ZOFF + s * M + c) - zbar[c];
+                for (int c = 0; c < M; ++c) dz[c] = Z[c * NS + s] - zbar[c];
 #pragma unroll
                 for (int r = 0; r < M; ++r)
 #pragma unroll
                     for (int c = 0; c <= r; ++c) S[tri(r, c)] += dz[r] * dz[c];
             }
+        }
 #pragma unroll
-            for (int r = 0; r < M; ++r)
+        for (int r = 0; r < M; ++r)
 #pragma unroll
-                for (int c = 0; c <= r; ++c) S[tri(r, c)] = 0.5 * S[tri(r, c)] + __ldg(a.R + r * M + c);
-            // Pxz = 0.5 sum (Xi [-] mu)(Zi - zbar)^T.  Xi [-] mu is +-L e_j by construction (the
-            // reference recovers it through log(exp(.)), identical below |.| < pi), and the zbar terms
-            // of a +- pair cancel: Pxz = 0.5 sum_j L e_j (Z+_j - Z-_j)^T.
-            double Pxz[N * M];
+            for (int c = 0; c <= r; ++c) S[tri(r, c)] = 0.5 * gsum<G>(S[tri(r, c)]) + __ldg(a.R + r * M + c);
+        // Pxz = 0.5 sum (Xi [-] mu)(Zi - zbar)^T.  Xi [-] mu is +-L e_j by construction (the reference
+        // recovers it through log(exp(.)), identical below |.| < pi), and the zbar terms of a +- pair
+        // cancel: Pxz = 0.5 L DZ with DZ_j = Z+_j - Z-_j.
+        for (int j = sub; j < N; j += G) {
 #pragma unroll
-            for (int e = 0; e < N * M; ++e) Pxz[e] = 0.0;
-#pragma unroll 1
-            for (int j = 0; j < N; ++j) {
-                double d[N], dz[M];
-                load_col(col, j, d);
+            for (int c = 0; c < M; ++c) DZ[j * M + c] = (Z[c * NS + 1 + 2 * j] - zbar[c]) - (Z[c * NS + 2 + 2 * j] - zbar[c]);
+        }
+        __syncwarp();
+        double Si[MP];
+        sym3_inverse(S, Si);
+        auto SiAt = [&](int r, int c) { return r >= c ? Si[tri(r, c)] : Si[tri(c, r)]; };
+        auto SAt = [&](int r, int c) { return r >= c ? S[tri(r, c)] : S[tri(c, r)]; };
+        double innov[M], m2 = 0.0;
 #pragma unroll
-                for (int c = 0; c < M; ++c)
-                    dz[c] = (col.at(ZOFF + (1 + 2 * j) * M + c) - zbar[c]) - (col.at(ZOFF + (2 + 2 * j) * M + c) - zbar[c]);
+        for (int c = 0; c < M; ++c) innov[c] = (valid ? a.z[(size_t)inst * M + c] : 0.0) - zbar[c];
 #pragma unroll
-                for (int r = 0; r < N; ++r)
+        for (int r = 0; r < M; ++r) {
+            double s = 0.0;
 #pragma unroll
-                    for (int c = 0; c < M; ++c) Pxz[r * M + c] += d[r] * dz[c];
-            }
+            for (int c = 0; c < M; ++c) s += SiAt(r, c) * innov[c];
+            m2 += innov[r] * s;
+        }
+        // rows sub, sub+G, ... of Pxz, K = Pxz S^-1, K S and delta = K innovation
 #pragma unroll
-            for (int e = 0; e < N * M; ++e) Pxz[e] *= 0.5;
-            double Si[MP];
-            static_assert(M == 3, "only 3-dof measurement models are wired to the UKF kernel");
-            sym3_inverse(S, Si);
-            auto SiAt = [&](int r, int c) { return r >= c ? Si[tri(r, c)] : Si[tri(c, r)]; };
-            auto SAt = [&](int r, int c) { return r >= c ? S[tri(r, c)] : S[tri(c, r)]; };
-            double K[N * M];
+        for (int t = 0; t < RROWS; ++t) {
+            const int r = sub + G * t;
+            if (r < N) {
+                double px[M];
 #pragma unroll
-            for (int r = 0; r < N; ++r)
+                for (int c = 0; c < M; ++c) px[c] = 0.0;
+                for (int j = 0; j <= r; ++j) {
+                    const double l = lf[tri(r, j)];
+#pragma unroll
+                    for (int c = 0; c < M; ++c) px[c] = fma(l, DZ[j * M + c], px[c]);
+                }
+                double K[M], dsum = 0.0;
 #pragma unroll
                 for (int c = 0; c < M; ++c) {
                     double s = 0.0;
 #pragma unroll
-                    for (int p = 0; p < M; ++p) s += Pxz[r * M + p] * SiAt(p, c);
-                    K[r * M + c] = s;
+                    for (int p = 0; p < M; ++p) s += (0.5 * px[p]) * SiAt(p, c);
+                    K[c] = s;
+                    dsum += s * innov[c];
                 }
-            double innov[M], m2 = 0.0;
 #pragma unroll
-            for (int c = 0; c < M; ++c) innov[c] = a.z[(size_t)i * M + c] - zbar[c];
-#pragma unroll
-            for (int r = 0; r < M; ++r) {
-                double s = 0.0;
-#pragma unroll
-                for (int c = 0; c < M; ++c) s += SiAt(r, c) * innov[c];
-                m2 += innov[r] * s;
-            }
-#pragma unroll
-            for (int e = 0; e < NP; ++e) P[e] = col.at(PSOFF + e);
-            if (chi2_accept(m2, a.gate)) {
-                // sigma -= K S K^T   (lower triangle; the reference's LLT reads only that, Q8)
-                double KS[N * M];
-#pragma unroll
-                for (int r = 0; r < N; ++r)
-#pragma unroll
-                    for (int c = 0; c < M; ++c) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int p = 0; p < M; ++p) s += K[r * M + p] * SAt(p, c);
-                        KS[r * M + c] = s;
-                    }
-#pragma unroll
-                for (int r = 0; r < N; ++r)
-#pragma unroll
-                    for (int c = 0; c <= r; ++c) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int p = 0; p < M; ++p) s += KS[r * M + p] * K[c * M + p];
-                        P[tri(r, c)] -= s;
-                    }
-                // apply_delta(K * innovation): re-draw sigma points around mu [+] delta
-                double delta[N];
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
+                for (int c = 0; c < M; ++c) {
                     double s = 0.0;
 #pragma unroll
-                    for (int c = 0; c < M; ++c) s += K[r * M + c] * innov[c];
-                    delta[r] = s;
+                    for (int p = 0; p < M; ++p) s += K[p] * SAt(p, c);
+                    Ks[r * M + c] = K[c];
+                    KSs[r * M + c] = s;
                 }
-                if (!factor_to_tail(col, P)) {
-                    st |= SLB_ST_CHOL_FAIL;
-                    alive = false;
-                } else {
-                    {
-                        double y[QD];
-                        boxplus<L>(mu, delta, 1.0, y);
-#pragma unroll
-                        for (int c = 0; c < QD; ++c) col.Y(0, c) = y[c];
-                    }
-#pragma unroll 1
-                    for (int j = 0; j < N; ++j) {
-                        double d[N], dp[N], dm[N];
-                        load_col(col, j, d);
-#pragma unroll
-                        for (int r = 0; r < N; ++r) { dp[r] = delta[r] + d[r]; dm[r] = delta[r] - d[r]; }
-                        double yp[QD], ym[QD];
-                        boxplus<L>(mu, dp, 1.0, yp);
-                        boxplus<L>(mu, dm, 1.0, ym);
-#pragma unroll
-                        for (int c = 0; c < QD; ++c) { col.Y(1 + 2 * j, c) = yp[c]; col.Y(2 + 2 * j, c) = ym[c]; }
-                    }
-                    if (!manifold_mean(col, mu)) st |= SLB_ST_MEAN_NOCONV;
-                    manifold_cov(col, mu, P);
-                }
-            } else {
-                st |= SLB_ST_GATE_REJECT;
+                DL[r] = dsum;
             }
+        }
+        __syncwarp();
+        const bool accept = chi2_accept(m2, a.gate);
+        if (alive && !accept) st |= SLB_ST_GATE_REJECT;
+        const bool apply = alive && accept;
+        // sigma -= K S K^T   (lower triangle; the reference's LLT reads only that, Q8)
+        if (apply) {
+#pragma unroll
+            for (int t = 0; t < RROWS; ++t) {
+                const int r = sub + G * t;
+                if (r < N) {
+                    const double k0 = KSs[r * M], k1 = KSs[r * M + 1], k2 = KSs[r * M + 2];
+                    for (int c = 0; c <= r; ++c)
+                        ps[tri(r, c)] -= k0 * Ks[c * M] + k1 * Ks[c * M + 1] + k2 * Ks[c * M + 2];
+                }
+            }
+        }
+        double delta[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) delta[r] = DL[r];
+        __syncwarp();
+        // apply_delta(K * innovation): re-draw sigma points around mu [+] delta.  Groups that do not
+        // apply (gate, earlier failure) run the same instructions on their untouched P and drop the result.
+        double Psave[(NP + G - 1) / G];
+        if (!apply) {
+#pragma unroll
+            for (int k = 0; k < (NP + G - 1) / G; ++k) Psave[k] = (sub + G * k < NP) ? ps[sub + G * k] : 0.0;
+#pragma unroll
+            for (int r = 0; r < N; ++r) delta[r] = 0.0;
+        }
+        const bool ok3 = group_chol<N>(ps, lf, sub);
+        if (apply && !ok3) { st |= SLB_ST_CHOL_FAIL; alive = false; }
+#pragma unroll 1
+        for (int t = 0; t < ROUNDS; ++t) {
+            const int s = sub + G * t;
+            if (s < NS) {
+                double d[N], x[QD];
+                sigma_offset<N>(lf, s, d);
+#pragma unroll
+                for (int r = 0; r < N; ++r) d[r] += delta[r];
+                boxplus<L>(mu, d, 1.0, x);
+#pragma unroll
+                for (int c = 0; c < QD; ++c) sig[c * NS + s] = x[c];
+            }
+        }
+        __syncwarp();
+        double nm[QD];
+        const bool conv = group_mean<L, G>(sig, sub, apply && ok3, nm);
+        if (apply && ok3) {
+            if (!conv) st |= SLB_ST_MEAN_NOCONV;
+#pragma unroll
+            for (int c = 0; c < QD; ++c) mu[c] = nm[c];
+        }
+        group_cov<L, G, false>(sig, ps, Qp, sub, nm);
+        if (!apply) {  // rejected update: sigma and mu stay as they were (Usckf.hpp:294 / ukf::update)
+#pragma unroll
+            for (int k = 0; k < (NP + G - 1) / G; ++k)
+                if (sub + G * k < NP) ps[sub + G * k] = Psave[k];
         }
     }
 
-    if (alive) {
-        bool finite = true;
+    // ---- publish: mean to the record, status, then the warp streams its records back to HBM ---------
+    bool finite = true;
 #pragma unroll
-        for (int c = 0; c < QD; ++c) finite = finite && isfinite(mu[c]);
-        if (!finite) st |= SLB_ST_NONFINITE;
+    for (int c = 0; c < QD; ++c) finite = finite && isfinite(mu[c]);
+    if (alive && !finite) st |= SLB_ST_NONFINITE;
+    if (sub == 0) {
 #pragma unroll
-        for (int c = 0; c < QD; ++c) a.mu[(size_t)c * a.stride + i] = mu[c];
-#pragma unroll
-        for (int e = 0; e < NP; ++e) a.P[(size_t)e * a.stride + i] = P[e];
+        for (int c = 0; c < QD; ++c) rec[R::MU + c] = mu[c];
+        rec[R::FLAG] = alive ? 1.0 : 0.0;
+        if (st && valid) a.status[inst] |= st;
     }
-    if (st) a.status[i] |= st;
+    __syncwarp();
+    {
+        const int li = lane % IPW, e0 = lane / IPW;
+        const double *src = wsm + li * R::IS;
+        if (wbase + li < a.B && src[R::FLAG] != 0.0) {
+#pragma unroll 4
+            for (int e = e0; e < QD + NP; e += G) {
+                if (e < QD) a.mu[(size_t)e * a.stride + wbase + li] = src[R::MU + e];
+                else a.P[(size_t)(e - QD) * a.stride + wbase + li] = src[R::PS + (e - QD)];
+            }
+        }
+    }
 }
 
 }  // namespace slbd
 
 namespace slb {
 
-template <class L, int PM, class MM, int TPB>
+template <class L, int PM, class MM>
 static int launch_ukf_t(bool predict, bool update, const FilterArgs &a, cudaStream_t s) {
-    constexpr size_t smem = (size_t)TPB * (2 * L::N + 1) * L::QD * sizeof(double);
-    static_assert(smem <= 227 * 1024, "sigma-point columns exceed shared memory");
-    const int grid = (a.B + TPB - 1) / TPB;
+    constexpr int G = 4, TPB = 128, MINB = 3;
+    typedef slbd::Rec<L, MM::M, G> R;
+    constexpr size_t smem = (size_t)(TPB / 32) * ((32 / G) * R::IS + L::NP) * sizeof(double);
+    static_assert(smem <= 227 * 1024, "instance records exceed shared memory");
+    const int ipb = TPB / G;
+    const int grid = (a.B + ipb - 1) / ipb;
     auto go = [&](auto kern) -> int {
         SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, TPB, smem, s>>>(a);
@@ -372,9 +489,9 @@ static int launch_ukf_t(bool predict, bool update, const FilterArgs &a, cudaStre
         SLB_CUDA(cudaGetLastError());
         return SLB_OK;
     };
-    if (predict && update) return go(slbd::ukf_kernel<L, PM, MM, TPB, true, true>);
-    if (predict) return go(slbd::ukf_kernel<L, PM, MM, TPB, true, false>);
-    if (update) return go(slbd::ukf_kernel<L, PM, MM, TPB, false, true>);
+    if (predict && update) return go(slbd::ukf_kernel<L, PM, MM, G, TPB, MINB, true, true>);
+    if (predict) return go(slbd::ukf_kernel<L, PM, MM, G, TPB, MINB, true, false>);
+    if (update) return go(slbd::ukf_kernel<L, PM, MM, G, TPB, MINB, false, true>);
     return set_error(SLB_ERR_INVALID, "ukf: nothing to do");
 }
 
@@ -383,11 +500,11 @@ int launch_ukf(int layout, int pm, int mm, bool predict, bool update, const Filt
     if (update && mm != SLB_MM_GPS_POS) return set_error(SLB_ERR_INVALID, "ukf: unsupported measurement model");
     if (!predict) pm = layout == SLB_LAYOUT_POSE6 ? SLB_PM_POSE6_ODOM : SLB_PM_UKFOM_IMU;
     if (layout == SLB_LAYOUT_MTK9 && pm == SLB_PM_UKFOM_IMU)
-        return launch_ukf_t<LayMtk9, SLB_PM_UKFOM_IMU, MmGpsPos, 128>(predict, update, a, s);
+        return launch_ukf_t<LayMtk9, SLB_PM_UKFOM_IMU, MmGpsPos>(predict, update, a, s);
     if (layout == SLB_LAYOUT_MTK9 && pm == SLB_PM_UKFOM_IMU_REFBUG)
-        return launch_ukf_t<LayMtk9, SLB_PM_UKFOM_IMU_REFBUG, MmGpsPos, 128>(predict, update, a, s);
+        return launch_ukf_t<LayMtk9, SLB_PM_UKFOM_IMU_REFBUG, MmGpsPos>(predict, update, a, s);
     if (layout == SLB_LAYOUT_POSE6 && pm == SLB_PM_POSE6_ODOM)
-        return launch_ukf_t<LayPose6, SLB_PM_POSE6_ODOM, MmGpsPos, 256>(predict, update, a, s);
+        return launch_ukf_t<LayPose6, SLB_PM_POSE6_ODOM, MmGpsPos>(predict, update, a, s);
     return set_error(SLB_ERR_INVALID, "ukf: unsupported layout / process model combination");
 }
 
