@@ -50,6 +50,21 @@ SLB_DEV double rcp_fast(double w) {
     r = fma(r, e, r);
     return r;
 }
+// sqrt(x) and 1/sqrt(x) for x > 0 from the MUFU.RSQ64H seed and two Newton steps (full double
+// accuracy, ~1 ulp; not the IEEE-rounded sqrt/div pair of the CPU oracle -- parity is at 1e-9).
+SLB_DEV void sqrt_rsqrt(double x, double &s, double &rs) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    double r = x * y;
+    r = fma(fma(-r, r, x), 0.5 * y, r);
+    s = r;
+    rs = y;
+}
+
 // MTK cos_sinc_sqrt: c = cos(sqrt(x)), s = sin(sqrt(x))/sqrt(x)
 SLB_DEV void cos_sinc_sqrt(double x, double &c, double &s) {
     if (x < 1.0) {  // |rotation| < 2 rad

@@ -81,15 +81,19 @@ __global__ void __launch_bounds__(WPB * 32) predict12_kernel(slb::FilterArgs a) 
 #pragma unroll
     for (int p = 0; p < 12; ++p) row[p] = (lane < 12 && p <= lane) ? PR(lane, ROW0 + p) : 0.0;
     bool ok = true;
+    double invd[12];  // 1 / L_kk (every lane computes the pivot: no IEEE division, whose slow path the zero
+                      // numerators of the idle lanes would take)
 #pragma unroll
     for (int k = 0; k < 12; ++k) {
         double s = row[k];
 #pragma unroll
-        for (int p = 0; p < k; ++p) s -= row[p] * bcast(row[p], k);
+        for (int p = 0; p < 12; ++p)
+            if (p < k) s = fma(-row[p], bcast(row[p], k), s);
         const double x = bcast(s, k);
         ok = ok && (x > 0.0);
-        const double sx = sqrt(x);
-        row[k] = (lane == k) ? sx : s / sx;
+        double sx;
+        sqrt_rsqrt(x, sx, invd[k]);
+        row[k] = (lane == k) ? sx : s * invd[k];
     }
     if (!ok) {
         if (lane == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(WPB * 32) predict12_kernel(slb::FilterArgs a) 
                 double s = W[r * 12 + lane];
     #pragma unroll
                 for (int p = r + 1; p < 12; ++p) s -= Ls[tri(p, r)] * x[p];
-                x[r] = s / Ls[tri(r, r)];
+                x[r] = s * invd[r];
             }
     #pragma unroll
             for (int r = 0; r < 12; ++r) Fk[lane * 12 + r] = x[r];

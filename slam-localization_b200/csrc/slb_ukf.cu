@@ -35,21 +35,6 @@ SLB_DEV double gsum(double v) {
     return v;
 }
 
-// sqrt(x) and 1/sqrt(x) for x > 0 from the MUFU.RSQ64H seed and two Newton steps (full double
-// accuracy, ~1 ulp; not the IEEE-rounded sqrt/div pair of the CPU oracle -- parity is at 1e-9).
-SLB_DEV void sqrt_rsqrt(double x, double &s, double &rs) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-(x * y), y, 1.0);
-    y = fma(0.5 * y, e, y);
-    e = fma(-(x * y), y, 1.0);
-    y = fma(0.5 * y, e, y);
-    double r = x * y;
-    r = fma(fma(-r, r, x), 0.5 * y, r);
-    s = r;
-    rs = y;
-}
-
 // In-register packed Cholesky (lower, row-major packed), pivots through sqrt_rsqrt.  Every loop has the
 // constant trip count N with compile-time predicates: nvcc then unrolls all three levels and the
 // matrix stays in registers (data-dependent bounds left a rolled loop over a local-memory array).

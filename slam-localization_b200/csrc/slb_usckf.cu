@@ -26,38 +26,114 @@ template <int NK, int NL>
 struct UpdCfg {
     static constexpr int N = 36 + NK + NL;
     static constexpr int NP = N * (N + 1) / 2;
-    static constexpr int NPPAD = (NP + 15) / 16 * 16;
     static constexpr int JM = 36 + NK;          // columns j >= JM cannot move h
     static constexpr int NSIG = 2 * JM + 1;     // sigma points that are actually evaluated
+    static constexpr int RT = (N + 3) / 4;      // register tile: rows i = a + 4r, r < RT
+    static constexpr int CT = (N + 7) / 8;      //                cols j = b + 8c, c < CT
+    static constexpr int LS = NP + 16;          // factor, column-major packed (+ pad for the tile overhang)
     static constexpr int ZW = NSIG * NK + JM * NK;
     static constexpr int KK = 2 * N * NK;
-    static constexpr int SCR = ZW > KK ? ZW : KK;  // Z|W, later overlaid by K|KS
-    static constexpr int SM = (NPPAD + SCR + N + 2 + 1) / 2 * 2;  // + delta + mbarrier slot; even: 16-B aligned warps
+    static constexpr int SCR = ZW > KK ? ZW : KK;  // Z | W, later overlaid by K | KS
+    static constexpr int SM = (LS + SCR + N + 1) / 2 * 2;
+    // first element of column k of the packed column-major factor; L(i,k) = Ls[cb(k) - k + i], i >= k
+    SLB_HD static constexpr int cb(int k) { return k * N - k * (k - 1) / 2; }
+    // tile (r,c) of the 2D-cyclic register layout holds at least one lower-triangular entry
+    SLB_HD static constexpr bool exists(int r, int c) { return 4 * r < N && 8 * c < N && 4 * r + 3 >= 8 * c; }
+    // ... and at least one entry (i,j) with j > k (hence i > k): it takes part in the trailing update of step k
+    SLB_HD static constexpr bool live(int k, int r, int c) { return exists(r, c) && 8 * c + 7 > k && 4 * r + 3 > k; }
+    SLB_HD static constexpr bool row_live(int k, int r) {
+        for (int c = 0; c < CT; ++c)
+            if (live(k, r, c)) return true;
+        return false;
+    }
+    SLB_HD static constexpr bool col_live(int k, int c) {
+        for (int r = 0; r < RT; ++r)
+            if (live(k, r, c)) return true;
+        return false;
+    }
 };
 
-template <int NK, int NL, int WPB>
-__global__ void __launch_bounds__(WPB * 32) usckf_update_kernel(slb::FilterArgs a) {
+// Right-looking Cholesky of the N x N covariance held 2D-cyclically in registers: lane (a, b), a = lane & 3,
+// b = lane >> 2, owns the entries (a + 4r, b + 8c).  Step K (compile-time, fully unrolled by recursion):
+// the pivot is broadcast from its owner, the 4 lanes holding column K scale it and publish it to shared memory
+// (column-major packed: exactly the layout the sigma points and L W need afterwards), then every lane
+// rank-1-updates its live tiles with two short operand vectors read back from that column.  Entries of
+// finished columns / of the upper triangle are never read again, so the update needs no predicate at all:
+// whole tiles are pruned at compile time and the rest is plain DFMA.
+template <class C, int K>
+struct CholStep {
+    template <class Tile>
+    SLB_DEV static void run(Tile &T, double *Ls, int a_, int b_, bool &ok) {
+        constexpr int N = C::N, RT = C::RT, CT = C::CT;
+        constexpr int ak = K & 3, rk = K >> 2, bk = K & 7, ck = K >> 3, owner = ak + 4 * bk;
+        constexpr int base = C::cb(K) - K;
+        const double x = __shfl_sync(FULL, T[rk][ck], owner);
+        ok = ok && (x > 0.0);
+        double sx, inv;
+        sqrt_rsqrt(x, sx, inv);
+        if (b_ == bk) {
+#pragma unroll
+            for (int r = rk; r < RT; ++r) {
+                const int i = a_ + 4 * r;
+                double v = T[r][ck] * inv;
+                if (r == rk && a_ == ak) v = sx;
+                if (i >= K && i < N) Ls[base + i] = v;
+            }
+        }
+        __syncwarp();
+        double li[RT], lj[CT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+            if (C::row_live(K, r)) li[r] = Ls[base + a_ + 4 * r];
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (C::col_live(K, c)) lj[c] = Ls[base + b_ + 8 * c];
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (C::live(K, r, c)) T[r][c] = fma(-li[r], lj[c], T[r][c]);
+        CholStep<C, K + 1>::run(T, Ls, a_, b_, ok);
+    }
+};
+template <class C>
+struct CholStep<C, C::N> {
+    template <class Tile>
+    SLB_DEV static void run(Tile &, double *, int, int, bool &) {}
+};
+
+template <int NK, int NL, int WPB, int MINB>
+__global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::FilterArgs a) {
     typedef UpdCfg<NK, NL> C;
-    constexpr int N = C::N, JM = C::JM, NSIG = C::NSIG;
+    constexpr int N = C::N, JM = C::JM, NSIG = C::NSIG, RT = C::RT, CT = C::CT;
     static_assert(NK == 3, "the 3x3 closed-form S^-1 is the only one wired so far");
-    static_assert(N > 32 && N <= 64, "two register rows per lane");
+    static_assert(N > 32 && N <= 64, "two rows per lane in the L W product");
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int inst = blockIdx.x * WPB + w;
     if (inst >= a.B) return;
-    double *Ps = smem + (size_t)w * C::SM, *Zs = Ps + C::NPPAD, *Ws = Zs + NSIG * NK, *Ks = Zs, *KSs = Zs + N * NK,
+    const int a_ = lane & 3, b_ = lane >> 2;
+    double *Ls = smem + (size_t)w * C::SM, *Zs = Ls + C::LS, *Ws = Zs + NSIG * NK, *Ks = Zs, *KSs = Zs + N * NK,
            *dl = Zs + C::SCR;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(dl + N);
     double *Pg = a.P + (size_t)inst * a.pstride;
     double *mug = a.mu + (size_t)inst * a.qstride;
 
-    // ---- stream the packed covariance record into shared memory with one TMA bulk copy -----------------
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, C::NPPAD * 8);
-        bulk_g2s(Ps, Pg, C::NPPAD * 8, bar);
+    // ---- the lower triangle of Pk straight from the HBM record into the 2D-cyclic register tiles ----------
+    // (for a fixed tile the 32 lanes read 4 rows x 8 consecutive doubles: full 32-byte sectors)
+    double T[RT][CT];
+    int rowoff[RT];  // tri(a + 4r, 0) + b
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const int i = a_ + 4 * r;
+        rowoff[r] = i * (i + 1) / 2 + b_;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (C::exists(r, c)) {
+                const int j = b_ + 8 * c;
+                T[r][c] = (i < N && j <= i) ? Pg[rowoff[r] + 8 * c] : 0.0;
+            }
     }
-    // mean blocks that h needs (statek pos/orient, statek_i pos/orient, featuresk) while the copy flies
+    // mean blocks that h needs (statek pos/orient, statek_i pos/orient, featuresk)
     double pk[3], qk[4], pi[3], qi[4], ft[NK];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { pk[c] = mug[c]; pi[c] = mug[26 + c]; }
@@ -65,50 +141,15 @@ __global__ void __launch_bounds__(WPB * 32) usckf_update_kernel(slb::FilterArgs 
     for (int c = 0; c < 4; ++c) { qk[c] = mug[3 + c]; qi[c] = mug[29 + c]; }
 #pragma unroll
     for (int c = 0; c < NK; ++c) ft[c] = mug[39 + c];
-    __syncwarp();
-    mbar_wait(bar, 0);
 
-    // ---- Eigen::LLT of Pk (:537): lane owns rows `lane` (ra) and `lane+32` (rb) -----------------------
-    const bool hasB = lane + 32 < N;
-    const int iB = hasB ? lane + 32 : N - 1;
-    double ra[32], rb[N];
-#pragma unroll
-    for (int p = 0; p < 32; ++p) ra[p] = (p <= lane) ? Ps[tri(lane, p)] : 0.0;
-#pragma unroll
-    for (int p = 0; p < N; ++p) rb[p] = (hasB && p <= lane + 32) ? Ps[tri(iB, p > iB ? iB : p)] : 0.0;
+    // ---- Eigen::LLT of Pk (:537) ------------------------------------------------------------------------
     bool ok = true;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        double sA = (k < 32) ? ra[k < 32 ? k : 0] : 0.0, sB = rb[k];
-#pragma unroll
-        for (int p = 0; p < k; ++p) {
-            const double bk = Ps[tri(k, p)];  // finished entry of row k: broadcast read
-            if (k < 32 && p < 32) sA -= ra[p] * bk;
-            sB -= rb[p] * bk;
-        }
-        const double x = (k < 32) ? bcast(sA, k) : bcast(sB, k - 32);
-        ok = ok && (x > 0.0);
-        const double sx = sqrt(x);
-        if (k < 32) {
-            const double v = (lane == k) ? sx : sA / sx;
-            ra[k < 32 ? k : 0] = v;
-            if (lane >= k) Ps[tri(lane, k)] = v;
-        }
-        {
-            const double v = (k >= 32 && lane == k - 32) ? sx : sB / sx;
-            rb[k] = v;
-            if (hasB && lane + 32 >= k) Ps[tri(iB, k)] = v;
-        }
-        __syncwarp();
-    }
+    CholStep<C, 0>::run(T, Ls, a_, b_, ok);
     if (!ok) {
         if (lane == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
         return;
     }
-#pragma unroll
-    for (int p = 0; p < 32; ++p) ra[p] = (p <= lane) ? ra[p] : 0.0;
-#pragma unroll
-    for (int p = 0; p < N; ++p) rb[p] = (hasB && p <= lane + 32) ? rb[p] : 0.0;
+    __syncwarp();
 
     // ---- sigma points through h (:275-278), lane per point ---------------------------------------------
     constexpr int NPASS = (NSIG + 31) / 32;
@@ -119,7 +160,8 @@ __global__ void __launch_bounds__(WPB * 32) usckf_update_kernel(slb::FilterArgs 
         const bool act = s < NSIG;
         const int j = act && s >= 1 ? (s - 1) >> 1 : 0;
         const double sgn = (s & 1) ? 1.0 : -1.0;
-        auto Lc = [&](int r) -> double { return (act && s >= 1 && r >= j) ? sgn * Ps[tri(r, j)] : 0.0; };
+        const int cj = j * N - j * (j - 1) / 2 - j;  // column j of the factor starts at Ls[cj + j]
+        auto Lc = [&](int r) -> double { return (act && s >= 1 && r >= j) ? sgn * Ls[cj + r] : 0.0; };
         double xpk[3], xqk[4], xpi[3], xqi[4], xf[NK];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { xpk[c] = pk[c] + Lc(c); xpi[c] = pi[c] + Lc(24 + c); }
@@ -186,17 +228,24 @@ __global__ void __launch_bounds__(WPB * 32) usckf_update_kernel(slb::FilterArgs 
         Ws[e] = 0.5 * ((Zs[(1 + 2 * jj) * NK + c] - zbar[c]) - (Zs[(2 + 2 * jj) * NK + c] - zbar[c]));
     }
     __syncwarp();
-    // ---- covXZ = L W (:283, :714-737), rows from registers ---------------------------------------------
+    // ---- covXZ = L W (:283, :714-737): lane owns rows `lane` and `lane + 32`; column jj of the factor is
+    //      contiguous in i, so the reads are conflict-free -------------------------------------------------
+    const bool hasB = lane + 32 < N;
     double pxA[NK], pxB[NK];
 #pragma unroll
     for (int c = 0; c < NK; ++c) pxA[c] = pxB[c] = 0.0;
 #pragma unroll
     for (int jj = 0; jj < JM; ++jj) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int cj = C::cb(jj) - jj;
+        const double la = (jj < 32 && lane >= jj) ? Ls[cj + lane] : 0.0;
+        const double lb = (hasB && lane + 32 >= jj) ? Ls[cj + lane + 32] : 0.0;
 #pragma unroll
         for (int c = 0; c < NK; ++c) {
             const double wv = Ws[jj * NK + c];
-            if (jj < 32) pxA[c] += ra[jj < 32 ? jj : 0] * wv;
-            pxB[c] += rb[jj] * wv;
+            if (jj < 32) pxA[c] = fma(la, wv, pxA[c]);
+            pxB[c] = fma(lb, wv, pxB[c]);
         }
     }
     // ---- K = covXZ S^-1 (:286-288), innovation, Mahalanobis gate (:290-294) ----------------------------
@@ -269,13 +318,30 @@ __global__ void __launch_bounds__(WPB * 32) usckf_update_kernel(slb::FilterArgs 
         mug[39 + lane - 12] = o;
         finite = finite && isfinite(o);
     }
-    // ---- Pk -= K S K^T (:296) on the HBM record (lower triangle), coalesced per row ---------------------
-#pragma unroll 2
-    for (int i = 0; i < N; ++i) {
-        const double k0 = KSs[i * NK], k1 = KSs[i * NK + 1], k2 = KSs[i * NK + 2];
-        for (int c = lane; c <= i; c += 32) {
-            const int e = tri(i, c);
-            Pg[e] = Pg[e] - (k0 * Ks[c * NK] + k1 * Ks[c * NK + 1] + k2 * Ks[c * NK + 2]);
+    // ---- Pk -= K S K^T (:296) on the HBM record (lower triangle), same 2D-cyclic tiles as the load ------
+    {
+        double kc[CT][NK];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const int j = b_ + 8 * c;
+#pragma unroll
+            for (int p = 0; p < NK; ++p) kc[c][p] = j < N ? Ks[j * NK + p] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+            const int i = a_ + 4 * r;
+            double ks[NK];
+#pragma unroll
+            for (int p = 0; p < NK; ++p) ks[p] = i < N ? KSs[i * NK + p] : 0.0;
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (C::exists(r, c)) {
+                    const int j = b_ + 8 * c;
+                    if (i < N && j <= i) {
+                        const int e = rowoff[r] + 8 * c;
+                        Pg[e] = Pg[e] - (ks[0] * kc[c][0] + ks[1] * kc[c][1] + ks[2] * kc[c][2]);
+                    }
+                }
         }
     }
     if (!__all_sync(FULL, finite) && lane == 0) a.status[inst] |= SLB_ST_NONFINITE;
@@ -364,9 +430,9 @@ static int launch_predict_t(const FilterArgs &a, cudaStream_t s) {
 
 template <int NK, int NL>
 static int launch_update_t(const FilterArgs &a, cudaStream_t s) {
-    constexpr int WPB = 4;
+    constexpr int WPB = 4, MINB = 3;
     constexpr size_t smem = (size_t)WPB * slbd::UpdCfg<NK, NL>::SM * sizeof(double);
-    auto kern = slbd::usckf_update_kernel<NK, NL, WPB>;
+    auto kern = slbd::usckf_update_kernel<NK, NL, WPB, MINB>;
     SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(a.B + WPB - 1) / WPB, WPB * 32, smem, s>>>(a);
     count_launch();
