@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         if (tid < M) {
             double s = 0.0;
             for (int t = 0; t < NS; ++t) s += RB[t * MS_ZS + tid];
-            const double zb = s / (double)NS;
+            const double zb = s * (1.0 / (double)NS);
             zbar[tid] = zb;
             nu[tid] = zg[tid] - zb;
         }
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 for (int q = q0; q < q0 + qb; ++q) {
                     double s = row[q];
                     for (int p = q0; p < q; ++p) s -= Sp[tri(q, p)] * row[p];
-                    row[q] = s / Sp[tri(q, q)];
+                    row[q] = s * rcp_fast(Sp[tri(q, q)]);
                 }
             }
             __syncthreads();
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         // ---- w = Ls^-1 nu (warp 0), delta = Y w ------------------------------------------------------
         if (warp == 0) {
             for (int q = 0; q < mk; ++q) {
-                const double wq = nu[q] / Sp[tri(q, q)];
+                const double wq = nu[q] * rcp_fast(Sp[tri(q, q)]);
                 __syncwarp();
                 if (lane == 0) wv[q] = wq;
                 for (int c = q + 1 + lane; c < mk; c += 32) nu[c] -= Sp[tri(c, q)] * wq;
@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             __syncthreads();
             if (tid < NB) {
                 const int b = tid, qo = ms_qoff(b);
-                const double d[3] = {acc[3 * b] / (double)NS, acc[3 * b + 1] / (double)NS, acc[3 * b + 2] / (double)NS};
+                const double wn = 1.0 / (double)NS;
+                const double d[3] = {acc[3 * b] * wn, acc[3 * b + 1] * wn, acc[3 * b + 2] * wn};
                 dl[3 * b] = d[0]; dl[3 * b + 1] = d[1]; dl[3 * b + 2] = d[2];
                 if (ms_so3(b)) {
                     double e[4], q[4];

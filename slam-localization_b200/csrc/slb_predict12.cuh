@@ -51,7 +51,7 @@ constexpr int PRED_SM = PRED_PR + PRED_PF + 78 + 25 * 13 + 144 + 144 + 1;  // do
 // ROW0: first row of the 12x12 block; MU0: q-vector offset of the block's mean; CROSS: propagate the
 // cross-covariances of the block's rows/columns with the rest of the state (USCKF) or not (MSCKF).
 template <int PM, int WPB, int ROW0, int MU0, bool CROSS>
-__global__ void __launch_bounds__(WPB * 32) predict12_kernel(slb::FilterArgs a) {
+__global__ void __launch_bounds__(WPB * 32, 2) predict12_kernel(slb::FilterArgs a) {
     typedef LayState12 L;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(WPB * 32) predict12_kernel(slb::FilterArgs a) 
         nrm2 = 0.0;
 #pragma unroll
         for (int r = 0; r < 12; ++r) {
-            md[r] = warp_sum(act ? dd[r] : 0.0) / 25.0;
+            md[r] = warp_sum(act ? dd[r] : 0.0) * (1.0 / 25.0);  // not "/ 25.0": zero numerators take div.rn's slow path
             nrm2 += md[r] * md[r];
         }
         boxplus<L>(ref, md, 1.0, nr);
@@ -156,14 +156,18 @@ __global__ void __launch_bounds__(WPB * 32) predict12_kernel(slb::FilterArgs a) 
     }
     __syncwarp();
     // ---- Pk_i = cov + Q (:178) and W = 0.5 (dY+ - dY-) -------------------------------------------------
-    for (int e = lane; e < 78; e += 32) {
-        int r = 0;
-        while (tri(r + 1, 0) <= e) ++r;
-        const int c = e - tri(r, 0);
-        double s = 0.0;
-#pragma unroll 5
-        for (int t = 0; t < 25; ++t) s += D[t * 13 + r] * D[t * 13 + c];
-        PR(r, ROW0 + c) = 0.5 * s + __ldg(a.Q + r * 12 + c);
+#pragma unroll
+    for (int e0 = 0; e0 < 96; e0 += 32) {
+        const int e = e0 + lane;
+        if (e < 78) {
+            int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);  // packed index -> (r, c), exact for e < 78
+            r += (tri(r + 1, 0) <= e) - (tri(r, 0) > e);
+            const int c = e - tri(r, 0);
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < 25; ++t) s = fma(D[t * 13 + r], D[t * 13 + c], s);
+            PR(r, ROW0 + c) = 0.5 * s + __ldg(a.Q + r * 12 + c);
+        }
     }
     if (CROSS) {
         for (int e = lane; e < 144; e += 32) {

@@ -135,7 +135,7 @@ SLB_DEV bool group_mean(const double *sig, int sub, bool go, double *ref) {
         double nrm2 = 0.0;
 #pragma unroll
         for (int r = 0; r < N; ++r) {
-            md[r] = gsum<G>(md[r]) / (double)NS;
+            md[r] = gsum<G>(md[r]) * (1.0 / (double)NS);  // not "/ NS": zero numerators take div.rn's slow path
             nrm2 += md[r] * md[r];
         }
         double nr[QD];
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
         }
         double zbar[M];
 #pragma unroll
-        for (int c = 0; c < M; ++c) zbar[c] = gsum<G>(zsum[c]) / (double)NS;
+        for (int c = 0; c < M; ++c) zbar[c] = gsum<G>(zsum[c]) * (1.0 / (double)NS);
         __syncwarp();
         // S = 0.5 sum (Zi - zbar)(Zi - zbar)^T + R   (packed lower)
         double S[MP];

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
         double s = 0.0;
 #pragma unroll
         for (int t = 0; t < NPASS; ++t) s += zr[t][c];
-        zbar[c] = (warp_sum(s) + NREST * z0[c]) / (double)(2 * N + 1);
+        zbar[c] = (warp_sum(s) + NREST * z0[c]) * (1.0 / (double)(2 * N + 1));
     }
     double S[NK * (NK + 1) / 2];
 #pragma unroll
