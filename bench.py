@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -113,7 +113,11 @@ class UkfomWorkload:
     layout = 9
     bytes_per_unit = 952            # 2*8*(45+10) + 72
     flops_per_unit = 1.4e4
-    kernel = "slbd::ukf_kernel<MTK9, IMU, GPS, fused>"
+    kernel = "slbd::ukf_kernel<MTK9, IMU, GPS, G=4, fused>"
+    phases = ("ukf_kernel",)
+    dominant = 0
+    traffic = 33.7e6 + 0.07e6       # ncu dram read+write per launch (profiles/r01_ncu_full_summary.txt); the 36 MB
+                                    # fleet fits L2, so the write-back of a lone profiled launch is not counted
 
     def __init__(self, rank, seed=1234):
         self.seed = seed + 1000 * rank
@@ -188,6 +192,9 @@ class FusionWorkload:
     bytes_per_unit = 648            # packed-symmetric accounting; dense traffic is 1008 B
     flops_per_unit = 2.6e3
     kernel = "slbd::datamodel_kernel<6, fusion>"
+    phases = ("datamodel_kernel",)
+    dominant = 0
+    traffic = 704.7e6 + 319.5e6     # ncu dram read+write per launch (profiles/r01_ncu_full_summary.txt)
 
     def __init__(self, rank, seed=99):
         self.sc = synth.fusion_scenario(self.B, d=self.d, seed=seed + rank)
@@ -273,9 +280,20 @@ class UsckfWorkload:
         self.hmu = torch.empty((self.B, 51), dtype=torch.float64).pin_memory()
         self.l2_policy = "fleet state %.0f MB per step > L2" % (self.B * (1184 + 52) * 8 / 1e6)
 
-    def step(self, k):
+    phases = ("predict12_kernel", "usckf_update_kernel")
+    dominant = 1
+    traffic = 18.9e3 * 524288       # ncu dram read+write of usckf_update_kernel, profiles/r01_ncu_full_summary.txt
+
+    def step_phase(self, k, p):
         e = self.engine
-        self.f.step(e.PM_USCKF_TEST, e.MM_USCKF_VO, self.du, self.sc["dt"], self.Q, self.dz, self.R)
+        if p == 0:
+            self.f.predict(e.PM_USCKF_TEST, self.du, self.sc["dt"], self.Q)
+        else:
+            self.f.update(e.MM_USCKF_VO, self.dz, self.R)
+
+    def step(self, k):
+        self.step_phase(k, 0)
+        self.step_phase(k, 1)
 
     def step_e2e(self, k):
         e = self.engine
@@ -355,10 +373,20 @@ class MsckfWorkload:
         self.hmu = torch.empty((self.B, 13 + 7 * self.K), dtype=torch.float64).pin_memory()
         self.l2_policy = "fleet state %.0f MB per step > L2" % (self.B * (2640 + 84) * 8 / 1e6)
 
-    def step(self, k):
+    phases = ("predict12_kernel", "msckf_update_kernel")
+    dominant = 1
+    traffic = None
+
+    def step_phase(self, k, p):
         e = self.engine
-        self.f.predict(e.PM_MSCKF_DELTAPOSE, self.du, 0.0, self.Q)
-        self.f.update(e.MM_MSCKF_REPROJ, self.lm, self.dz, self.R)
+        if p == 0:
+            self.f.predict(e.PM_MSCKF_DELTAPOSE, self.du, 0.0, self.Q)
+        else:
+            self.f.update(e.MM_MSCKF_REPROJ, self.lm, self.dz, self.R)
+
+    def step(self, k):
+        self.step_phase(k, 0)
+        self.step_phase(k, 1)
 
     def step_e2e(self, k):
         e = self.engine
@@ -489,11 +517,35 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for k in range(args.steps):
-        wl.step(args.warmup + k)
+    nph = len(wl.phases)
+    mids = []
+    if nph == 1:
+        for k in range(args.steps):
+            wl.step(args.warmup + k)
+    else:  # an event after every launch but the last of a step: the dominant kernel's own duration
+        for k in range(args.steps):
+            row = []
+            for p in range(nph):
+                wl.step_phase(args.warmup + k, p)
+                if p < nph - 1:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    row.append(ev)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            row.append(ev)
+            mids.append(row)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if nph == 1:
+        dom_ms = ms / args.steps
+    else:
+        tot = 0.0
+        for k, row in enumerate(mids):
+            start = (mids[k - 1][-1] if k else e0) if wl.dominant == 0 else row[wl.dominant - 1]
+            tot += start.elapsed_time(row[wl.dominant])
+        dom_ms = tot / args.steps
     launches = engine.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -539,7 +591,7 @@ def main():
 
     if rank == 0:
         ms_per_step = ms_max / args.steps
-        launch_ms = ms_per_step / wl.launches_per_step()
+        launch_ms = dom_ms                # average duration of the dominant kernel's launches (CUDA events, rank 0)
         achieved = wl.bytes_per_unit * wl.units_per_step() / (launch_ms * 1e-3) / 1e9
         fp64_peak = engine.fp64_peak_tflops()
         fp64_ach = wl.flops_per_unit * wl.units_per_step() / (ms_per_step * 1e-3) / 1e12
@@ -549,8 +601,9 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(wl.describe(), l2=wl.l2_policy, parallelism="instance-index shard x%d, no step-path collective" % world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": wl.kernel, "algorithmic_bytes_per_unit": wl.bytes_per_unit},
+                         "frac": achieved / hbm_peak, "traffic": wl.traffic, "peak_source": peak_src,
+                         "kernel": wl.kernel, "kernel_ms": launch_ms, "algorithmic_bytes_per_unit": wl.bytes_per_unit,
+                         "launches_per_step": list(wl.phases)},
             "roofline_fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
                               "frac": fp64_ach / fp64_peak if fp64_peak else None,
                               "algorithmic_flops_per_unit": wl.flops_per_unit,

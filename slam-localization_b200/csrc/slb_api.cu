@@ -282,6 +282,11 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->stage, h->stage_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->shared_small, 128 * 1024);
     if (e == cudaSuccess) e = cudaMalloc(&h->counts_dev, 4 * sizeof(int64_t));
+    for (int i = 0; i < SLB_NXS && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&h->xs[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemset(h->mu, 0, mu_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->P, 0, P_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->status, 0, (size_t)h->B * 4);
@@ -298,6 +303,11 @@ int slb_destroy(slb_handle h) {
     if (!h) return SLB_OK;
     cudaFree(h->mu); cudaFree(h->P); cudaFree(h->status); cudaFree(h->outliers);
     cudaFree(h->stage); cudaFree(h->shared_small); cudaFree(h->counts_dev);
+    for (int i = 0; i < SLB_NXS; ++i) {
+        if (h->xs[i]) cudaStreamDestroy(h->xs[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
     delete h;
     return SLB_OK;
 }
@@ -420,31 +430,77 @@ int slb_ukf_step(slb_handle h, int pm, int mm, const double *u, double dt, const
     return ukf_call(h, pm, mm, true, true, u, dt, Q, z, R, gate_dof, stream);
 }
 
-// Shared host-buffer step: stage u | z | Q | R on the device, run, return the posterior means.
-static int step_host(slb_handle h, int pm, int mm, int nu, int m, int nq, const double *u_host, double dt,
-                     const double *Q_host, const double *z_host, const double *R_host, int gate, double *mu_out,
-                     void *stream, bool usckf) {
-    if (!h || !u_host || !Q_host || !z_host || !R_host) return set_error(SLB_ERR_INVALID, "slb_*_step_host: null argument");
+// Shared host-buffer step: the batch is cut into chunks that travel on a small ring of internal streams, so
+// the H2D copy of chunk c+1 (u, z), the kernels of chunk c and the D2H copy of the posterior means of chunk
+// c-1 overlap (PCIe is full duplex).  Q, R and the model parameters are small shared inputs copied first on
+// the caller's stream; the call returns after everything has completed.
+struct HostStep {
+    int pm, mm, nu, m, nq, nparams, gate;
+    double dt;
+    const double *u, *Q, *params, *z, *R;
+    double *mu_out;
+};
+
+static int launch_chunk(slb_handle h, const HostStep &hs, int b0, int cnt, const double *du, const double *dz,
+                        const double *dQ, const double *dp, const double *dR, cudaStream_t st) {
+    FilterArgs a = make_args(h);
+    const bool soa = h->cfg.kind == SLB_KIND_UKF;
+    a.mu += soa ? (size_t)b0 : (size_t)b0 * h->qstride;
+    a.P += soa ? (size_t)b0 : (size_t)b0 * h->pstride;
+    a.status += b0;
+    a.outliers += b0;
+    a.B = cnt;
+    a.u = du; a.dt = hs.dt; a.Q = dQ; a.z = dz; a.R = dR; a.params = dp; a.gate = hs.gate; a.m = hs.m;
+    switch (h->cfg.kind) {
+        case SLB_KIND_UKF: return launch_ukf(h->cfg.layout, hs.pm, hs.mm, true, true, a, st);
+        case SLB_KIND_USCKF: return launch_usckf(hs.pm, hs.mm, true, true, a, st);
+        default: {
+            int rc = launch_msckf_predict(hs.pm, a, st);
+            return rc != SLB_OK ? rc : launch_msckf_update(hs.mm, a, st);
+        }
+    }
+}
+
+static int step_host(slb_handle h, const HostStep &hs, void *stream) {
+    if (!h || !hs.u || !hs.Q || !hs.z || !hs.R) return set_error(SLB_ERR_INVALID, "slb_*_step_host: null argument");
     cudaStream_t s = S(stream);
-    const size_t ub = (size_t)h->B * nu * 8, zb = (size_t)h->B * m * 8;
-    const size_t mub = (size_t)h->B * h->QD * 8;
-    if (ub + zb + mub > h->stage_bytes) return set_error(SLB_ERR_INVALID, "slb_*_step_host: batch too large for the staging buffer");
-    double *du = h->stage, *dz = h->stage + (size_t)h->B * nu, *dmu = dz + (size_t)h->B * m;
-    double *dQ = h->shared_small, *dR = h->shared_small + nq * nq;
-    SLB_CUDA(cudaMemcpyAsync(du, u_host, ub, cudaMemcpyHostToDevice, s));
-    SLB_CUDA(cudaMemcpyAsync(dz, z_host, zb, cudaMemcpyHostToDevice, s));
-    SLB_CUDA(cudaMemcpyAsync(dQ, Q_host, (size_t)nq * nq * 8, cudaMemcpyHostToDevice, s));
-    SLB_CUDA(cudaMemcpyAsync(dR, R_host, (size_t)m * m * 8, cudaMemcpyHostToDevice, s));
-    int rc = usckf ? slb_usckf_step(h, pm, mm, du, dt, dQ, dz, dR, gate, stream)
-                   : slb_ukf_step(h, pm, mm, du, dt, dQ, dz, dR, gate, stream);
-    if (rc != SLB_OK) return rc;
-    if (mu_out) {
-        const int work = h->B * h->QD, tpb = 256;
-        if (usckf) rec_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, s>>>(h->mu, dmu, 0, h->B, h->QD, h->qstride);
-        else soa_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, s>>>(h->mu, dmu, 0, h->B, h->QD, h->stride);
-        count_launch();
-        SLB_CUDA(cudaGetLastError());
-        SLB_CUDA(cudaMemcpyAsync(mu_out, dmu, mub, cudaMemcpyDeviceToHost, s));
+    const size_t ub = (size_t)h->B * hs.nu * 8, zb = (size_t)h->B * hs.m * 8, mub = (size_t)h->B * h->QD * 8;
+    const size_t small = (size_t)(hs.nq * hs.nq + hs.m * hs.m + hs.nparams) * 8;
+    if (ub + zb + mub > h->stage_bytes || small > 128 * 1024)
+        return set_error(SLB_ERR_INVALID, "slb_*_step_host: batch / shared inputs too large for the staging buffers");
+    double *du = h->stage, *dz = du + (size_t)h->B * hs.nu, *dmu = dz + (size_t)h->B * hs.m;
+    double *dQ = h->shared_small, *dp = dQ + hs.nq * hs.nq, *dR = dp + hs.nparams;
+    SLB_CUDA(cudaMemcpyAsync(dQ, hs.Q, (size_t)hs.nq * hs.nq * 8, cudaMemcpyHostToDevice, s));
+    if (hs.nparams) SLB_CUDA(cudaMemcpyAsync(dp, hs.params, (size_t)hs.nparams * 8, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaMemcpyAsync(dR, hs.R, (size_t)hs.m * hs.m * 8, cudaMemcpyHostToDevice, s));
+    SLB_CUDA(cudaEventRecord(h->ev_start, s));
+    // chunks of >= 8192 instances (multiples of 32 so no warp straddles a chunk), at most 8
+    int nchunk = h->B / 16384;
+    nchunk = nchunk < 1 ? 1 : nchunk > 8 ? 8 : nchunk;
+    const int per = ((h->B + nchunk - 1) / nchunk + 31) / 32 * 32;
+    const bool soa = h->cfg.kind == SLB_KIND_UKF;
+    int used = 0;
+    for (int c = 0, b0 = 0; b0 < h->B; ++c, b0 += per) {
+        const int cnt = h->B - b0 < per ? h->B - b0 : per;
+        cudaStream_t st = h->xs[c % SLB_NXS];
+        if (c < SLB_NXS) { SLB_CUDA(cudaStreamWaitEvent(st, h->ev_start, 0)); used = c + 1; }
+        SLB_CUDA(cudaMemcpyAsync(du + (size_t)b0 * hs.nu, hs.u + (size_t)b0 * hs.nu, (size_t)cnt * hs.nu * 8, cudaMemcpyHostToDevice, st));
+        SLB_CUDA(cudaMemcpyAsync(dz + (size_t)b0 * hs.m, hs.z + (size_t)b0 * hs.m, (size_t)cnt * hs.m * 8, cudaMemcpyHostToDevice, st));
+        const int rc = launch_chunk(h, hs, b0, cnt, du + (size_t)b0 * hs.nu, dz + (size_t)b0 * hs.m, dQ, dp, dR, st);
+        if (rc != SLB_OK) return rc;
+        if (hs.mu_out) {
+            const int work = cnt * h->QD, tpb = 256;
+            double *dst = dmu + (size_t)b0 * h->QD;
+            if (soa) soa_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, st>>>(h->mu, dst, b0, cnt, h->QD, h->stride);
+            else rec_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, st>>>(h->mu, dst, b0, cnt, h->QD, h->qstride);
+            count_launch();
+            SLB_CUDA(cudaGetLastError());
+            SLB_CUDA(cudaMemcpyAsync(hs.mu_out + (size_t)b0 * h->QD, dst, (size_t)cnt * h->QD * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int i = 0; i < used; ++i) {
+        SLB_CUDA(cudaEventRecord(h->ev_done[i], h->xs[i]));
+        SLB_CUDA(cudaStreamWaitEvent(s, h->ev_done[i], 0));
     }
     SLB_CUDA(cudaStreamSynchronize(s));
     return SLB_OK;
@@ -452,7 +508,9 @@ static int step_host(slb_handle h, int pm, int mm, int nu, int m, int nq, const 
 int slb_ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
                       const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_UKF) return set_error(SLB_ERR_INVALID, "slb_ukf_step_host: handle is not a UKF batch");
-    return step_host(h, pm, mm, pm_nu(pm), 3, h->N, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, false);
+    if (mm != SLB_MM_GPS_POS) return set_error(SLB_ERR_INVALID, "ukf: unsupported measurement model");
+    const HostStep hs = {pm, mm, pm_nu(pm), 3, h->N, 0, gate_dof, dt, u_host, Q_host, nullptr, z_host, R_host, mu_out_host};
+    return step_host(h, hs, stream);
 }
 
 // ---- localization::Usckf -----------------------------------------------------------------------------
@@ -478,7 +536,8 @@ int slb_usckf_step(slb_handle h, int pm, int mm, const double *u, double dt, con
 int slb_usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
                         const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_step_host: handle is not a USCKF batch");
-    return step_host(h, pm, mm, pm_nu(pm), h->cfg.nk, 12, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, true);
+    const HostStep hs = {pm, mm, pm_nu(pm), h->cfg.nk, 12, 0, gate_dof, dt, u_host, Q_host, nullptr, z_host, R_host, mu_out_host};
+    return step_host(h, hs, stream);
 }
 int slb_usckf_clone(slb_handle h, int mode, void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_clone: handle is not a USCKF batch");
@@ -518,31 +577,9 @@ int slb_msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, doub
     if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: handle is not an MSCKF batch");
     if (!u_host || !Q_host || !params_host || !z_host || !R_host || m <= 0 || nparams <= 0)
         return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: null argument");
-    cudaStream_t s = S(stream);
-    const int nu = pm_nu(pm);
-    const size_t ub = (size_t)h->B * nu * 8, zb = (size_t)h->B * m * 8, mub = (size_t)h->B * h->QD * 8;
-    const size_t small = (size_t)(144 + m * m + nparams) * 8;
-    if (ub + zb + mub > h->stage_bytes || small > 128 * 1024)
-        return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: batch / shared inputs too large for the staging buffers");
-    double *du = h->stage, *dz = du + (size_t)h->B * nu, *dmu = dz + (size_t)h->B * m;
-    double *dQ = h->shared_small, *dp = dQ + 144, *dR = dp + nparams;
-    SLB_CUDA(cudaMemcpyAsync(du, u_host, ub, cudaMemcpyHostToDevice, s));
-    SLB_CUDA(cudaMemcpyAsync(dz, z_host, zb, cudaMemcpyHostToDevice, s));
-    SLB_CUDA(cudaMemcpyAsync(dQ, Q_host, 144 * 8, cudaMemcpyHostToDevice, s));
-    SLB_CUDA(cudaMemcpyAsync(dp, params_host, (size_t)nparams * 8, cudaMemcpyHostToDevice, s));
-    SLB_CUDA(cudaMemcpyAsync(dR, R_host, (size_t)m * m * 8, cudaMemcpyHostToDevice, s));
-    int rc = slb_msckf_predict(h, pm, du, dt, dQ, stream);
-    if (rc == SLB_OK) rc = slb_msckf_update(h, mm, dp, m, dz, dR, gate, stream);
-    if (rc != SLB_OK) return rc;
-    if (mu_out_host) {
-        const int work = h->B * h->QD, tpb = 256;
-        rec_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, s>>>(h->mu, dmu, 0, h->B, h->QD, h->qstride);
-        count_launch();
-        SLB_CUDA(cudaGetLastError());
-        SLB_CUDA(cudaMemcpyAsync(mu_out_host, dmu, mub, cudaMemcpyDeviceToHost, s));
-    }
-    SLB_CUDA(cudaStreamSynchronize(s));
-    return SLB_OK;
+    const HostStep hs = {pm, mm, pm_nu(pm), m, 12, nparams, gate, dt, u_host, Q_host, params_host, z_host, R_host, mu_out_host};
+    if (mm != SLB_MM_MSCKF_REPROJ || (m & 1)) return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: bad measurement model / m");
+    return step_host(h, hs, stream);
 }
 
 // ---- localization::DataModel -------------------------------------------------------------------------

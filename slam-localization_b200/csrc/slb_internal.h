@@ -5,6 +5,8 @@
 
 #include "../../include/slb.h"
 
+constexpr int SLB_NXS = 3;  // internal streams of the *_step_host pipelines
+
 struct slb_batch_s {
     slb_config cfg;
     int N;        // tangent dimension of the full filter state
@@ -23,6 +25,8 @@ struct slb_batch_s {
     size_t stage_bytes;
     double *shared_small; // device copy of Q / R / params passed from host pointers
     int64_t *counts_dev;  // 4 counters for slb_status
+    cudaStream_t xs[SLB_NXS];  // chunk ring of the *_step_host entry points
+    cudaEvent_t ev_start, ev_done[SLB_NXS];
 };
 
 namespace slb {

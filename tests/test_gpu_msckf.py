@@ -109,3 +109,19 @@ def test_msckf_full_size_properties():
         np.testing.assert_array_equal(mu[r * 512:(r + 1) * 512], g.mu())
         np.testing.assert_array_equal(P[r * 512:(r + 1) * 512], g.P())
     assert np.linalg.eigvalsh(P[::257]).min() > 0
+
+
+def test_msckf_step_host_matches_device_path():
+    B, k = 300, 10
+    sc = synth.msckf_scenario(B, seed=91, k=k)
+    a, b = engine.Msckf(B, nclones=k), engine.Msckf(B, nclones=k)
+    for f in (a, b):
+        f.set_state(sc["mu"], sc["P"])
+    a.predict(engine.PM_MSCKF_DELTAPOSE, sc["u"], 0.0, sc["Q"])
+    a.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"])
+    out = np.empty((B, 13 + 7 * k))
+    b.step_host(engine.PM_MSCKF_DELTAPOSE, engine.MM_MSCKF_REPROJ, sc["u"], 0.0, sc["Q"], np.ascontiguousarray(sc["landmarks"]),
+                sc["z"], sc["R"], mu_out=out)
+    np.testing.assert_array_equal(out, a.mu())
+    np.testing.assert_array_equal(b.P(), a.P())
+    np.testing.assert_array_equal(b.outliers(), a.outliers())

@@ -150,3 +150,19 @@ def test_ensemble_stats_matches_host(slo):
     assert out[0] == B
     np.testing.assert_allclose(out[1:10], X.sum(0), rtol=1e-10, atol=1e-9)
     np.testing.assert_allclose(out[10:].reshape(9, 9), X.T @ X, rtol=1e-10, atol=1e-9)
+
+
+@pytest.mark.parametrize("B", [40000, 65536 + 17])
+def test_ukf_step_host_chunked_pipeline_is_bitwise_the_device_path(B):
+    """slb_ukf_step_host cuts batches >= 32768 into chunks on internal streams (H2D / kernel / D2H overlap);
+    ragged sizes must give exactly what the single-launch device path gives."""
+    sc = synth.ukfom_scenario(B, seed=37)
+    a, b = engine.Ukf(B), engine.Ukf(B)
+    a.set_state(sc["mu"], sc["P"])
+    b.set_state(sc["mu"], sc["P"])
+    a.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"])
+    out = np.empty((B, 10))
+    b.step_host(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"], mu_out=out)
+    np.testing.assert_array_equal(out, a.mu())
+    np.testing.assert_array_equal(b.P(), a.P())
+    np.testing.assert_array_equal(b.status(), a.status())

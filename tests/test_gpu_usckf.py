@@ -196,3 +196,19 @@ def test_usckf_fleet_properties():
         np.testing.assert_array_equal(mu[r * 2048:(r + 1) * 2048], g.mu())
         np.testing.assert_array_equal(P[r * 2048:(r + 1) * 2048], g.P())
     assert np.linalg.eigvalsh(P[::511]).min() > 0
+
+
+def test_usckf_step_host_chunked_pipeline_is_bitwise_the_device_path():
+    B, npri = 33000, 500
+    sc = synth.usckf_scenario(npri, seed=77)
+    rep = -(-B // npri)
+    u, z = np.tile(sc["u"], (rep, 1))[:B].copy(), np.tile(sc["z"], (rep, 1))[:B].copy()
+    a, b = engine.Usckf(B), engine.Usckf(B)
+    for f in (a, b):
+        f.set_state(sc["mu"], sc["P"], replicate=True)
+    a.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u, sc["dt"], sc["Q"], z, sc["R"])
+    out = np.empty((B, 51))
+    b.step_host(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u, sc["dt"], sc["Q"], z, sc["R"], mu_out=out)
+    np.testing.assert_array_equal(out, a.mu())
+    np.testing.assert_array_equal(b.P(first=2048), a.P(first=2048))
+    np.testing.assert_array_equal(b.status(), a.status())
