@@ -46,14 +46,19 @@ SLB_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
 // =====================================================================================================
 constexpr int PRED_PR = 366;           // packed rows 24..35: T(36) - T(24) (USCKF; MSCKF uses 78 of it)
 constexpr int PRED_PF = 28 * 12;       // feature-row segments, nk + nl <= 28
-constexpr int PRED_SM = PRED_PR + PRED_PF + 78 + 25 * 13 + 144 + 144 + 1;  // doubles per warp (odd)
+constexpr int PRED_SM = PRED_PR + PRED_PF + 78 + 25 * 13 + 144 + 144 + 3;  // doubles per warp (even: 16-B aligned
+                                                                           // warps for the bulk copy; last slot = mbarrier)
+SLB_DEV void pred_cp_async8(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr(smem_dst)), "l"(gsrc) : "memory");
+}
+SLB_DEV void pred_cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ROW0: first row of the 12x12 block; MU0: q-vector offset of the block's mean; CROSS: propagate the
 // cross-covariances of the block's rows/columns with the rest of the state (USCKF) or not (MSCKF).
 template <int PM, int WPB, int ROW0, int MU0, bool CROSS>
 __global__ void __launch_bounds__(WPB * 32, 2) predict12_kernel(slb::FilterArgs a) {
     typedef LayState12 L;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int inst = blockIdx.x * WPB + w;
     if (inst >= a.B) return;
@@ -66,15 +71,32 @@ __global__ void __launch_bounds__(WPB * 32, 2) predict12_kernel(slb::FilterArgs 
     double *mug = a.mu + (size_t)inst * a.qstride;
     auto PR = [&](int r, int c) -> double & { return Pr[tri(ROW0 + r, c) - T0]; };  // row ROW0+r, col c
 
-    for (int e = lane; e < SPAN; e += 32) Pr[e] = Pg[T0 + e];
+    // The block's rows are one contiguous span of the packed record: one TMA bulk copy (UBLKCP) brings it in,
+    // the 12-wide feature-row segments follow as LDGSTS; the mean and the control input load meanwhile.
+    static_assert((T0 * 8) % 16 == 0 && (SPAN * 8) % 16 == 0 && PRED_SM % 2 == 0, "bulk copy needs 16-byte alignment");
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Fk + 144);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, SPAN * 8);
+        bulk_g2s(Pr, Pg + T0, SPAN * 8, bar);
+    }
     for (int e = lane; e < nf * 12; e += 32) {
         const int r = e / 12, c = e - r * 12;
-        Pf[e] = Pg[tri(36 + r, 24 + c)];
+        pred_cp_async8(Pf + e, Pg + tri(36 + r, 24 + c));
     }
     double mu[13];
 #pragma unroll
     for (int c = 0; c < 13; ++c) mu[c] = mug[MU0 + c];
+    ProcessModel<PM> f;
+    {
+        double u[ProcessModel<PM>::NU];
+#pragma unroll
+        for (int c = 0; c < ProcessModel<PM>::NU; ++c) u[c] = a.u[(size_t)inst * ProcessModel<PM>::NU + c];
+        f.prepare(u, a.dt);
+    }
+    pred_cp_async_wait_all();
     __syncwarp();
+    mbar_wait(bar, 0);
 
     // ---- Cholesky of Pk_i (12x12): lane l < 12 owns row l; rows are broadcast with shuffles -----------
     double row[12];
@@ -107,13 +129,6 @@ __global__ void __launch_bounds__(WPB * 32, 2) predict12_kernel(slb::FilterArgs 
     __syncwarp();
 
     // ---- sigma point `lane` (Usckf.hpp:572-598), process model (:141) ---------------------------------
-    ProcessModel<PM> f;
-    {
-        double u[ProcessModel<PM>::NU];
-#pragma unroll
-        for (int c = 0; c < ProcessModel<PM>::NU; ++c) u[c] = a.u[(size_t)inst * ProcessModel<PM>::NU + c];
-        f.prepare(u, a.dt);
-    }
     const bool act = lane < 25;
     const int j = (lane - 1) >> 1;
     const double sgn = (lane & 1) ? 1.0 : -1.0;

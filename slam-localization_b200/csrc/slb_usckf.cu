@@ -150,6 +150,18 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
         return;
     }
     __syncwarp();
+    // The tiles were consumed by the factorisation; Pk -= K S K^T needs Pk again.  Re-issue the same loads now
+    // (L2 hits) so their latency hides behind the sigma-point / gain phases instead of stalling the epilogue.
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        const int i = a_ + 4 * r;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+            if (C::exists(r, c)) {
+                const int j = b_ + 8 * c;
+                T[r][c] = (i < N && j <= i) ? __ldcg(Pg + rowoff[r] + 8 * c) : 0.0;
+            }
+    }
 
     // ---- sigma points through h (:275-278), lane per point ---------------------------------------------
     constexpr int NPASS = (NSIG + 31) / 32;
@@ -337,10 +349,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
             for (int c = 0; c < CT; ++c)
                 if (C::exists(r, c)) {
                     const int j = b_ + 8 * c;
-                    if (i < N && j <= i) {
-                        const int e = rowoff[r] + 8 * c;
-                        Pg[e] = Pg[e] - (ks[0] * kc[c][0] + ks[1] * kc[c][1] + ks[2] * kc[c][2]);
-                    }
+                    if (i < N && j <= i)
+                        Pg[rowoff[r] + 8 * c] = T[r][c] - (ks[0] * kc[c][0] + ks[1] * kc[c][1] + ks[2] * kc[c][2]);
                 }
         }
     }

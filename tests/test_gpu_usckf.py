@@ -212,3 +212,38 @@ def test_usckf_step_host_chunked_pipeline_is_bitwise_the_device_path():
     np.testing.assert_array_equal(out, a.mu())
     np.testing.assert_array_equal(b.P(first=2048), a.P(first=2048))
     np.testing.assert_array_equal(b.status(), a.status())
+
+
+def test_usckf_config1_10k_steps_free_running(slo):
+    """BASELINE configs[0]: USCKF, 12-dof IMU-driven state + cloned poses, 1 kHz inputs, 10,000 free-running
+    steps (predict every step, VO update every 3rd, the clone / setMeasurement cycle every 12th) on the GPU and
+    on the CPU oracle from the same prior; north_star tolerance after 10k steps: 1e-6, symmetric PSD P."""
+    B, steps, dt = 4, 10000, 1e-3
+    sc = synth.usckf_scenario(B, seed=147)
+    Q = 0.1 * dt * np.eye(12)
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], sc["P"])
+    mo, Po = sc["mu"], sc["P"]
+    rng = np.random.default_rng(148)
+    Rk = 0.008 * np.eye(3)
+    for k in range(steps):
+        u = np.concatenate([rng.normal(size=(B, 3)), rng.normal(size=(B, 3)) * 0.2 + 0.1 * np.sin(1e-3 * k)], axis=1)
+        f.predict(engine.PM_USCKF_TEST, u, dt, Q)
+        mo, Po, st, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, mo, Po, u, dt, Q, None, None,
+                                       update=False, nthreads=4)
+        if k % 3 == 2:
+            z = mo[:, 39:42] + rng.normal(size=(B, 3)) * 0.1
+            f.update(engine.MM_USCKF_VO, z, sc["R"])
+            mo, Po, st, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, mo, Po, None, 0.0, None, z, sc["R"],
+                                           predict=False, nthreads=4)
+        if k % 12 == 11:
+            for mode in (engine.STATEK_L, engine.STATEK_I):
+                f.cloning(mode)
+                mo, Po = slo.usckf_clone(mode, 3, 9, mo, Po)
+            zk = 3.3 + 0.1 * rng.normal(size=(B, 3))
+            f.set_measurement(engine.STATEK, zk, Rk)
+            mo, Po = slo.usckf_set_measurement(slo.STATEK, 3, 9, mo, Po, zk, Rk)
+    assert not f.status().any()
+    P = f.P()
+    parity.assert_parity(slo, AUG, f.mu(), P, mo, parity.symmetrize_lower(Po), nfeat=12, tol=parity.LONG_TOL)
+    assert np.linalg.eigvalsh(P).min() > -1e-12 * np.abs(P).max()
