@@ -5,45 +5,128 @@
 // update (Msckf.hpp:220-277, removeOutliers :723-754, applyDelta :659-666) at BASELINE config 3
 // (10 clones -> N = 72, 145 sigma points, 50 features -> m = 100) keeps everything of one instance in
 // shared memory (~224 KB: one CTA per SM, persistent over the batch):
-//   A  5056 doubles : P -> L (Cholesky in place) ... later S -> Ls ... later P_new -> L2 -> P_out
-//   B 14645 doubles : Z (145 x 101) ... later compacted S'/Pxz' (outliers) ... later X / D (145 x 83)
-//   C  7272 doubles : W -> covXZ (in-place TRMM) -> Y = covXZ Ls^-T (in-place TRSM)
+//   A  5056 doubles : P -> L (Cholesky in place) ... later S -> Ls ... later P_new -> L2
+//   B 14800 doubles : Z (148 x 100) ... later compacted S' (outliers) ... later X / D (148 x 84)
+//   C  7200 doubles : W -> covXZ (in-place TRMM) -> Y = covXZ Ls^-T (in-place TRSM)
 // Algebra: with S = Ls Ls^T and Y = covXZ Ls^-T the reference's  K = covXZ S^-1, Pk -= K S K^T,
 // delta = K nu  become  Pk -= Y Y^T,  delta = Y (Ls^-1 nu)  -- same maths as :257-263 without forming
 // the explicit inverse (quirk Q9).  covXZ = L W with W_j = 0.5 (Z+_j - Z-_j), as in the other kernels.
+//
+// FP64 tensor cores: every rank-k contraction here (S = Zc^T Zc, covXZ = L W, the trailing updates of the
+// blocked Cholesky / triangular solve, P - Y Y^T, the re-estimated covariance D^T D) runs as 8x8x4 DMMA
+// tiles (mma.sync.m8n8k4.f64).  profiles/r01_dmma_vs_dfma_peak.txt: on B200 the DMMA pipe delivers the same
+// 37 TFLOP/s as the SIMT FP64 pipe, so it does not raise the roofline -- but one DMMA replaces 8 DFMA issue
+// slots per lane and needs 2 operand loads per 8 FMA instead of the 4x4 register tile's 8 per 16, and this
+// kernel was bound by instruction issue and shared-memory operand traffic (FP64 pipe 7.5 % busy before),
+// not by FP64 throughput.  Row strides of the [k][col] / [row][k] operand arrays are = 4 (mod 16) doubles so a
+// fragment load (4 k x 8 rows-or-cols) touches 32 distinct banks.
 #include "slb_predict12.cuh"
 
 namespace slbd {
 
 constexpr int MS_T = 256;          // threads per CTA
-constexpr int MS_NMAX = 72, MS_MMAX = 100, MS_NSMAX = 145, MS_QMAX = 83;
+constexpr int MS_W = MS_T / 32;
+constexpr int MS_NMAX = 72, MS_MMAX = 100, MS_NSMAX = 145;
+constexpr int MS_NSPAD = 148;                    // sigma-point count padded to the DMMA k-step
 constexpr int MS_A = 5056;                       // >= 100*101/2 and >= 72*73/2
-constexpr int MS_ZS = MS_MMAX + 1;               // odd row stride of Z and of covXZ / Y
-constexpr int MS_B = MS_NSMAX * MS_ZS;           // 14645
-constexpr int MS_C = MS_NMAX * MS_ZS;            // 7272
-constexpr int MS_D = 768;                        // small vectors
+constexpr int MS_ZS = 100;                       // row stride of Z and of covXZ / Y   (= 4 mod 16)
+constexpr int MS_QS = 84;                        // row stride of the sigma points X / deviations D (= 4 mod 16)
+constexpr int MS_B = MS_NSPAD * MS_ZS;           // 14800
+constexpr int MS_C = MS_NMAX * MS_ZS;            // 7200
+constexpr int MS_D = 896;                        // small vectors
 constexpr int MS_SMEM_DOUBLES = MS_A + MS_B + MS_C + MS_D;
 static_assert(MS_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF update working set exceeds shared memory");
-static_assert(MS_NSMAX * MS_QMAX <= MS_B, "sigma points do not fit region B");
+static_assert(MS_NSPAD * MS_QS <= MS_B, "sigma points do not fit region B");
+static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_B, "compacted S does not fit region B");
 
-// In-place Cholesky of a packed lower matrix in shared memory, right-looking, all threads of the CTA.
-// ok_flag (shared int) is cleared on a non-positive pivot.
-SLB_DEV void chol_smem(double *A, int n, int *ok_flag) {
-    const int tid = threadIdx.x;
-    const int ti = tid >> 4, tj = tid & 15;
-    for (int k = 0; k < n; ++k) {
-        if (tid == 0) {
-            const double x = A[tri(k, k)];
-            if (!(x > 0.0)) *ok_flag = 0;
-            A[tri(k, k)] = sqrt(x);
+// D(8x8) += A(8x4) B(4x8): lane holds a = A[lane>>2][lane&3], b = B[lane&3][lane>>2] and the accumulator
+// pair d0 = D[lane>>2][2*(lane&3)], d1 = D[lane>>2][2*(lane&3)+1].
+SLB_DEV void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+// linear index of a lower-triangular tile -> (tr, tc), tc <= tr
+SLB_DEV void tri_tile(int t, int &tr, int &tc) {
+    int r = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    r += (tri(r + 1, 0) <= t) - (tri(r, 0) > t);
+    tr = r;
+    tc = t - tri(r, 0);
+}
+
+// In-place Cholesky of a packed lower matrix in shared memory, all threads of the CTA.  Blocked right-looking
+// with 8-wide panels: warp 0 factors the 8x8 diagonal block (lane per row, shuffle broadcasts), one thread per
+// row solves the panel below it, then every warp rank-8-updates its share of the trailing 8x8 tiles with two
+// DMMAs each.  invd[i] = 1 / L_ii is left for the triangular solves.  ok_flag (shared int) is cleared on a
+// non-positive pivot (Eigen::LLT's info(), which the reference ignores: quirk Q8).
+SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int p0 = 0; p0 < n; p0 += 8) {
+        const int pb = min(8, n - p0);
+        if (warp == 0) {
+            double row[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) row[c] = (lane < pb && c <= lane) ? A[tri(p0 + lane, p0 + c)] : 0.0;
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                double sk = row[k];
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    if (p < k) sk = fma(-row[p], bcast(row[p], k), sk);
+                const double x = bcast(sk, k);
+                if (k < pb) {
+                    ok = ok && (x > 0.0);
+                    double sx, inv;
+                    sqrt_rsqrt(x, sx, inv);
+                    row[k] = (lane == k) ? sx : sk * inv;
+                    if (lane == 0) invd[p0 + k] = inv;
+                }
+            }
+            if (lane < pb) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c <= lane) A[tri(p0 + lane, p0 + c)] = row[c];
+            }
+            if (!ok && lane == 0) *ok_flag = 0;
         }
         __syncthreads();
-        const double inv = 1.0 / A[tri(k, k)];
-        for (int i = k + 1 + tid; i < n; i += MS_T) A[tri(i, k)] *= inv;
+        const int r0 = p0 + pb;
+        for (int i = r0 + tid; i < n; i += MS_T) {
+            double x[8];
+            double *Ai = A + tri(i, p0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c < pb) {
+                    double sv = Ai[c];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < c) sv = fma(-x[q], A[tri(p0 + c, p0 + q)], sv);
+                    x[c] = sv * invd[p0 + c];
+                    Ai[c] = x[c];
+                }
+            }
+        }
         __syncthreads();
-        for (int i = k + 1 + ti; i < n; i += 16) {
-            const double lik = A[tri(i, k)];
-            for (int j = k + 1 + tj; j <= i; j += 16) A[tri(i, j)] -= lik * A[tri(j, k)];
+        const int nt = (n - r0 + 7) >> 3, ntiles = nt * (nt + 1) / 2;
+        for (int t = warp; t < ntiles; t += MS_W) {
+            int tr, tc;
+            tri_tile(t, tr, tc);
+            const int i0 = r0 + 8 * tr, j0 = r0 + 8 * tc;
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += 4) {
+                const int kk = k0 + fk;
+                const double av = (i0 + fr < n && kk < pb) ? A[tri(i0 + fr, p0 + kk)] : 0.0;
+                const double bv = (j0 + fr < n && kk < pb) ? A[tri(j0 + fr, p0 + kk)] : 0.0;
+                dmma884(d0, d1, av, bv);
+            }
+            const int i = i0 + fr, j = j0 + 2 * fk;
+            if (i < n) {
+                if (j <= i) A[tri(i, j)] -= d0;
+                if (j + 1 <= i) A[tri(i, j + 1)] -= d1;
+            }
         }
         __syncthreads();
     }
@@ -57,12 +140,15 @@ SLB_DEV bool ms_so3(int b) { return b < 4 ? b == 1 : ((b - 4) & 1); }
 __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a) {
     extern __shared__ __align__(16) double sm[];
     double *RA = sm, *RB = RA + MS_A, *RC = RB + MS_B, *RD = RC + MS_C;
-    double *mu = RD, *zbar = mu + 84, *nu = zbar + 100, *wv = nu + 100, *dl = wv + 100, *acc = dl + 72, *ref = acc + 72;
-    int *kept = reinterpret_cast<int *>(ref + 84);  // 100 ints
-    int *flags = kept + 100;                        // [0] chol ok, [1] kept count, [2] outliers, [3] loop, [4] iters
+    double *mu = RD, *zbar = mu + 84, *nu = zbar + 100, *wv = nu + 100, *dl = wv + 100, *acc = dl + 72, *ref = acc + 72,
+           *invd = ref + 84;  // 104
+    int *kept = reinterpret_cast<int *>(invd + 104);  // 100 ints
+    int *flags = kept + 100;                          // [0] chol ok, [1] kept count, [2] outliers, [3] loop, [4] iters
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;          // DMMA fragment coordinates of this lane
     const int k = a.k, N = 12 + 6 * k, QD = 13 + 7 * k, NS = 2 * N + 1, M = a.m, NF = M / 2, NB = 4 + 2 * k;
     const int NP = N * (N + 1) / 2;
+    const int nrt = (N + 7) >> 3;                     // 8-row tiles of the state
 
     for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         double *Pg = a.P + (size_t)inst * a.pstride;
@@ -74,7 +160,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         if (tid == 0) { flags[0] = 1; flags[1] = M; flags[2] = 0; }
         __syncthreads();
         // ---- L = chol(Pk) (:229 -> :412) -------------------------------------------------------------
-        chol_smem(RA, N, flags);
+        chol_blocked(RA, N, flags, invd);
         int st = 0;
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
@@ -101,8 +187,9 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                                           __ldg(a.params + 3 * f + 2) - p[2]};
                     double pc[3];
                     quat_rotate_inv(q, dv, pc);
-                    Zr[2 * f] = pc[0] / pc[2];
-                    Zr[2 * f + 1] = pc[1] / pc[2];
+                    const double iz = rcp_fast(pc[2]);
+                    Zr[2 * f] = pc[0] * iz;
+                    Zr[2 * f + 1] = pc[1] * iz;
                 }
             }
         }
@@ -116,96 +203,97 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             nu[tid] = zg[tid] - zb;
         }
         // ---- W_j = 0.5 (Z+_j - Z-_j) into region C ---------------------------------------------------
-        for (int e = tid; e < N * M; e += MS_T) {
-            const int j = e / M, c = e - j * M;
-            RC[j * MS_ZS + c] = 0.5 * (RB[(1 + 2 * j) * MS_ZS + c] - RB[(2 + 2 * j) * MS_ZS + c]);
-        }
+        for (int j = warp; j < N; j += MS_W)
+            for (int c = lane; c < M; c += 32)
+                RC[j * MS_ZS + c] = 0.5 * (RB[(1 + 2 * j) * MS_ZS + c] - RB[(2 + 2 * j) * MS_ZS + c]);
         __syncthreads();
         // centre Z for the covariance
-        for (int e = tid; e < NS * M; e += MS_T) {
-            const int s = e / M, c = e - s * M;
-            RB[s * MS_ZS + c] -= zbar[c];
-        }
-        // ---- covXZ = L W (:239 -> :635-657): in-place TRMM on region C, 8 rows per pass, bottom up --------
-        for (int i0 = ((N - 1) / 8) * 8; i0 >= 0; i0 -= 8) {
-            const int rows = min(8, N - i0);
-            double out[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int o = tid + MS_T * t;
-                double s = 0.0;
-                if (o < rows * M) {
-                    const int i = i0 + o / M, c = o % M;
-                    for (int j = 0; j <= i; ++j) s += RA[tri(i, j)] * RC[j * MS_ZS + c];
+        for (int s = warp; s < NS; s += MS_W)
+            for (int c = lane; c < M; c += 32) RB[s * MS_ZS + c] -= zbar[c];
+        // ---- covXZ = L W (:239 -> :635-657): in-place TRMM on region C.  A warp owns an 8-column strip and
+        //      walks the row tiles bottom-up (row tile tr reads only rows <= 8 tr + 7 of its own strip) ------
+        for (int tc = warp; tc < ((M + 7) >> 3); tc += MS_W) {
+            const int bc = 8 * tc + fr;
+            for (int tr = nrt - 1; tr >= 0; --tr) {
+                const int ai = 8 * tr + fr;
+                double d0 = 0.0, d1 = 0.0;
+                for (int k0 = 0; k0 < 8 * tr + 8; k0 += 4) {
+                    const int kk = k0 + fk;
+                    const double av = (ai < N && kk <= ai) ? RA[tri(ai, kk)] : 0.0;
+                    const double bv = (kk < N && bc < M) ? RC[kk * MS_ZS + bc] : 0.0;
+                    dmma884(d0, d1, av, bv);
                 }
-                out[t] = s;
+                __syncwarp();
+                const int oc = 8 * tc + 2 * fk;
+                if (ai < N) {
+                    if (oc < M) RC[ai * MS_ZS + oc] = d0;
+                    if (oc + 1 < M) RC[ai * MS_ZS + oc + 1] = d1;
+                }
+                __syncwarp();
             }
-            __syncthreads();
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int o = tid + MS_T * t;
-                if (o < rows * M) RC[(i0 + o / M) * MS_ZS + o % M] = out[t];
-            }
-            __syncthreads();
         }
-        // ---- S = 0.5 Zc^T Zc + R (:238) into region A (L is dead), 5x5 register tiles -------------------
+        __syncthreads();
+        // ---- S = 0.5 Zc^T Zc + R (:238) into region A (L is dead): lower 8x8 tiles, K = sigma points ----------
         {
-            const int nt = (M + 4) / 5;
-            int tr = 0, rem = tid;
-            while (rem > tr) { rem -= tr + 1; ++tr; }  // tid -> (tr, tc) lower tile index
-            const int tc = rem;
-            if (tr < nt) {
-                double accS[5][5];
-#pragma unroll
-                for (int x = 0; x < 5; ++x)
-#pragma unroll
-                    for (int y = 0; y < 5; ++y) accS[x][y] = 0.0;
-                const int r0 = 5 * tr, c0 = 5 * tc;
-                for (int s = 0; s < NS; ++s) {
-                    const double *Zr = RB + s * MS_ZS;
-                    double zr[5], zc[5];
-#pragma unroll
-                    for (int x = 0; x < 5; ++x) { zr[x] = (r0 + x < M) ? Zr[r0 + x] : 0.0; zc[x] = (c0 + x < M) ? Zr[c0 + x] : 0.0; }
-#pragma unroll
-                    for (int x = 0; x < 5; ++x)
-#pragma unroll
-                        for (int y = 0; y < 5; ++y) accS[x][y] += zr[x] * zc[y];
+            const int nt = (M + 7) >> 3, ntiles = nt * (nt + 1) / 2;
+            for (int t = warp; t < ntiles; t += MS_W) {
+                int tr, tc;
+                tri_tile(t, tr, tc);
+                const int ar = 8 * tr + fr, bc = 8 * tc + fr;
+                const bool av_ok = ar < M, bv_ok = bc < M;
+                double d0 = 0.0, d1 = 0.0;
+                for (int k0 = 0; k0 < NS; k0 += 4) {
+                    const int kk = k0 + fk;
+                    const double av = (av_ok && kk < NS) ? RB[kk * MS_ZS + ar] : 0.0;
+                    const double bv = (bv_ok && kk < NS) ? RB[kk * MS_ZS + bc] : 0.0;
+                    dmma884(d0, d1, av, bv);
                 }
-#pragma unroll
-                for (int x = 0; x < 5; ++x)
-#pragma unroll
-                    for (int y = 0; y < 5; ++y) {
-                        const int r = r0 + x, c = c0 + y;
-                        if (r < M && c <= r) RA[tri(r, c)] = 0.5 * accS[x][y] + __ldg(a.R + r * M + c);
-                    }
+                const int r = 8 * tr + fr, c = 8 * tc + 2 * fk;
+                if (r < M) {
+                    if (c <= r) RA[tri(r, c)] = 0.5 * d0 + __ldg(a.R + r * M + c);
+                    if (c + 1 <= r) RA[tri(r, c + 1)] = 0.5 * d1 + __ldg(a.R + r * M + c + 1);
+                }
             }
         }
         __syncthreads();
         // ---- removeOutliers (:241 -> :723-754), index quirk Q6 reproduced ---------------------------------
-        if (a.gate && tid == 0) {
-            int len = M, out = 0, i = 0;
-            for (int e = 0; e < M; ++e) kept[e] = e;
-            while (i < len / 2) {
-                const int ia = kept[2 * i], ib = kept[2 * i + 1];
-                const double s00 = RA[tri(ia, ia)], s11 = RA[tri(ib, ib)], s10 = ib > ia ? RA[tri(ib, ia)] : RA[tri(ia, ib)];
+        if (a.gate) {
+            // every feature against the 2-dof 5% bound in parallel first: while nothing is rejected the reference's
+            // sequential scan keeps the identity indexing, so "all accepted" needs no scan at all
+            bool rej = false;
+            if (tid < NF) {
+                const int ia = 2 * tid, ib = ia + 1;
+                const double s00 = RA[tri(ia, ia)], s11 = RA[tri(ib, ib)], s10 = RA[tri(ib, ia)];
                 const double det = s00 * s11 - s10 * s10;
                 const double v0 = nu[ia], v1 = nu[ib];
                 const double m2 = (v0 * (s11 * v0 - s10 * v1) + v1 * (s00 * v1 - s10 * v0)) / det;
-                if (!(m2 < 5.99)) {
-                    // removeRow(2i); removeRow(2i+1) -- the second index is NOT re-based (Q6)
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const int pos = 2 * i + pass, num = len - 1;
-                        if (pos < num)
-                            for (int e = pos; e < num; ++e) kept[e] = kept[e + 1];
-                        len = num;
-                    }
-                    ++out;
-                } else {
-                    ++i;
-                }
+                rej = !(m2 < 5.99);
             }
-            flags[1] = len;
-            flags[2] = out;
+            if (__syncthreads_or(rej) && tid == 0) {
+                int len = M, out = 0, i = 0;
+                for (int e = 0; e < M; ++e) kept[e] = e;
+                while (i < len / 2) {
+                    const int ia = kept[2 * i], ib = kept[2 * i + 1];
+                    const double s00 = RA[tri(ia, ia)], s11 = RA[tri(ib, ib)], s10 = ib > ia ? RA[tri(ib, ia)] : RA[tri(ia, ib)];
+                    const double det = s00 * s11 - s10 * s10;
+                    const double v0 = nu[ia], v1 = nu[ib];
+                    const double m2 = (v0 * (s11 * v0 - s10 * v1) + v1 * (s00 * v1 - s10 * v0)) / det;
+                    if (!(m2 < 5.99)) {
+                        // removeRow(2i); removeRow(2i+1) -- the second index is NOT re-based (Q6)
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int pos = 2 * i + pass, num = len - 1;
+                            if (pos < num)
+                                for (int e = pos; e < num; ++e) kept[e] = kept[e + 1];
+                            len = num;
+                        }
+                        ++out;
+                    } else {
+                        ++i;
+                    }
+                }
+                flags[1] = len;
+                flags[2] = out;
+            }
         }
         __syncthreads();
         const int mk = flags[1];
@@ -230,36 +318,54 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             __syncthreads();
         }
         // ---- Ls = chol(S') -------------------------------------------------------------------------------
-        chol_smem(Sp, mk, flags);
+        chol_blocked(Sp, mk, flags, invd);
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
         }
-        // ---- Y = covXZ' Ls^-T: right-looking TRSM, 4 columns per pass ---------------------------------
-        for (int q0 = 0; q0 < mk; q0 += 4) {
-            const int qb = min(4, mk - q0);
-            if (tid < N) {
-                double *row = Xz + tid * MS_ZS;
-                for (int q = q0; q < q0 + qb; ++q) {
-                    double s = row[q];
-                    for (int p = q0; p < q; ++p) s -= Sp[tri(q, p)] * row[p];
-                    row[q] = s * rcp_fast(Sp[tri(q, q)]);
+        // ---- Y = covXZ' Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates -----
+        for (int p0 = 0; p0 < mk; p0 += 8) {
+            const int pb = min(8, mk - p0);
+            for (int i = tid; i < N; i += MS_T) {
+                double *row = Xz + i * MS_ZS + p0;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < pb) {
+                        double sv = row[c];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q < c) sv = fma(-x[q], Sp[tri(p0 + c, p0 + q)], sv);
+                        x[c] = sv * invd[p0 + c];
+                        row[c] = x[c];
+                    }
                 }
             }
             __syncthreads();
-            const int rest = mk - q0 - qb;
-            for (int e = tid; e < N * rest; e += MS_T) {
-                const int i = e / rest, c = q0 + qb + e % rest;
-                double s = Xz[i * MS_ZS + c];
-                for (int p = q0; p < q0 + qb; ++p) s -= Xz[i * MS_ZS + p] * Sp[tri(c, p)];
-                Xz[i * MS_ZS + c] = s;
+            const int j0 = p0 + pb, nct = (mk - j0 + 7) >> 3;
+            for (int t = warp; t < nrt * nct; t += MS_W) {
+                const int tr = t / nct, tc = t - tr * nct;
+                const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < 8; k0 += 4) {
+                    const int kk = k0 + fk;
+                    const double av = (ai < N && kk < pb) ? Xz[ai * MS_ZS + p0 + kk] : 0.0;
+                    const double bv = (bj < mk && kk < pb) ? Sp[tri(bj, p0 + kk)] : 0.0;
+                    dmma884(d0, d1, av, bv);
+                }
+                const int oc = j0 + 8 * tc + 2 * fk;
+                if (ai < N) {
+                    if (oc < mk) Xz[ai * MS_ZS + oc] -= d0;
+                    if (oc + 1 < mk) Xz[ai * MS_ZS + oc + 1] -= d1;
+                }
             }
             __syncthreads();
         }
         // ---- w = Ls^-1 nu (warp 0), delta = Y w ------------------------------------------------------
         if (warp == 0) {
             for (int q = 0; q < mk; ++q) {
-                const double wq = nu[q] * rcp_fast(Sp[tri(q, q)]);
+                const double wq = nu[q] * invd[q];
                 __syncwarp();
                 if (lane == 0) wv[q] = wq;
                 for (int c = q + 1 + lane; c < mk; c += 32) nu[c] -= Sp[tri(c, q)] * wq;
@@ -267,50 +373,37 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
-        for (int i = warp; i < N; i += MS_T / 32) {
+        for (int i = warp; i < N; i += MS_W) {
             double s = 0.0;
             for (int q = lane; q < mk; q += 32) s += Xz[i * MS_ZS + q] * wv[q];
             s = warp_sum(s);
             if (lane == 0) dl[i] = s;
         }
-        // ---- P_new = Pk - Y Y^T (:262) into region A from the HBM record, 4x4 register tiles ------------
+        // ---- P_new = Pk - Y Y^T (:262) into region A from the HBM record: lower 8x8 tiles, K = mk ------------
         __syncthreads();
         {
-            const int nt = (N + 3) / 4;
-            int tr = 0, rem = tid;
-            while (rem > tr) { rem -= tr + 1; ++tr; }
-            const int tc = rem;
-            if (tr < nt) {
-                double ac[4][4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) ac[x][y] = 0.0;
-                const int r0 = 4 * tr, c0 = 4 * tc;
-                for (int q = 0; q < mk; ++q) {
-                    double yr[4], yc[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        yr[x] = (r0 + x < N) ? Xz[(r0 + x) * MS_ZS + q] : 0.0;
-                        yc[x] = (c0 + x < N) ? Xz[(c0 + x) * MS_ZS + q] : 0.0;
-                    }
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) ac[x][y] += yr[x] * yc[y];
+            const int ntiles = nrt * (nrt + 1) / 2;
+            for (int t = warp; t < ntiles; t += MS_W) {
+                int tr, tc;
+                tri_tile(t, tr, tc);
+                const int ai = 8 * tr + fr, bj = 8 * tc + fr;
+                double d0 = 0.0, d1 = 0.0;
+                for (int k0 = 0; k0 < mk; k0 += 4) {
+                    const int kk = k0 + fk;
+                    const double av = (ai < N && kk < mk) ? Xz[ai * MS_ZS + kk] : 0.0;
+                    const double bv = (bj < N && kk < mk) ? Xz[bj * MS_ZS + kk] : 0.0;
+                    dmma884(d0, d1, av, bv);
                 }
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const int r = r0 + x, c = c0 + y;
-                        if (r < N && c <= r) RA[tri(r, c)] = Pg[tri(r, c)] - ac[x][y];
-                    }
+                const int r = ai, c = 8 * tc + 2 * fk;
+                if (r < N) {
+                    if (c <= r) RA[tri(r, c)] = Pg[tri(r, c)] - d0;
+                    if (c + 1 <= r) RA[tri(r, c + 1)] = Pg[tri(r, c + 1)] - d1;
+                }
             }
         }
         __syncthreads();
         // ---- applyDelta(K nu) (:263 -> :659-666): L2 = chol(P_new), X = mu [+] (delta +- L2 e_j) ----------
-        chol_smem(RA, N, flags);
+        chol_blocked(RA, N, flags, invd);
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
@@ -318,7 +411,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         if (tid < NS) {
             const int s = tid, j = s >= 1 ? (s - 1) >> 1 : 0;
             const double sgn = (s & 1) ? 1.0 : -1.0;
-            double *X = RB + s * MS_QMAX;
+            double *X = RB + s * MS_QS;
             for (int b = 0; b < NB; ++b) {
                 double d[3];
 #pragma unroll
@@ -347,7 +440,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             for (int b = 0; b < NB; ++b) {
                 double d[3] = {0.0, 0.0, 0.0};
                 if (tid < NS) {
-                    const double *X = RB + tid * MS_QMAX;
+                    const double *X = RB + tid * MS_QS;
                     const int qo = ms_qoff(b);
                     if (ms_so3(b)) {
                         double r[4];
@@ -398,7 +491,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         if (flags[4] >= 10000) st |= SLB_ST_MEAN_NOCONV;
         // deviations d_s = X_s [-] mean, in place (72 <= 83 slots per sigma point)
         if (tid < NS) {
-            double *X = RB + tid * MS_QMAX;
+            double *X = RB + tid * MS_QS;
             for (int b = 0; b < NB; ++b) {
                 const int qo = ms_qoff(b);
                 double d[3];
@@ -414,36 +507,25 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
-        // ---- Pk = 0.5 sum d d^T (:574-589) straight to the HBM record, 4x4 register tiles ----------------
+        // ---- Pk = 0.5 sum d d^T (:574-589) straight to the HBM record: lower 8x8 tiles, K = sigma points ------
         {
-            const int nt = (N + 3) / 4;
-            int tr = 0, rem = tid;
-            while (rem > tr) { rem -= tr + 1; ++tr; }
-            const int tc = rem;
-            if (tr < nt) {
-                double ac[4][4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) ac[x][y] = 0.0;
-                const int r0 = 4 * tr, c0 = 4 * tc;
-                for (int s = 0; s < NS; ++s) {
-                    const double *Dr = RB + s * MS_QMAX;
-                    double yr[4], yc[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) { yr[x] = (r0 + x < N) ? Dr[r0 + x] : 0.0; yc[x] = (c0 + x < N) ? Dr[c0 + x] : 0.0; }
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) ac[x][y] += yr[x] * yc[y];
+            const int ntiles = nrt * (nrt + 1) / 2;
+            for (int t = warp; t < ntiles; t += MS_W) {
+                int tr, tc;
+                tri_tile(t, tr, tc);
+                const int ar = 8 * tr + fr, bc = 8 * tc + fr;
+                double d0 = 0.0, d1 = 0.0;
+                for (int k0 = 0; k0 < NS; k0 += 4) {
+                    const int kk = k0 + fk;
+                    const double av = (ar < N && kk < NS) ? RB[kk * MS_QS + ar] : 0.0;
+                    const double bv = (bc < N && kk < NS) ? RB[kk * MS_QS + bc] : 0.0;
+                    dmma884(d0, d1, av, bv);
                 }
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const int r = r0 + x, c = c0 + y;
-                        if (r < N && c <= r) Pg[tri(r, c)] = 0.5 * ac[x][y];
-                    }
+                const int r = ar, c = 8 * tc + 2 * fk;
+                if (r < N) {
+                    if (c <= r) Pg[tri(r, c)] = 0.5 * d0;
+                    if (c + 1 <= r) Pg[tri(r, c + 1)] = 0.5 * d1;
+                }
             }
         }
         bool finite = true;

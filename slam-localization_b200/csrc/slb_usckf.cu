@@ -142,6 +142,19 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
 #pragma unroll
     for (int c = 0; c < NK; ++c) ft[c] = mug[39 + c];
 
+    // this lane's share of the mean for the final mu [+] K nu (lane b < 12 owns block b of the three States, lanes
+    // 12.. own the feature scalars): fetched now so that the epilogue does not wait on HBM
+    const int msidx = lane >> 2, mbw = lane & 3;
+    const int mqo = lane < 12 ? 13 * msidx + (mbw == 0 ? 0 : mbw == 1 ? 3 : mbw == 2 ? 7 : 10) : 39 + lane - 12;
+    double mym[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < 12) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < 3 || mbw == 1) mym[c] = mug[mqo + c];
+    } else if (lane - 12 < NK + NL) {
+        mym[0] = mug[mqo];
+    }
+
     // ---- Eigen::LLT of Pk (:537) ------------------------------------------------------------------------
     bool ok = true;
     CholStep<C, 0>::run(T, Ls, a_, b_, ok);
@@ -307,27 +320,24 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
     // ---- mu = mu [+] K nu (:299-301): lane b < 12 owns block b, lanes 12.. own the feature scalars -----
     bool finite = true;
     if (lane < 12) {
-        const int sidx = lane >> 2, bw = lane & 3;
-        const int qo = 13 * sidx + (bw == 0 ? 0 : bw == 1 ? 3 : bw == 2 ? 7 : 10);
         const double v[3] = {dl[3 * lane], dl[3 * lane + 1], dl[3 * lane + 2]};
-        if (bw == 1) {
-            const double q[4] = {mug[qo], mug[qo + 1], mug[qo + 2], mug[qo + 3]};
+        if (mbw == 1) {
             double e[4], o[4];
             so3_exp(v, 1.0, e);
-            quat_mul(q, e, o);
+            quat_mul(mym, e, o);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { mug[qo + c] = o[c]; finite = finite && isfinite(o[c]); }
+            for (int c = 0; c < 4; ++c) { mug[mqo + c] = o[c]; finite = finite && isfinite(o[c]); }
         } else {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const double o = mug[qo + c] + v[c];
-                mug[qo + c] = o;
+                const double o = mym[c] + v[c];
+                mug[mqo + c] = o;
                 finite = finite && isfinite(o);
             }
         }
     } else if (lane - 12 < NK + NL) {
-        const double o = mug[39 + lane - 12] + dl[36 + lane - 12];
-        mug[39 + lane - 12] = o;
+        const double o = mym[0] + dl[36 + lane - 12];
+        mug[mqo] = o;
         finite = finite && isfinite(o);
     }
     // ---- Pk -= K S K^T (:296) on the HBM record (lower triangle), same 2D-cyclic tiles as the load ------
