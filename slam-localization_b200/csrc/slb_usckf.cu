@@ -10,11 +10,13 @@
 //   point s (25 of 32 lanes); Fk = Pxy^T Pii^-1 is obtained as W^T L^-1 with W = 0.5 (dY+ - dY-) by a
 //   triangular solve, because X_i [-] mu_old is +-L e_j by construction (same algebra as :152-154,
 //   without the explicit inverse).
-// update (Usckf.hpp:260-308): the 48x48 Cholesky runs left-looking with every lane owning rows
-//   (lane) and (lane+32) of the factor in REGISTERS; finished rows are published through shared
-//   memory and re-read as broadcasts, so the inner loop is 1 LDS per 2 DFMA.  Sigma points are
-//   evaluated lane-per-point for the columns that can move h (j < 36+nk); the rest equal Z0.
+// update (Usckf.hpp:260-308): the 48x48 Cholesky runs right-looking on 2D-cyclic REGISTER tiles in its
+//   square-root-free form (see CholStep); finished columns are published through shared memory.
+//   Sigma points are evaluated lane-per-point for the columns that can move h (j < 36+nk); the rest
+//   equal Z0.
 //   P -= K S K^T is applied straight to the HBM record (re-read through L2), coalesced.
+#include <cstdlib>
+
 #include "slb_predict12.cuh"
 
 namespace slbd {
@@ -53,32 +55,35 @@ struct UpdCfg {
     }
 };
 
-// Right-looking Cholesky of the N x N covariance held 2D-cyclically in registers: lane (a, b), a = lane & 3,
-// b = lane >> 2, owns the entries (a + 4r, b + 8c).  Step K (compile-time, fully unrolled by recursion):
-// the pivot is broadcast from its owner, the 4 lanes holding column K scale it and publish it to shared memory
-// (column-major packed: exactly the layout the sigma points and L W need afterwards), then every lane
-// rank-1-updates its live tiles with two short operand vectors read back from that column.  Entries of
-// finished columns / of the upper triangle are never read again, so the update needs no predicate at all:
-// whole tiles are pruned at compile time and the rest is plain DFMA.
+// Right-looking factorisation of the N x N covariance held 2D-cyclically in registers: lane (a, b), a = lane & 3,
+// b = lane >> 2, owns the entries (a + 4r, b + 8c).  It is computed in the square-root-free form Pk = U D^-1 U^T
+// (U = L sqrt(D), unit-free "unscaled" columns: U(i,k) is the Schur-complement entry (i,k) at step k, D = diag U):
+// Eigen::LLT's factor is L(:,k) = U(:,k) / sqrt(d_k), a per-column scale that the consumers (sigma points, L W)
+// fold into their own per-column coefficients.  What this buys is the length of the serial chain per column: the
+// pivot's 1/sqrt no longer sits between the previous trailing update and the publication of the column.  Step K
+// (compile-time, fully unrolled by recursion): the 4 lanes holding column K publish it to shared memory as it is
+// (column-major packed: exactly the layout the sigma points and L W need afterwards), every lane rank-1-updates
+// its live tiles with U(i,K) and -U(j,K)/d_K read back from that column.  -1/d_K arrives from the previous step
+// (look-ahead: d_{K+1} = T(K+1,K+1) - U(K+1,K)^2/d_K is formed redundantly by all lanes from one broadcast of
+// the old diagonal entry, with the same operations as the owner's tile update so both agree bitwise), so the
+// reciprocal's latency overlaps the trailing update.  Entries of finished columns / of the upper triangle are
+// never read again, so the update needs no predicate at all: whole tiles are pruned at compile time and the rest
+// is plain DFMA.
 template <class C, int K>
 struct CholStep {
     template <class Tile>
-    SLB_DEV static void run(Tile &T, double *Ls, int a_, int b_, bool &ok) {
+    SLB_DEV static void run(Tile &T, double *Ls, int a_, int b_, bool &ok, double x, double nrcp) {
         constexpr int N = C::N, RT = C::RT, CT = C::CT;
-        constexpr int ak = K & 3, rk = K >> 2, bk = K & 7, ck = K >> 3, owner = ak + 4 * bk;
+        constexpr int rk = K >> 2, bk = K & 7, ck = K >> 3;
+        constexpr int K1 = K + 1 < N ? K + 1 : K;
+        constexpr int owner1 = (K1 & 3) + 4 * (K1 & 7);
         constexpr int base = C::cb(K) - K;
-        const double x = __shfl_sync(FULL, T[rk][ck], owner);
         ok = ok && (x > 0.0);
-        double sx, inv;
-        sqrt_rsqrt(x, sx, inv);
-        if (b_ == bk) {
+        const double xn_old = __shfl_sync(FULL, T[K1 >> 2][K1 >> 3], owner1);
 #pragma unroll
-            for (int r = rk; r < RT; ++r) {
-                const int i = a_ + 4 * r;
-                double v = T[r][ck] * inv;
-                if (r == rk && a_ == ak) v = sx;
-                if (i >= K && i < N) Ls[base + i] = v;
-            }
+        for (int r = rk; r < RT; ++r) {
+            const int i = a_ + 4 * r;
+            if (b_ == bk && i >= K && i < N) Ls[base + i] = T[r][ck];
         }
         __syncwarp();
         double li[RT], lj[CT];
@@ -87,19 +92,25 @@ struct CholStep {
             if (C::row_live(K, r)) li[r] = Ls[base + a_ + 4 * r];
 #pragma unroll
         for (int c = 0; c < CT; ++c)
-            if (C::col_live(K, c)) lj[c] = Ls[base + b_ + 8 * c];
+            if (C::col_live(K, c)) lj[c] = Ls[base + b_ + 8 * c] * nrcp;
+        double xn = x, nrcpn = nrcp;
+        if (K + 1 < N) {
+            const double u1 = Ls[base + K + 1];
+            xn = fma(u1, u1 * nrcp, xn_old);
+            nrcpn = -rcp_fast(xn);
+        }
 #pragma unroll
         for (int r = 0; r < RT; ++r)
 #pragma unroll
             for (int c = 0; c < CT; ++c)
-                if (C::live(K, r, c)) T[r][c] = fma(-li[r], lj[c], T[r][c]);
-        CholStep<C, K + 1>::run(T, Ls, a_, b_, ok);
+                if (C::live(K, r, c)) T[r][c] = fma(li[r], lj[c], T[r][c]);
+        CholStep<C, K + 1>::run(T, Ls, a_, b_, ok, xn, nrcpn);
     }
 };
 template <class C>
 struct CholStep<C, C::N> {
     template <class Tile>
-    SLB_DEV static void run(Tile &, double *, int, int, bool &) {}
+    SLB_DEV static void run(Tile &, double *, int, int, bool &, double, double) {}
 };
 
 template <int NK, int NL, int WPB, int MINB>
@@ -133,31 +144,12 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
                 T[r][c] = (i < N && j <= i) ? Pg[rowoff[r] + 8 * c] : 0.0;
             }
     }
-    // mean blocks that h needs (statek pos/orient, statek_i pos/orient, featuresk)
-    double pk[3], qk[4], pi[3], qi[4], ft[NK];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { pk[c] = mug[c]; pi[c] = mug[26 + c]; }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { qk[c] = mug[3 + c]; qi[c] = mug[29 + c]; }
-#pragma unroll
-    for (int c = 0; c < NK; ++c) ft[c] = mug[39 + c];
-
-    // this lane's share of the mean for the final mu [+] K nu (lane b < 12 owns block b of the three States, lanes
-    // 12.. own the feature scalars): fetched now so that the epilogue does not wait on HBM
-    const int msidx = lane >> 2, mbw = lane & 3;
-    const int mqo = lane < 12 ? 13 * msidx + (mbw == 0 ? 0 : mbw == 1 ? 3 : mbw == 2 ? 7 : 10) : 39 + lane - 12;
-    double mym[4] = {0.0, 0.0, 0.0, 0.0};
-    if (lane < 12) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < 3 || mbw == 1) mym[c] = mug[mqo + c];
-    } else if (lane - 12 < NK + NL) {
-        mym[0] = mug[mqo];
-    }
-
     // ---- Eigen::LLT of Pk (:537) ------------------------------------------------------------------------
     bool ok = true;
-    CholStep<C, 0>::run(T, Ls, a_, b_, ok);
+    {
+        const double x0 = __shfl_sync(FULL, T[0][0], 0);
+        CholStep<C, 0>::run(T, Ls, a_, b_, ok, x0, -rcp_fast(x0));
+    }
     if (!ok) {
         if (lane == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
         return;
@@ -176,6 +168,28 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
             }
     }
 
+    // mean blocks that h needs (statek pos/orient, statek_i pos/orient, featuresk)
+    double pk[3], qk[4], pi[3], qi[4], ft[NK];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { pk[c] = mug[c]; pi[c] = mug[26 + c]; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { qk[c] = mug[3 + c]; qi[c] = mug[29 + c]; }
+#pragma unroll
+    for (int c = 0; c < NK; ++c) ft[c] = mug[39 + c];
+
+    // this lane's share of the mean for the final mu [+] K nu (lane b < 12 owns block b of the three States, lanes
+    // 12.. own the feature scalars): fetched here, after the factorisation (registers), long before the epilogue needs it
+    const int msidx = lane >> 2, mbw = lane & 3;
+    const int mqo = lane < 12 ? 13 * msidx + (mbw == 0 ? 0 : mbw == 1 ? 3 : mbw == 2 ? 7 : 10) : 39 + lane - 12;
+    double mym[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < 12) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < 3 || mbw == 1) mym[c] = mug[mqo + c];
+    } else if (lane - 12 < NK + NL) {
+        mym[0] = mug[mqo];
+    }
+
     // ---- sigma points through h (:275-278), lane per point ---------------------------------------------
     constexpr int NPASS = (NSIG + 31) / 32;
     double zr[NPASS][NK];
@@ -184,8 +198,12 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
         const int s = lane + 32 * t;
         const bool act = s < NSIG;
         const int j = act && s >= 1 ? (s - 1) >> 1 : 0;
-        const double sgn = (s & 1) ? 1.0 : -1.0;
         const int cj = j * N - j * (j - 1) / 2 - j;  // column j of the factor starts at Ls[cj + j]
+        // L(:,j) = U(:,j) / sqrt(d_j), d_j = U(j,j): the column scale rides on the sigma point's sign
+        double sq_, rs_;
+        sqrt_rsqrt(Ls[cj + j], sq_, rs_);
+        const double sgn = (s & 1) ? rs_ : -rs_;
+        if (act && (s & 1)) dl[j] = rs_;
         auto Lc = [&](int r) -> double { return (act && s >= 1 && r >= j) ? sgn * Ls[cj + r] : 0.0; };
         double xpk[3], xqk[4], xpi[3], xqi[4], xf[NK];
 #pragma unroll
@@ -248,9 +266,10 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
         }
     __syncwarp();
     // W[j] = 0.5 (Z+_j - Z-_j): the only part of covXZ's right factor that survives the +- pairing
+    // (times 1/sqrt(d_j), so that covXZ = L W = U W')
     for (int e = lane; e < JM * NK; e += 32) {
         const int jj = e / NK, c = e - jj * NK;
-        Ws[e] = 0.5 * ((Zs[(1 + 2 * jj) * NK + c] - zbar[c]) - (Zs[(2 + 2 * jj) * NK + c] - zbar[c]));
+        Ws[e] = (0.5 * dl[jj]) * ((Zs[(1 + 2 * jj) * NK + c] - zbar[c]) - (Zs[(2 + 2 * jj) * NK + c] - zbar[c]));
     }
     __syncwarp();
     // ---- covXZ = L W (:283, :714-737): lane owns rows `lane` and `lane + 32`; column jj of the factor is
@@ -448,9 +467,9 @@ static int launch_predict_t(const FilterArgs &a, cudaStream_t s) {
     return SLB_OK;
 }
 
-template <int NK, int NL>
-static int launch_update_t(const FilterArgs &a, cudaStream_t s) {
-    constexpr int WPB = 4, MINB = 3;
+template <int NK, int NL, int MINB>
+static int launch_update_m(const FilterArgs &a, cudaStream_t s) {
+    constexpr int WPB = 4;
     constexpr size_t smem = (size_t)WPB * slbd::UpdCfg<NK, NL>::SM * sizeof(double);
     auto kern = slbd::usckf_update_kernel<NK, NL, WPB, MINB>;
     SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -458,6 +477,13 @@ static int launch_update_t(const FilterArgs &a, cudaStream_t s) {
     count_launch();
     SLB_CUDA(cudaGetLastError());
     return SLB_OK;
+}
+
+// experiment knob: SLB_USCKF_MINB=4 selects the 128-register build (4 CTAs of 4 warps per SM)
+template <int NK, int NL>
+static int launch_update_t(const FilterArgs &a, cudaStream_t s) {
+    static const int minb = [] { const char *e = getenv("SLB_USCKF_MINB"); return e ? atoi(e) : 3; }();
+    return minb == 4 ? launch_update_m<NK, NL, 4>(a, s) : launch_update_m<NK, NL, 3>(a, s);
 }
 
 int launch_usckf(int pm, int mm, bool predict, bool update, const FilterArgs &a, cudaStream_t s) {
