@@ -199,6 +199,48 @@ int slb_datamodel_addsub(int d, int64_t n, int sign, const double *x1, const dou
 int slb_datamodel_fuse_host(int d, int64_t n, const double *x1, const double *C1,
                             const double *x2, const double *C2, double *xo, double *Co);
 
+/* ==== SURVEY section 8(f) "next" rows ======================================================= */
+
+/* ---- f2: error-state EKF of src/filters/UsckfError.hpp (the Joseph-form variant of Usckf) ----
+ * Instance-major device arrays holding what the reference object holds: mu = mu_state as 3 x 16
+ * q-vector scalars (statek | statek_l | statek_i; per state pos vel quat(w,x,y,z) gbias abias, the
+ * 15-DOF layout of :527-531), err = mu_error vectorised (n x 45), P = Pk_error dense row-major
+ * (n x 45 x 45; the lower triangle is read, both are written). */
+/* ekfPredict(F, Q) UsckfError.hpp:87-137.  F: n x 15 x 15 (per instance), Q: 15 x 15 shared. */
+int slb_ekf_predict(int64_t n, double *err, double *P, const double *F, const double *Q, void *stream);
+/* ekfUpdate(z, H, R[, mt]) UsckfError.hpp:322-384: Joseph-form covariance update + symmetrisation.
+ * H: m x 45 shared, R: m x m shared, z: n x m.  gate 0 = accept any; otherwise the 5% chi-square
+ * table with dof = m - 1 (the reference passes innovation.size()-1, :350).  ret (n x m) receives
+ * the function's return value (zeros when accepted, the innovation when rejected), accepted (n)
+ * the decision.  Like the reference only Pk_error changes.  m = 3. */
+int slb_ekf_update(int64_t n, int m, const double *mu, double *P, const double *z, const double *H,
+                   const double *R, int gate, double *ret, int32_t *accepted, void *stream);
+/* ekfSingleUpdate(z, H, R[, mt]) UsckfError.hpp:489-571 on the statek_i block; H: m x 15.  The
+ * corrections are applied to mu_state.statek_i whatever the gate says (:553-568). m = 3. */
+int slb_ekf_single_update(int64_t n, int m, double *mu, const double *err, double *P, const double *z,
+                          const double *H, const double *R, int gate, int32_t *accepted, void *stream);
+/* cloning() UsckfError.hpp:573-603 */
+int slb_ekf_clone(int64_t n, double *mu, double *err, double *P, void *stream);
+
+/* ---- f3: DataModel<double,3>::safeFusion(data2) DataModel.hpp:62-130 (d = 3 only, :104) ------ */
+int slb_datamodel_safe_fuse(int64_t n, const double *x1, const double *C1, const double *x2,
+                            const double *C2, double *xo, double *Co, void *stream);
+
+/* ---- f4: the producers of the filters' odometry input ----------------------------------------
+ * Poses are pos(3) quat(w,x,y,z); covariances are 6 x 6 over [r t], rotation first
+ * (Transform.hpp:48-60).  result = t2 * t1, TransformWithUncertainty::operator* Transform.cpp:215-254
+ * (both operands uncertain). */
+int slb_transform_compose(int64_t n, const double *pose2, const double *cov2, const double *pose1,
+                          const double *cov1, double *pose_out, double *cov_out, void *stream);
+/* DeadReckon::updatePose(delta_t, cartesianVelocities, cartesianVelCov, prevPose, postPose)
+ * DeadReckon.hpp:30-79 (with updateAttitude :246-286).  vel0 / vel1: n x 6 (linear, angular) at the
+ * current and the previous sample; velcov: 6 x 6 shared.  post = prev * delta; the returned
+ * deltaPose goes to delta_pose / delta_cov. */
+int slb_deadreckon_update_pose(int64_t n, double dt, const double *vel0, const double *vel1,
+                               const double *velcov, const double *prev_pose, const double *prev_cov,
+                               double *post_pose, double *post_cov, double *delta_pose,
+                               double *delta_cov, void *stream);
+
 /* ---- device buffers for callers without a CUDA binding (cgo / JNI / ctypes, the C++ facade) ---- */
 int slb_dev_alloc(size_t bytes, void **dev);
 int slb_dev_free(void *dev);

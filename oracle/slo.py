@@ -234,3 +234,72 @@ def datamodel_default(d):
     x, Cv = np.empty(d), np.empty((d, d))
     lib().slo_datamodel_default(d, _p(x), _p(Cv))
     return x, Cv
+
+
+# ---- SURVEY 8(f) next rows (oracle/slo_next.hpp) ----------------------------------------------
+def ekf_predict(err, P, F, Q, nthreads=1):
+    err, P, F, Q = _d(err).copy(), _d(P).copy(), _d(F), _d(Q)
+    lib().slo_ekf_predict(C.c_longlong(err.shape[0]), _p(err), _p(P), _p(F), _p(Q), nthreads)
+    return err, P
+
+
+def ekf_update(mu, P, z, H, R, gate=0, nthreads=1):
+    mu, P, z, H, R = _d(mu), _d(P).copy(), _d(z), _d(H), _d(R)
+    n, m = z.shape
+    ret, acc = np.empty((n, m)), np.empty(n, dtype=np.int32)
+    lib().slo_ekf_update(C.c_longlong(n), m, _p(mu), _p(P), _p(z), _p(H), _p(R), int(gate), _p(ret), _p(acc), nthreads)
+    return P, ret, acc
+
+
+def ekf_single_update(mu, err, P, z, H, R, gate=0, nthreads=1):
+    mu, err, P, z, H, R = _d(mu).copy(), _d(err), _d(P).copy(), _d(z), _d(H), _d(R)
+    n, m = z.shape
+    acc = np.empty(n, dtype=np.int32)
+    lib().slo_ekf_single_update(C.c_longlong(n), m, _p(mu), _p(err), _p(P), _p(z), _p(H), _p(R), int(gate), _p(acc), nthreads)
+    return mu, P, acc
+
+
+def ekf_clone(mu, err, P):
+    mu, err, P = _d(mu).copy(), _d(err).copy(), _d(P).copy()
+    lib().slo_ekf_clone(C.c_longlong(mu.shape[0]), _p(mu), _p(err), _p(P))
+    return mu, err, P
+
+
+def safe_fusion(x1, C1, x2, C2, nthreads=1):
+    x1, C1, x2, C2 = _d(x1), _d(C1), _d(x2), _d(C2)
+    xo, Co = np.empty_like(x1), np.empty_like(C1)
+    lib().slo_safe_fusion(C.c_longlong(x1.shape[0]), _p(x1), _p(C1), _p(x2), _p(C2), _p(xo), _p(Co), nthreads)
+    return xo, Co
+
+
+def jacobi_svd(A):
+    A = _d(A)
+    n = A.shape[0]
+    U, sv = np.empty((n, n)), np.empty(n)
+    lib().slo_jacobi_svd(n, _p(A), _p(U), _p(sv))
+    return U, sv
+
+
+def transform_compose(pose2, cov2, pose1, cov1, nthreads=1):
+    pose2, cov2, pose1, cov1 = _d(pose2), _d(cov2), _d(pose1), _d(cov1)
+    po, co = np.empty_like(pose2), np.empty_like(cov2)
+    lib().slo_transform_compose(C.c_longlong(pose2.shape[0]), _p(pose2), _p(cov2), _p(pose1), _p(cov1), _p(po), _p(co), nthreads)
+    return po, co
+
+
+def dr_update_pose(dt, vel0, vel1, velcov, prev_pose, prev_cov, nthreads=1):
+    vel0, vel1, velcov, prev_pose, prev_cov = _d(vel0), _d(vel1), _d(velcov), _d(prev_pose), _d(prev_cov)
+    n = vel0.shape[0]
+    post, pcov, dpose, dcov = np.empty((n, 7)), np.empty((n, 6, 6)), np.empty((n, 7)), np.empty((n, 6, 6))
+    lib().slo_dr_update_pose.argtypes = [C.c_longlong, C.c_double] + [C.c_void_p] * 9 + [C.c_int]
+    lib().slo_dr_update_pose(n, float(dt), _p(vel0), _p(vel1), _p(velcov), _p(prev_pose), _p(prev_cov), _p(post), _p(pcov),
+                             _p(dpose), _p(dcov), nthreads)
+    return post, pcov, dpose, dcov
+
+
+def dr_update_attitude(dt, w0, w1):
+    w0, w1 = _d(w0), _d(w1)
+    dq = np.empty(4)
+    lib().slo_dr_update_attitude.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib().slo_dr_update_attitude(float(dt), _p(w0), _p(w1), _p(dq))
+    return dq

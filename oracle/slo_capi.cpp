@@ -9,6 +9,7 @@
 #include <thread>
 
 #include "slo_models.hpp"
+#include "slo_next.hpp"
 
 using namespace slo;
 
@@ -231,6 +232,100 @@ void slo_datamodel_default(int d, double *x, double *C) {
     std::copy(a.data.begin(), a.data.end(), x);
     store_mat(a.Cov, C);
 }
+
+// ---- SURVEY 8(f) next rows (slo_next.hpp) ------------------------------------------------------
+// f2: error-state EKF, batches instance-major: mu n x 48, err n x 45, P n x 45 x 45
+int slo_ekf_predict(long long n, double *err, double *P, const double *F, const double *Q, int nthreads) {
+    const Mat Qm = load_mat(Q, EKF_NS, EKF_NS);
+    parallel_for((int)n, nthreads, [&](int i) {
+        Vec e(err + (size_t)i * EKF_NA, err + (size_t)(i + 1) * EKF_NA);
+        Mat Pm = load_mat(P + (size_t)i * EKF_NA * EKF_NA, EKF_NA, EKF_NA);
+        ekf_predict(e, Pm, load_mat(F + (size_t)i * EKF_NS * EKF_NS, EKF_NS, EKF_NS), Qm);
+        std::copy(e.begin(), e.end(), err + (size_t)i * EKF_NA);
+        store_mat(Pm, P + (size_t)i * EKF_NA * EKF_NA);
+    });
+    return 0;
+}
+// H: m x 45 shared, R: m x m shared, z: n x m; ret: n x m; accepted: n
+int slo_ekf_update(long long n, int m, const double *mu, double *P, const double *z, const double *H, const double *R,
+                   int gate, double *ret, int *accepted, int nthreads) {
+    const Mat Hm = load_mat(H, m, EKF_NA), Rm = load_mat(R, m, m);
+    parallel_for((int)n, nthreads, [&](int i) {
+        Mat Pm = load_mat(P + (size_t)i * EKF_NA * EKF_NA, EKF_NA, EKF_NA);
+        Vec r;
+        accepted[i] = ekf_update(mu + (size_t)i * EKF_QA, Pm, Vec(z + (size_t)i * m, z + (size_t)(i + 1) * m), Hm, Rm, gate, r) ? 1 : 0;
+        std::copy(r.begin(), r.end(), ret + (size_t)i * m);
+        store_mat(Pm, P + (size_t)i * EKF_NA * EKF_NA);
+    });
+    return 0;
+}
+// H: m x 15 shared
+int slo_ekf_single_update(long long n, int m, double *mu, const double *err, double *P, const double *z, const double *H,
+                          const double *R, int gate, int *accepted, int nthreads) {
+    const Mat Hm = load_mat(H, m, EKF_NS), Rm = load_mat(R, m, m);
+    parallel_for((int)n, nthreads, [&](int i) {
+        Mat Pm = load_mat(P + (size_t)i * EKF_NA * EKF_NA, EKF_NA, EKF_NA);
+        accepted[i] = ekf_single_update(mu + (size_t)i * EKF_QA, Vec(err + (size_t)i * EKF_NA, err + (size_t)(i + 1) * EKF_NA), Pm,
+                                        Vec(z + (size_t)i * m, z + (size_t)(i + 1) * m), Hm, Rm, gate) ? 1 : 0;
+        store_mat(Pm, P + (size_t)i * EKF_NA * EKF_NA);
+    });
+    return 0;
+}
+int slo_ekf_clone(long long n, double *mu, double *err, double *P) {
+    for (long long i = 0; i < n; ++i) {
+        Vec e(err + (size_t)i * EKF_NA, err + (size_t)(i + 1) * EKF_NA);
+        Mat Pm = load_mat(P + (size_t)i * EKF_NA * EKF_NA, EKF_NA, EKF_NA);
+        ekf_clone(mu + (size_t)i * EKF_QA, e, Pm);
+        std::copy(e.begin(), e.end(), err + (size_t)i * EKF_NA);
+        store_mat(Pm, P + (size_t)i * EKF_NA * EKF_NA);
+    }
+    return 0;
+}
+// f3: safeFusion, d = 3
+int slo_safe_fusion(long long n, const double *x1, const double *C1, const double *x2, const double *C2, double *xo,
+                    double *Co, int nthreads) {
+    parallel_for((int)n, nthreads, [&](int i) {
+        Vec a(x1 + (size_t)i * 3, x1 + (size_t)(i + 1) * 3);
+        Mat Ca = load_mat(C1 + (size_t)i * 9, 3, 3);
+        safe_fusion3(a, Ca, Vec(x2 + (size_t)i * 3, x2 + (size_t)(i + 1) * 3), load_mat(C2 + (size_t)i * 9, 3, 3));
+        std::copy(a.begin(), a.end(), xo + (size_t)i * 3);
+        store_mat(Ca, Co + (size_t)i * 9);
+    });
+    return 0;
+}
+void slo_jacobi_svd(int n, const double *A, double *U, double *sv) {
+    Mat Um;
+    Vec s;
+    jacobi_svd(load_mat(A, n, n), Um, s);
+    store_mat(Um, U);
+    std::copy(s.begin(), s.end(), sv);
+}
+// f4: poses n x 7 (pos, quat wxyz), covariances n x 6 x 6 over [r t]
+int slo_transform_compose(long long n, const double *pose2, const double *cov2, const double *pose1, const double *cov1,
+                          double *pose_out, double *cov_out, int nthreads) {
+    parallel_for((int)n, nthreads, [&](int i) {
+        Mat co;
+        transform_compose(pose2 + (size_t)i * 7, load_mat(cov2 + (size_t)i * 36, 6, 6), pose1 + (size_t)i * 7,
+                          load_mat(cov1 + (size_t)i * 36, 6, 6), pose_out + (size_t)i * 7, co);
+        store_mat(co, cov_out + (size_t)i * 36);
+    });
+    return 0;
+}
+// vel0 / vel1: n x 6 (linear, angular) at t and t - dt; velcov: 6 x 6 shared
+int slo_dr_update_pose(long long n, double dt, const double *vel0, const double *vel1, const double *velcov,
+                       const double *prev_pose, const double *prev_cov, double *post_pose, double *post_cov,
+                       double *delta_pose, double *delta_cov, int nthreads) {
+    const Mat vc = load_mat(velcov, 6, 6);
+    parallel_for((int)n, nthreads, [&](int i) {
+        Mat pc, dc;
+        dr_update_pose(dt, vel0 + (size_t)i * 6, vel1 + (size_t)i * 6, vc, prev_pose + (size_t)i * 7,
+                       load_mat(prev_cov + (size_t)i * 36, 6, 6), post_pose + (size_t)i * 7, pc, delta_pose + (size_t)i * 7, dc);
+        store_mat(pc, post_cov + (size_t)i * 36);
+        store_mat(dc, delta_cov + (size_t)i * 36);
+    });
+    return 0;
+}
+void slo_dr_update_attitude(double dt, const double *w0, const double *w1, double *dq) { dr_update_attitude(dt, w0, w1, dq); }
 
 int slo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 

@@ -1,0 +1,412 @@
+// slb_ekf.cu -- SURVEY 8(f) row f2: the error-state EKF of src/filters/UsckfError.hpp, one instance per WARP.
+//
+//   ekfPredict(F, Q)          UsckfError.hpp:87-137   ->  ekf_predict_kernel
+//   ekfUpdate(z, H, R, mt)    UsckfError.hpp:322-384  ->  ekf_update_kernel<M>        (Joseph form + symmetrisation)
+//   ekfSingleUpdate(z,H,R,mt) UsckfError.hpp:489-571  ->  ekf_single_update_kernel<M> (Joseph form on the statek_i block)
+//   cloning()                 UsckfError.hpp:573-603  ->  ekf_clone_kernel
+//
+// Data in HBM is what the reference object holds, instance-major: mu_state as 3 x 16 q-vector scalars
+// (pos vel quat(w,x,y,z) gbias abias per single state -- the 15-DOF layout of :527-531; the reference's own type
+// is not in its tree), mu_error vectorised (45), Pk_error as a DENSE 45 x 45 row-major matrix.  Only the lower
+// triangle of a covariance block is read (like every other kernel here); both triangles are written.
+//
+// All three filter kernels are HBM-bound (2-3 flop/B): a warp streams its instance's rows with coalesced
+// loads into shared memory, does the O(N^2 m) algebra there and streams the result back.
+// The Joseph form (I-KH) P (I-KH)^T + K R K^T is evaluated in its expanded, algebraically identical form
+//   P - K A^T - A K^T + K S K^T,   A = P H^T,  S = H A + R
+// (O(N^2 m) instead of two N^3 products) and symmetrised as 0.5 (P + P^T) like :359.
+#include "slb_internal.h"
+#include "slb_math.cuh"
+
+namespace slbd {
+
+constexpr int EKF_NS = 15, EKF_NA = 45, EKF_QS = 16, EKF_QA = 48;
+constexpr unsigned EKF_FULL = 0xffffffffu;
+
+// closed-form inverse of a general 3x3 (Eigen's fixed-size path: cofactors / determinant)
+SLB_DEV void inv3(const double *A, double *C) {
+    auto a = [&](int i, int j) { return A[i * 3 + j]; };
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return a(i1, j1) * a(i2, j2) - a(i1, j2) * a(i2, j1);
+    };
+    const double c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    const double det = c00 * a(0, 0) + c10 * a(1, 0) + c20 * a(2, 0);
+    const double id = 1.0 / det;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C[j * 3 + i] = cof(i, j) * id;
+}
+
+// ---- ekfPredict ---------------------------------------------------------------------------------------
+// block row i = rows 30..44:  [P_ik P_il P_ii] <- F [P_ik P_il P_ii],  P_ii <- (F P_ii) F^T + Q,  columns 30..44 of
+// rows 0..29 by symmetry (the reference updates P_ki = P_ki F^T separately, :109-116: the same numbers for a
+// symmetric Pk_error).
+constexpr int EKP_SM = 15 * 16 + 15 * 46 + 15 * 46;  // F (row stride 16) | block row (stride 46) | result (stride 46)
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) ekf_predict_kernel(int64_t n, double *err, double *P, const double *F, const double *Q) {
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t inst = (int64_t)blockIdx.x * WPB + w;
+    if (inst >= n) return;
+    double *Fs = sm + (size_t)w * EKP_SM, *Rs = Fs + 15 * 16, *Ys = Rs + 15 * 46;
+    double *Pg = P + inst * (EKF_NA * EKF_NA);
+    const double *Fg = F + inst * (EKF_NS * EKF_NS);
+    for (int e = lane; e < 225; e += 32) Fs[(e / 15) * 16 + e % 15] = Fg[e];
+    for (int e = lane; e < 675; e += 32) Rs[(e / 45) * 46 + e % 45] = Pg[30 * 45 + e];
+    double ei = lane < 15 ? err[inst * EKF_NA + 30 + lane] : 0.0;
+    __syncwarp();
+    // mu_error.statek_i <- F mu_error.statek_i (:93)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+            const double ek = __shfl_sync(EKF_FULL, ei, k);
+            if (lane < 15) s += Fs[lane * 16 + k] * ek;
+        }
+        if (lane < 15) err[inst * EKF_NA + 30 + lane] = s;
+    }
+    // Y = F * block row: lane owns column c (and c + 32)
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int c = lane + 32 * pass;
+        if (c < 45) {
+            double col[15];
+#pragma unroll
+            for (int k = 0; k < 15; ++k) col[k] = Rs[k * 46 + c];
+#pragma unroll 1
+            for (int r = 0; r < 15; ++r) {  // rolled: unrolled, ptxas hoists all 225 F entries into registers and spills
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < 15; ++k) s += Fs[r * 16 + k] * col[k];
+                Ys[r * 46 + c] = s;
+            }
+        }
+    }
+    __syncwarp();
+    // P_ii = Y_ii F^T + Q (:96)
+    for (int e = lane; e < 225; e += 32) {
+        const int r = e / 15, c = e - r * 15;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) s += Ys[r * 46 + 30 + k] * Fs[c * 16 + k];
+        Rs[r * 46 + 30 + c] = s + __ldg(Q + e);
+    }
+    __syncwarp();
+    for (int e = lane; e < 675; e += 32) {
+        const int r = e / 45, c = e - r * 45;
+        Pg[30 * 45 + e] = c < 30 ? Ys[r * 46 + c] : Rs[r * 46 + c];
+    }
+    // mirrored blocks: row k < 30, columns 30..44
+    for (int e = lane; e < 450; e += 32) {
+        const int k = e / 15, c = e - k * 15;
+        Pg[k * 45 + 30 + c] = Ys[c * 46 + k];
+    }
+}
+
+// ---- ekfUpdate: N = 45 on the whole Pk_error, M = 3 ---------------------------------------------------------
+// shared memory per warp: packed lower triangle (also the result), A | K | G rows, H
+template <int N, int M>
+struct EkuCfg {
+    static constexpr int NP = N * (N + 1) / 2;
+    static constexpr int ROW = 12;  // K(3) A(3) G(3) + pad: 16-byte aligned rows
+    static constexpr int SM = (NP + N * ROW + M * N + 1) / 2 * 2;
+};
+
+// Joseph-form update of the packed lower triangle Pl (N x N) held in shared memory; H (M x N) in shared memory.
+// Returns the acceptance decision; innovation in `innov`.
+template <int N, int M>
+SLB_DEV bool joseph_update(double *Pl, double *rows, const double *Hs, const double *xhat /* smem, N */, const double *zg,
+                           const double *Rg, int gate, int lane, double *innov) {
+    typedef EkuCfg<N, M> C;
+    static_assert(M == 3, "S^-1 is the closed-form 3x3 inverse");
+    static_assert(N <= 64, "two rows per lane");
+    // A = P H^T: lane owns rows lane, lane + 32
+    double A0[M], A1[M];
+#pragma unroll
+    for (int c = 0; c < M; ++c) A0[c] = A1[c] = 0.0;
+    const int i0 = lane, i1 = lane + 32;
+    for (int j = 0; j < N; ++j) {
+        const double p0 = i0 < N ? Pl[i0 >= j ? tri(i0, j) : tri(j, i0)] : 0.0;
+        const double p1 = i1 < N ? Pl[i1 >= j ? tri(i1, j) : tri(j, i1)] : 0.0;
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            const double h = Hs[c * N + j];
+            A0[c] = fma(p0, h, A0[c]);
+            A1[c] = fma(p1, h, A1[c]);
+        }
+    }
+    if (i0 < N) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) rows[i0 * C::ROW + 3 + c] = A0[c];
+    }
+    if (i1 < N) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) rows[i1 * C::ROW + 3 + c] = A1[c];
+    }
+    __syncwarp();
+    // S = H A + R, H x_hat: every lane redundantly (broadcast reads)
+    double S[M * M], hx[M];
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+        hx[r] = 0.0;
+#pragma unroll
+        for (int c = 0; c < M; ++c) S[r * M + c] = 0.0;
+    }
+    for (int i = 0; i < N; ++i) {
+        const double x = xhat[i];
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            const double h = Hs[r * N + i];
+            hx[r] = fma(h, x, hx[r]);
+#pragma unroll
+            for (int c = 0; c < M; ++c) S[r * M + c] = fma(h, rows[i * C::ROW + 3 + c], S[r * M + c]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < M * M; ++e) S[e] += __ldg(Rg + e);
+    double Si[M * M];
+    inv3(S, Si);
+    double m2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < M; ++r) innov[r] = zg[r] - hx[r];
+#pragma unroll
+    for (int r = 0; r < M; ++r) {
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < M; ++c) t += Si[r * M + c] * innov[c];
+        m2 += innov[r] * t;
+    }
+    const bool accept = chi2_accept(m2, gate == 0 ? 0 : M - 1);  // dof = innovation.size() - 1 (:350)
+    // K = A S^-1, G = K S - A
+    auto finish = [&](const double *Ar, int i) {
+        double K[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int p = 0; p < M; ++p) s += Ar[p] * Si[p * M + c];
+            K[c] = s;
+        }
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            double s = -Ar[c];
+#pragma unroll
+            for (int p = 0; p < M; ++p) s = fma(K[p], S[p * M + c], s);
+            rows[i * C::ROW + c] = K[c];
+            rows[i * C::ROW + 6 + c] = s;
+        }
+    };
+    if (i0 < N) finish(A0, i0);
+    if (i1 < N) finish(A1, i1);
+    __syncwarp();
+    if (!accept) return false;
+    // P'_ij = P_ij - 0.5 (K_i.A_j + K_j.A_i) + 0.5 (G_i.K_j + G_j.K_i): lane l takes rows l and N-1-l (N+1 entries)
+    for (int half = 0; half < 2; ++half) {
+        const int i = half == 0 ? lane : N - 1 - lane;
+        if (lane >= (N + 1) / 2 || (half == 1 && i == lane)) continue;
+        double Ki[M], Ai[M], Gi[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) { Ki[c] = rows[i * C::ROW + c]; Ai[c] = rows[i * C::ROW + 3 + c]; Gi[c] = rows[i * C::ROW + 6 + c]; }
+        for (int j = 0; j <= i; ++j) {
+            double ka = 0.0, gk = 0.0;
+#pragma unroll
+            for (int c = 0; c < M; ++c) {
+                const double Kj = rows[j * C::ROW + c], Aj = rows[j * C::ROW + 3 + c], Gj = rows[j * C::ROW + 6 + c];
+                ka = fma(Ki[c], Aj, ka);
+                ka = fma(Kj, Ai[c], ka);
+                gk = fma(Gi[c], Kj, gk);
+                gk = fma(Gj, Ki[c], gk);
+            }
+            Pl[tri(i, j)] = Pl[tri(i, j)] + 0.5 * (gk - ka);
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+template <int M, int WPB>
+__global__ void __launch_bounds__(WPB * 32) ekf_update_kernel(int64_t n, const double *mu, double *P, const double *z, const double *H,
+                                                              const double *R, int gate, double *ret, int32_t *accepted) {
+    constexpr int N = EKF_NA;
+    typedef EkuCfg<N, M> C;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t inst = (int64_t)blockIdx.x * WPB + w;
+    if (inst >= n) return;
+    double *Pl = sm + (size_t)w * (C::SM + N + 1) , *rows = Pl + C::NP, *Hs = rows + N * C::ROW, *xh = sm + (size_t)w * (C::SM + N + 1) + C::SM;
+    double *Pg = P + inst * (N * N);
+    for (int i = 0; i < N; ++i)
+        for (int j = lane; j <= i; j += 32) Pl[tri(i, j)] = Pg[i * N + j];
+    for (int e = lane; e < M * N; e += 32) Hs[e] = __ldg(H + e);
+    // x_hat = mu_state vectorised with the error-quaternion convention (:331)
+    for (int e = lane; e < N; e += 32) {
+        const int s = e / EKF_NS, c = e - s * EKF_NS;
+        xh[e] = mu[inst * EKF_QA + s * EKF_QS + (c < 6 ? c : c + 1)];
+    }
+    __syncwarp();
+    double innov[M];
+    const bool ok = joseph_update<N, M>(Pl, rows, Hs, xh, z + inst * M, R, gate, lane, innov);
+    if (lane == 0) {
+        accepted[inst] = ok ? 1 : 0;
+#pragma unroll
+        for (int c = 0; c < M; ++c) ret[inst * M + c] = ok ? 0.0 : innov[c];  // :361 / :371
+    }
+    if (!ok) return;
+    for (int e = lane; e < N * N; e += 32) {
+        const int i = e / N, j = e - i * N;
+        Pg[e] = Pl[i >= j ? tri(i, j) : tri(j, i)];
+    }
+}
+
+// ---- ekfSingleUpdate: the 15 x 15 statek_i block and mu_state.statek_i --------------------------------------
+template <int M, int WPB>
+__global__ void __launch_bounds__(WPB * 32) ekf_single_update_kernel(int64_t n, double *mu, const double *err, double *P, const double *z,
+                                                                     const double *H, const double *R, int gate, int32_t *accepted) {
+    constexpr int N = EKF_NS;
+    typedef EkuCfg<N, M> C;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t inst = (int64_t)blockIdx.x * WPB + w;
+    if (inst >= n) return;
+    double *Pl = sm + (size_t)w * (C::SM + N + 1), *rows = Pl + C::NP, *Hs = rows + N * C::ROW, *xk = sm + (size_t)w * (C::SM + N + 1) + C::SM;
+    double *Pg = P + inst * (EKF_NA * EKF_NA);
+    for (int e = lane; e < N * N; e += 32) {
+        const int i = e / N, j = e - i * N;
+        if (j <= i) Pl[tri(i, j)] = Pg[(30 + i) * EKF_NA + 30 + j];
+    }
+    for (int e = lane; e < M * N; e += 32) Hs[e] = __ldg(H + e);
+    if (lane < N) xk[lane] = err[inst * EKF_NA + 30 + lane];
+    __syncwarp();
+    double innov[M];
+    const bool ok = joseph_update<N, M>(Pl, rows, Hs, xk, z + inst * M, R, gate, lane, innov);
+    if (lane == 0) accepted[inst] = ok ? 1 : 0;
+    if (ok) {
+        for (int e = lane; e < N * N; e += 32) {
+            const int i = e / N, j = e - i * N;
+            Pg[(30 + i) * EKF_NA + 30 + j] = Pl[i >= j ? tri(i, j) : tri(j, i)];
+        }
+    }
+    // corrections (:553-568), applied whether or not the gate accepted; x = xk (+ K innovation when accepted)
+    double x = 0.0;
+    if (lane < N) {
+        x = xk[lane];
+        if (ok) {
+#pragma unroll
+            for (int c = 0; c < M; ++c) x = fma(rows[lane * C::ROW + c], innov[c], x);
+        }
+    }
+    double *s = mu + inst * EKF_QA + 2 * EKF_QS;
+    const double qx = __shfl_sync(EKF_FULL, x, 6), qy = __shfl_sync(EKF_FULL, x, 7), qz = __shfl_sync(EKF_FULL, x, 8);
+    if (lane < 6) s[lane] += x;                       // pos, vel
+    else if (lane >= 9 && lane < N) s[lane + 1] += x;  // gbias, abias
+    if (lane == 6) {
+        const double q0[4] = {s[6], s[7], s[8], s[9]}, qe[4] = {1.0, qx, qy, qz};
+        double q[4];
+        quat_mul(q0, qe, q);
+        const double nn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[6 + c] = q[c] / nn;
+    }
+}
+
+// ---- cloning() (:573-603): every 15 x 15 block <- P_ii, statek = statek_l = statek_i ---------------------------
+__global__ void ekf_clone_kernel(int64_t n, double *mu, double *err, double *P) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int PER = EKF_NA * EKF_NA + 2 * EKF_QS + 2 * EKF_NS;
+    if (t >= n * PER) return;
+    const int64_t inst = t / PER;
+    const int e = (int)(t - inst * PER);
+    if (e < EKF_NA * EKF_NA) {
+        const int i = e / EKF_NA, j = e - i * EKF_NA;
+        if (i >= 30 && j >= 30) return;
+        P[inst * (EKF_NA * EKF_NA) + e] = P[inst * (EKF_NA * EKF_NA) + (30 + i % 15) * EKF_NA + 30 + j % 15];
+    } else if (e < EKF_NA * EKF_NA + 2 * EKF_QS) {
+        const int c = e - EKF_NA * EKF_NA;
+        mu[inst * EKF_QA + c] = mu[inst * EKF_QA + 2 * EKF_QS + c % EKF_QS];
+    } else {
+        const int c = e - EKF_NA * EKF_NA - 2 * EKF_QS;
+        err[inst * EKF_NA + c] = err[inst * EKF_NA + 2 * EKF_NS + c % EKF_NS];
+    }
+}
+
+}  // namespace slbd
+
+using namespace slb;
+
+extern "C" {
+
+int slb_ekf_predict(int64_t n, double *err, double *P, const double *F, const double *Q, void *stream) {
+    if (n < 0 || !err || !P || !F || !Q) return set_error(SLB_ERR_INVALID, "slb_ekf_predict: bad argument");
+    if (n == 0) return SLB_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_ekf_predict: no CUDA device (this engine has no CPU fallback)");
+    }
+    constexpr int WPB = 8;
+    constexpr size_t smem = (size_t)WPB * slbd::EKP_SM * 8;
+    auto kern = slbd::ekf_predict_kernel<WPB>;
+    SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((n + WPB - 1) / WPB), WPB * 32, smem, (cudaStream_t)stream>>>(n, err, P, F, Q);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+int slb_ekf_update(int64_t n, int m, const double *mu, double *P, const double *z, const double *H, const double *R, int gate,
+                   double *ret, int32_t *accepted, void *stream) {
+    if (n < 0 || !mu || !P || !z || !H || !R || !ret || !accepted) return set_error(SLB_ERR_INVALID, "slb_ekf_update: bad argument");
+    if (m != 3) return set_error(SLB_ERR_INVALID, "slb_ekf_update: built for m = 3 (delay-position / velocity measurements)");
+    if (n == 0) return SLB_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_ekf_update: no CUDA device (this engine has no CPU fallback)");
+    }
+    constexpr int WPB = 8;
+    constexpr size_t smem = (size_t)WPB * (slbd::EkuCfg<45, 3>::SM + 46) * 8;
+    auto kern = slbd::ekf_update_kernel<3, WPB>;
+    SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((n + WPB - 1) / WPB), WPB * 32, smem, (cudaStream_t)stream>>>(n, mu, P, z, H, R, gate, ret, accepted);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+int slb_ekf_single_update(int64_t n, int m, double *mu, const double *err, double *P, const double *z, const double *H,
+                          const double *R, int gate, int32_t *accepted, void *stream) {
+    if (n < 0 || !mu || !err || !P || !z || !H || !R || !accepted) return set_error(SLB_ERR_INVALID, "slb_ekf_single_update: bad argument");
+    if (m != 3) return set_error(SLB_ERR_INVALID, "slb_ekf_single_update: built for m = 3");
+    if (n == 0) return SLB_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_ekf_single_update: no CUDA device (this engine has no CPU fallback)");
+    }
+    constexpr int WPB = 8;
+    constexpr size_t smem = (size_t)WPB * (slbd::EkuCfg<15, 3>::SM + 16) * 8;
+    auto kern = slbd::ekf_single_update_kernel<3, WPB>;
+    kern<<<(unsigned)((n + WPB - 1) / WPB), WPB * 32, smem, (cudaStream_t)stream>>>(n, mu, err, P, z, H, R, gate, accepted);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+int slb_ekf_clone(int64_t n, double *mu, double *err, double *P, void *stream) {
+    if (n < 0 || !mu || !err || !P) return set_error(SLB_ERR_INVALID, "slb_ekf_clone: bad argument");
+    if (n == 0) return SLB_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(SLB_ERR_NO_DEVICE, "slb_ekf_clone: no CUDA device (this engine has no CPU fallback)");
+    }
+    const int64_t work = n * (45 * 45 + 32 + 30);
+    slbd::ekf_clone_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, mu, err, P);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+}  // extern "C"

@@ -28,7 +28,8 @@ EXPORTS = [
     "slb_usckf_set_measurement", "slb_msckf_predict", "slb_msckf_update", "slb_datamodel_fuse",
     "slb_datamodel_addsub", "slb_datamodel_fuse_host", "slb_status", "slb_clear_status", "slb_ensemble_stats",
     "slb_launch_count", "slb_bench_fp64_peak", "slb_replicate", "slb_dev_alloc", "slb_dev_free", "slb_dev_copy",
-    "slb_msckf_step_host",
+    "slb_msckf_step_host", "slb_ekf_predict", "slb_ekf_update", "slb_ekf_single_update", "slb_ekf_clone",
+    "slb_datamodel_safe_fuse", "slb_transform_compose", "slb_deadreckon_update_pose",
 ]
 
 
@@ -78,6 +79,13 @@ def lib():
         L.slb_datamodel_fuse.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp, vp]
         L.slb_datamodel_addsub.argtypes = [i32, i64, i32, dp, dp, dp, dp, dp, dp, vp]
         L.slb_datamodel_fuse_host.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp]
+        L.slb_ekf_predict.argtypes = [i64, dp, dp, dp, dp, vp]
+        L.slb_ekf_update.argtypes = [i64, i32, dp, dp, dp, dp, dp, i32, dp, vp, vp]
+        L.slb_ekf_single_update.argtypes = [i64, i32, dp, dp, dp, dp, dp, dp, i32, vp, vp]
+        L.slb_ekf_clone.argtypes = [i64, dp, dp, dp, vp]
+        L.slb_datamodel_safe_fuse.argtypes = [i64, dp, dp, dp, dp, dp, dp, vp]
+        L.slb_transform_compose.argtypes = [i64, dp, dp, dp, dp, dp, dp, vp]
+        L.slb_deadreckon_update_pose.argtypes = [i64, dbl, dp, dp, dp, dp, dp, dp, dp, dp, dp, vp]
         L.slb_status.argtypes = [vp, C.POINTER(C.c_int64), vp]
         L.slb_clear_status.argtypes = [vp, vp]
         L.slb_ensemble_stats.argtypes = [vp, dp, vp]
@@ -330,3 +338,71 @@ class DataModel:
         xo, Co = np.empty_like(x1), np.empty_like(C1)
         check(lib().slb_datamodel_fuse_host(d, n, _hp(x1), _hp(C1), _hp(x2), _hp(C2), _hp(xo), _hp(Co)))
         return xo, Co
+
+    @staticmethod
+    def safe_fuse(x1, C1, x2, C2, out=None):
+        """DataModel<double,3>::safeFusion (DataModel.hpp:62-130), d = 3."""
+        x1, C1, x2, C2 = dev(x1), dev(C1), dev(x2), dev(C2)
+        n, d = x1.t.shape
+        if d != 3:
+            raise SlbError("safeFusion is only defined for d = 3 (DataModel.hpp:104)")
+        xo, Co = out if out is not None else (DeviceArray(shape=(n, 3)), DeviceArray(shape=(n, 3, 3)))
+        check(lib().slb_datamodel_safe_fuse(n, x1.ptr, C1.ptr, x2.ptr, C2.ptr, xo.ptr, Co.ptr, _stream()))
+        return xo, Co
+
+
+class ErrorStateEkf:
+    """Batch of the error-state `Usckf` of src/filters/UsckfError.hpp: ekfPredict, ekfUpdate and
+    ekfSingleUpdate with Joseph-form covariance updates, cloning.  State lives in device arrays laid out as the
+    reference object holds it: mu (n x 48), err (n x 45), P (n x 45 x 45 dense)."""
+
+    def __init__(self, mu, err, P):
+        self.mu, self.err, self.P = dev(mu), dev(err), dev(P)
+        self.n = self.mu.t.shape[0]
+        torch = _torch()
+        self.accepted = torch.zeros(self.n, dtype=torch.int32, device="cuda")
+
+    def ekf_predict(self, F, Q):
+        F, Q = dev(F), dev(Q)
+        check(lib().slb_ekf_predict(self.n, self.err.ptr, self.P.ptr, F.ptr, Q.ptr, _stream()))
+
+    def ekf_update(self, z, H, R, gate=True):
+        z, H, R = dev(z), dev(H), dev(R)
+        m = z.t.shape[1]
+        ret = DeviceArray(shape=(self.n, m))
+        check(lib().slb_ekf_update(self.n, m, self.mu.ptr, self.P.ptr, z.ptr, H.ptr, R.ptr, 1 if gate else 0, ret.ptr,
+                                   C.c_void_p(self.accepted.data_ptr()), _stream()))
+        return ret
+
+    def ekf_single_update(self, z, H, R, gate=True):
+        z, H, R = dev(z), dev(H), dev(R)
+        m = z.t.shape[1]
+        check(lib().slb_ekf_single_update(self.n, m, self.mu.ptr, self.err.ptr, self.P.ptr, z.ptr, H.ptr, R.ptr,
+                                          1 if gate else 0, C.c_void_p(self.accepted.data_ptr()), _stream()))
+
+    def cloning(self):
+        check(lib().slb_ekf_clone(self.n, self.mu.ptr, self.err.ptr, self.P.ptr, _stream()))
+
+
+class DeadReckon:
+    """DeadReckon::updatePose with uncertainty and TransformWithUncertainty::operator* over n independent poses
+    (DeadReckon.hpp:30-79,246-286; Transform.cpp:215-254).  Poses: pos(3) quat(w,x,y,z); covariances 6x6 over [r t]."""
+
+    @staticmethod
+    def compose(pose2, cov2, pose1, cov1):
+        pose2, cov2, pose1, cov1 = dev(pose2), dev(cov2), dev(pose1), dev(cov1)
+        n = pose2.t.shape[0]
+        po, co = DeviceArray(shape=(n, 7)), DeviceArray(shape=(n, 6, 6))
+        check(lib().slb_transform_compose(n, pose2.ptr, cov2.ptr, pose1.ptr, cov1.ptr, po.ptr, co.ptr, _stream()))
+        return po, co
+
+    @staticmethod
+    def update_pose(dt, vel0, vel1, velcov, prev_pose, prev_cov, out=None):
+        vel0, vel1, velcov, prev_pose, prev_cov = dev(vel0), dev(vel1), dev(velcov), dev(prev_pose), dev(prev_cov)
+        n = vel0.t.shape[0]
+        if out is None:
+            out = (DeviceArray(shape=(n, 7)), DeviceArray(shape=(n, 6, 6)), DeviceArray(shape=(n, 7)), DeviceArray(shape=(n, 6, 6)))
+        post, pcov, dpose, dcov = out
+        check(lib().slb_deadreckon_update_pose(n, float(dt), vel0.ptr, vel1.ptr, velcov.ptr, prev_pose.ptr, prev_cov.ptr,
+                                               post.ptr, pcov.ptr, dpose.ptr, dcov.ptr, _stream()))
+        return post, pcov, dpose, dcov

@@ -191,3 +191,72 @@ def datamodel_fixture():
     x2 = np.array([[0.0168381, 0.000632167, -0.0235605]])
     Cm = 1e-10 * np.eye(3)[None]
     return dict(x1=x1, C1=Cm, x2=x2, C2=Cm, x_expected=0.5 * (x1 + x2), C_expected=0.5 * Cm)
+
+
+# ---- SURVEY 8(f) "next" rows ------------------------------------------------------------------------
+def ekf_vectorize(mu):
+    """ERROR_QUATERNION vectorisation of an augmented error-state mean (n x 48 -> n x 45): per single
+    state pos vel (qx qy qz) gbias abias (UsckfError.hpp:521-531)."""
+    mu = np.asarray(mu)
+    parts = []
+    for s in range(3):
+        q = mu[:, 16 * s:16 * s + 16]
+        parts += [q[:, 0:6], q[:, 7:10], q[:, 10:16]]
+    return np.concatenate(parts, axis=1)
+
+
+def ekf_scenario(n, seed=0, dt=0.01, p_scale=1e-2, cond=1e3, r_sigma=0.05, outlier_frac=0.0):
+    """Row f2: error-state EKF (3 x 15-DOF augmented state).  F = I + dt * A with a random strictly
+    local A per instance (what a linearised IMU error model looks like), delay-position measurement
+    H = [0 .. -I_3(statek_l.pos) .. +I_3(statek_i.pos)], velocity measurement for the single update."""
+    rng = np.random.default_rng(seed)
+    mu = np.zeros((n, 48))
+    for s in range(3):
+        mu[:, 16 * s:16 * s + 6] = rng.normal(size=(n, 6))
+        mu[:, 16 * s + 6:16 * s + 10] = random_unit_quat(rng, n, max_angle=1.0)
+        mu[:, 16 * s + 10:16 * s + 16] = 0.01 * rng.normal(size=(n, 6))
+    err = 1e-3 * rng.normal(size=(n, 45))
+    P = random_spd(rng, n, 45, scale=p_scale, cond=cond)
+    F = np.eye(15)[None] + dt * rng.normal(size=(n, 15, 15))
+    Q = 1e-4 * dt * np.eye(15)
+    H = np.zeros((3, 45))
+    H[:, 15:18] = -np.eye(3)
+    H[:, 30:33] = np.eye(3)
+    R = (r_sigma ** 2) * np.eye(3)
+    z = ekf_vectorize(mu) @ H.T + r_sigma * rng.normal(size=(n, 3))
+    if outlier_frac > 0:
+        bad = rng.uniform(size=n) < outlier_frac
+        z[bad] += 50.0 * r_sigma * np.sign(rng.normal(size=(int(bad.sum()), 3)))
+    Hs = np.zeros((3, 15))
+    Hs[:, 3:6] = np.eye(3)
+    zs = 1e-2 * rng.normal(size=(n, 3))
+    return dict(mu=mu, err=err, P=P, F=F, Q=Q, H=H, R=R, z=z, Hs=Hs, zs=zs, dt=dt)
+
+
+def safe_fusion_scenario(n, seed=5, log_spread=2.0):
+    """Row f3: pairs of 3-D estimates (safeFusion is d = 3 only, DataModel.hpp:104)."""
+    sc = fusion_scenario(n, d=3, seed=seed, log_spread=log_spread)
+    return sc
+
+
+def safe_fusion_fixture():
+    """test/DataModelUnitTest.cpp:66-74: data3 = data1 (x1, 1e-10 I), data3.safeFusion(data2)."""
+    fx = datamodel_fixture()
+    return dict(x1=fx["x1"], C1=fx["C1"], x2=fx["x2"], C2=fx["C2"])
+
+
+def deadreckon_scenario(n, seed=11, dt=0.01):
+    """Row f4: body velocities at two consecutive samples (linear 3, angular 3), their shared 6x6
+    covariance, and a previous pose with uncertainty (pos(3) quat(w,x,y,z); cov over [r t])."""
+    rng = np.random.default_rng(seed)
+    vel0 = np.concatenate([rng.normal(size=(n, 3)), 0.5 * rng.normal(size=(n, 3))], axis=1)
+    vel1 = vel0 + 0.05 * rng.normal(size=(n, 6))
+    A = rng.normal(size=(6, 6))
+    velcov = np.zeros((6, 6))
+    velcov[:3, :3] = 1e-2 * (A[:3, :3] @ A[:3, :3].T + np.eye(3))
+    velcov[3:, 3:] = 1e-3 * (A[3:, 3:] @ A[3:, 3:].T + np.eye(3))
+    prev_pose = np.concatenate([rng.normal(size=(n, 3)) * 5.0, random_unit_quat(rng, n, max_angle=np.pi)], axis=1)
+    flip = rng.uniform(size=n) < 0.3          # both quaternion signs reach the matrix->quaternion branch logic
+    prev_pose[flip, 3:] *= -1.0
+    prev_cov = random_spd(rng, n, 6, scale=1e-3, cond=1e2)
+    return dict(dt=dt, vel0=vel0, vel1=vel1, velcov=velcov, prev_pose=prev_pose, prev_cov=prev_cov)
