@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- filter-steps/sec of the batched sigma-point filter hot path on N B200s of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ukfom|usckf|msckf|fusion]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ukfom|usckf|msckf|fusion|ekf|safefusion|deadreckon]
                   [--impl reference]
 
 A "step" is one pass of the hot path (predict + update) over one batch of synthetic inputs.  The
@@ -421,15 +421,10 @@ class MsckfWorkload:
 WORKLOADS = {"ukfom": UkfomWorkload, "fusion": FusionWorkload, "usckf": UsckfWorkload, "msckf": MsckfWorkload}
 
 
-def register_workload(cls):
-    WORKLOADS[cls.name] = cls
-    return cls
+import bench_workloads  # noqa: E402  (SURVEY 8f "next" rows: ekf, safefusion, deadreckon)
 
-
-try:  # heavier workloads live next to the kernels they exercise
-    import bench_workloads  # noqa: F401,E402
-except ImportError:
-    pass
+for _cls in bench_workloads.WORKLOADS:
+    WORKLOADS[_cls.name] = _cls
 
 
 # ------------------------------------------------------------------------------------------------------

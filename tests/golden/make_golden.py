@@ -56,10 +56,28 @@ def fusion():
         np.savez_compressed(os.path.join(OUT, "fusion_d%d.npz" % d), xo=xo, Co=Co, **sc)
 
 
+def next_rows():
+    """error-state EKF, safeFusion, dead reckoning with uncertainty."""
+    sc = synth.ekf_scenario(6, seed=104, outlier_frac=0.3)
+    err1, P1 = slo.ekf_predict(sc["err"], sc["P"], sc["F"], sc["Q"])
+    P2, ret, acc = slo.ekf_update(sc["mu"], P1, sc["z"], sc["H"], sc["R"], gate=1)
+    mu3, P3, acc3 = slo.ekf_single_update(sc["mu"], err1, P2, sc["zs"], sc["Hs"], sc["R"], gate=1)
+    np.savez_compressed(os.path.join(OUT, "ekf_n45.npz"), mu0=sc["mu"], err0=sc["err"], P0=sc["P"], F=sc["F"], Q=sc["Q"],
+                        H=sc["H"], R=sc["R"], z=sc["z"], Hs=sc["Hs"], zs=sc["zs"], err1=err1, P1=P1, P2=P2, ret=ret, acc=acc,
+                        mu3=mu3, P3=P3, acc3=acc3)
+    sf = synth.safe_fusion_scenario(64, log_spread=1.5)
+    xo, Co = slo.safe_fusion(sf["x1"], sf["C1"], sf["x2"], sf["C2"])
+    np.savez_compressed(os.path.join(OUT, "safe_fusion_d3.npz"), xo=xo, Co=Co, **sf)
+    dr = synth.deadreckon_scenario(32, seed=105)
+    post, pcov, dpose, dcov = slo.dr_update_pose(dr["dt"], dr["vel0"], dr["vel1"], dr["velcov"], dr["prev_pose"], dr["prev_cov"])
+    np.savez_compressed(os.path.join(OUT, "deadreckon.npz"), post=post, pcov=pcov, dpose=dpose, dcov=dcov, **dr)
+
+
 if __name__ == "__main__":
     ukf()
     usckf()
     msckf()
     fusion()
+    next_rows()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -152,3 +152,29 @@ def test_dead_reckon_chain(slo):
     sgn = np.sign(np.sum(a[:, 3:] * pose[:, 3:], axis=1, keepdims=True))
     assert _rel(sgn * a[:, 3:], pose[:, 3:]) <= 1e-7
     assert cov_error(dcov.numpy(), cov) <= 1e-6
+
+
+def test_next_rows_against_committed_golden():
+    """The CUDA path against the committed fixtures of tests/golden/ (no oracle in the loop)."""
+    import os
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(G, "ekf_n45.npz"))
+    f = engine.ErrorStateEkf(g["mu0"], g["err0"], g["P0"])
+    f.ekf_predict(g["F"], g["Q"])
+    assert cov_error(f.P.numpy(), g["P1"]) <= STEP_TOL
+    ret = f.ekf_update(g["z"], g["H"], g["R"], gate=True).numpy()
+    np.testing.assert_array_equal(f.accepted.cpu().numpy(), g["acc"])
+    assert cov_error(f.P.numpy(), g["P2"]) <= STEP_TOL
+    assert _rel(ret, g["ret"]) <= STEP_TOL
+    f.ekf_single_update(g["zs"], g["Hs"], g["R"], gate=True)
+    np.testing.assert_array_equal(f.accepted.cpu().numpy(), g["acc3"])
+    assert cov_error(f.P.numpy(), g["P3"]) <= STEP_TOL
+    assert _rel(f.mu.numpy(), g["mu3"]) <= STEP_TOL
+    g = np.load(os.path.join(G, "safe_fusion_d3.npz"))
+    xo, Co = engine.DataModel.safe_fuse(g["x1"], g["C1"], g["x2"], g["C2"])
+    np.testing.assert_array_equal(xo.numpy(), g["xo"])
+    np.testing.assert_array_equal(Co.numpy(), g["Co"])
+    g = np.load(os.path.join(G, "deadreckon.npz"))
+    out = engine.DeadReckon.update_pose(float(g["dt"]), g["vel0"], g["vel1"], g["velcov"], g["prev_pose"], g["prev_cov"])
+    for a, k in zip(out, ("post", "pcov", "dpose", "dcov")):
+        assert _rel(a.numpy(), g[k]) <= STEP_TOL, k

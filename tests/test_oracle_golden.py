@@ -44,3 +44,27 @@ def test_fusion_golden(slo):
         xo, Co = slo.datamodel(0, g["x1"], g["C1"], g["x2"], g["C2"])
         np.testing.assert_array_equal(xo, g["xo"])
         np.testing.assert_array_equal(Co, g["Co"])
+
+
+def test_next_rows_golden(slo):
+    g = np.load(os.path.join(G, "ekf_n45.npz"))
+    err1, P1 = slo.ekf_predict(g["err0"], g["P0"], g["F"], g["Q"])
+    np.testing.assert_allclose(err1, g["err1"], **TOL)
+    np.testing.assert_allclose(P1, g["P1"], **TOL)
+    P2, ret, acc = slo.ekf_update(g["mu0"], P1, g["z"], g["H"], g["R"], gate=1)
+    np.testing.assert_allclose(P2, g["P2"], **TOL)
+    np.testing.assert_allclose(ret, g["ret"], **TOL)
+    np.testing.assert_array_equal(acc, g["acc"])
+    assert 0 < acc.sum() < len(acc)
+    mu3, P3, acc3 = slo.ekf_single_update(g["mu0"], err1, P2, g["zs"], g["Hs"], g["R"], gate=1)
+    np.testing.assert_allclose(mu3, g["mu3"], **TOL)
+    np.testing.assert_allclose(P3, g["P3"], **TOL)
+    np.testing.assert_array_equal(acc3, g["acc3"])
+    g = np.load(os.path.join(G, "safe_fusion_d3.npz"))
+    xo, Co = slo.safe_fusion(g["x1"], g["C1"], g["x2"], g["C2"])
+    np.testing.assert_array_equal(xo, g["xo"])
+    np.testing.assert_array_equal(Co, g["Co"])
+    g = np.load(os.path.join(G, "deadreckon.npz"))
+    out = slo.dr_update_pose(float(g["dt"]), g["vel0"], g["vel1"], g["velcov"], g["prev_pose"], g["prev_cov"])
+    for a, k in zip(out, ("post", "pcov", "dpose", "dcov")):
+        np.testing.assert_allclose(a, g[k], **TOL)
