@@ -233,4 +233,90 @@ class DeadReckonWorkload:
         return time.perf_counter() - t0
 
 
-WORKLOADS = [EkfWorkload, SafeFusionWorkload, DeadReckonWorkload]
+class MsckfEkfWorkload:
+    """Row f1: batched MSCKF with the EKF-flavoured update (Jacobian, information-matrix outlier gate, QR compression),
+    config-3 shapes: 10 clones (N = 72), 50 features (m = 100), 16,384 instances per GPU; predict + update, two launches."""
+    name = "msckf_ekf"
+    metric = "filter-steps/sec (predict + EKF update with QR compression)"
+    unit = "filter-steps/s"
+    B = 16384
+    NPRIOR = 512
+    K = 10
+    NFEAT = 50
+    bytes_per_unit = 44176          # same state traffic as the UKF flavour (SURVEY 8d): 2*8*(2628+83) + 800
+    # information: H P H^T (sparse H) 0.13M + chol 100 0.33M + L^-1 0.33M; QR 100x72 0.79M + thin Q 0.79M;
+    # Q^T R Q 2.5M; Hr P Hr^T 0.75M; chol 72 0.12M; TRSM 0.37M; Y Y^T 0.37M
+    flops_per_unit = 6.5e6
+    kernel = "slbd::msckf_ekf_update_kernel (+ predict12_kernel)"
+    phases = ("predict12_kernel", "msckf_ekf_update_kernel")
+    dominant = 1
+    traffic = None
+
+    def __init__(self, rank, seed=777):
+        self.sc = synth.msckf_scenario(self.NPRIOR, seed=seed + 1000 * rank, k=self.K, nfeat=self.NFEAT)
+        rng = np.random.default_rng(seed + 1000 * rank + 1)
+        rep = self.B // self.NPRIOR
+        self.u = np.tile(self.sc["u"], (rep, 1))
+        self.u[:, 0:3] = 0.0
+        self.u[:, 3:7] = [1.0, 0.0, 0.0, 0.0]
+        self.z = np.tile(self.sc["z"], (rep, 1)) + rng.normal(size=(self.B, 2 * self.NFEAT)) * 1e-3
+
+    def describe(self):
+        return {"workload": "SURVEY 8f row f1: batched MSCKF, EKF-flavoured update with outlier gate and QR compression, "
+                            "10 clones (N=72), 50 features (m=100)", "instances_per_gpu": self.B, "N": 72, "m": 100}
+
+    def setup_gpu(self, engine, torch):
+        self.engine, self.torch = engine, torch
+        self.f = engine.Msckf(self.B, nclones=self.K)
+        self.f.set_state(self.sc["mu"], self.sc["P"], replicate=True)
+        self.Q, self.R, self.lm = (engine.DeviceArray(self.sc[k]) for k in ("Q", "R", "landmarks"))
+        self.du, self.dz = engine.DeviceArray(self.u), engine.DeviceArray(self.z)
+        self.hu = torch.from_numpy(self.u).pin_memory()
+        self.hz = torch.from_numpy(self.z).pin_memory()
+        self.hmu = torch.empty((self.B, 13 + 7 * self.K), dtype=torch.float64).pin_memory()
+        self.l2_policy = "fleet state %.0f MB per step > L2" % (self.B * (2640 + 84) * 8 / 1e6)
+
+    def step_phase(self, k, p):
+        e = self.engine
+        if p == 0:
+            self.f.predict(e.PM_MSCKF_DELTAPOSE, self.du, 0.0, self.Q)
+        else:
+            self.f.update_ekf(e.MM_MSCKF_REPROJ, self.lm, self.dz, self.R, gate=True)
+
+    def step(self, k):
+        self.step_phase(k, 0)
+        self.step_phase(k, 1)
+
+    def step_e2e(self, k):
+        self.du.t.copy_(self.hu, non_blocking=True)
+        self.dz.t.copy_(self.hz, non_blocking=True)
+        self.step(k)
+        self.hmu.copy_(self.torch.from_numpy(self.f.mu()))   # slb_download: device records -> host q-vectors
+
+    def e2e_bytes(self):
+        return self.B * (13 + 2 * self.NFEAT) * 8, self.B * (13 + 7 * self.K) * 8
+
+    def units_per_step(self):
+        return self.B
+
+    def launches_per_step(self):
+        return 2
+
+    def status_ok(self):
+        c = self.f.status_counts()
+        return c[0] == 0 and c[1] == 0 and c[3] == 0
+
+    def stats_tensor(self):
+        return self.f.ensemble_stats().t
+
+    def cpu_step(self, slo, nsample, nthreads):
+        sc = self.sc
+        n = min(nsample, self.NPRIOR)
+        t0 = time.perf_counter()
+        mu, P, _ = slo.msckf_predict(slo.PM_MSCKF_DELTAPOSE, self.K, sc["mu"][:n], sc["P"][:n], self.u[:n], 0.0, sc["Q"],
+                                     nthreads=nthreads)
+        slo.msckf_update_ekf(slo.MM_MSCKF_REPROJ, self.K, mu, P, sc["landmarks"], self.z[:n], sc["R"], nthreads=nthreads)
+        return (time.perf_counter() - t0) * nsample / n
+
+
+WORKLOADS = [EkfWorkload, SafeFusionWorkload, DeadReckonWorkload, MsckfEkfWorkload]

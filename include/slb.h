@@ -47,7 +47,9 @@ enum {
     SLB_ST_CHOL_FAIL = 1,   /* LLT pivot <= 0 [Eigen::LLT info() ignored, Usckf.hpp:537-538]  */
     SLB_ST_MEAN_NOCONV = 2, /* manifold mean hit max_it [assert(false), Usckf.hpp:620-624]     */
     SLB_ST_GATE_REJECT = 4, /* significance test rejected the update [Usckf.hpp:294]           */
-    SLB_ST_NONFINITE = 8    /* NaN/Inf met in the state                                        */
+    SLB_ST_NONFINITE = 8,   /* NaN/Inf met in the state                                        */
+    SLB_ST_QR_ROWS = 16     /* Msckf EKF update: fewer measurement rows than DOF left after the
+                               outlier removal [R.block(0,0,N,N) out of range, Msckf.hpp:808]  */
 };
 
 /* Filter kinds (which reference class the batch stands for). */
@@ -177,6 +179,15 @@ int slb_msckf_predict(slb_handle h, int pm, const double *u_dev, double dt, cons
  * return value, :276) is kept in SLB_FIELD_OUTLIERS. */
 int slb_msckf_update(slb_handle h, int mm, const double *params_dev, int m, const double *z_dev,
                      const double *R_dev, int gate, void *stream);
+
+/* SURVEY 8(f) row f1 -- update(z, h, H, R[, mt]) Msckf.hpp:285-349, the EKF flavour: h also returns
+ * its Jacobian H (m x N), removeOutliers works on the information matrix (:756-792, quirk Q6 and the
+ * never-compacted `information` reproduced), reduceDimension compresses (H, innovation, R) through a
+ * Householder QR (:794-816), then S = H P H^T + R, K = P H^T S^-1, Pk -= K S K^T, mu = mu [+] K nu.
+ * Same arguments as slb_msckf_update; an instance left with fewer rows than DOF is flagged
+ * SLB_ST_QR_ROWS and left unchanged. */
+int slb_msckf_update_ekf(slb_handle h, int mm, const double *params_dev, int m, const double *z_dev,
+                         const double *R_dev, int gate, void *stream);
 
 /* predict + update with HOST buffers: u (batch x nu), z (batch x m) and the shared Q (12x12),
  * params (nparams doubles), R (m x m) are copied to the device, both kernels run, the posterior

@@ -303,3 +303,30 @@ def dr_update_attitude(dt, w0, w1):
     lib().slo_dr_update_attitude.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     lib().slo_dr_update_attitude(float(dt), _p(w0), _p(w1), _p(dq))
     return dq
+
+
+def msckf_update_ekf(mm, k, mu, P, landmarks, z, R, gate=True, nthreads=1):
+    """Msckf::update, EKF flavour (Msckf.hpp:297-349).  Returns mu, P, outliers, status."""
+    mu, P, landmarks, z, R = _d(mu).copy(), _d(P).copy(), _d(landmarks), _d(z), _d(R)
+    B, m = z.shape
+    out, st = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    rc = lib().slo_msckf_update_ekf(int(mm), B, int(k), _p(mu), _p(P), _p(landmarks), m, _p(z), _p(R), 1 if gate else 0,
+                                    _p(out), _p(st), nthreads)
+    assert rc == 0
+    return mu, P, out, st
+
+
+def msckf_reproj_jac(k, mu, landmarks):
+    mu, landmarks = _d(mu), _d(landmarks)
+    nfeat = landmarks.shape[0]
+    z, H = np.empty(2 * nfeat), np.empty((2 * nfeat, 12 + 6 * k))
+    lib().slo_msckf_reproj_jac(int(k), _p(mu), _p(landmarks), nfeat, _p(z), _p(H))
+    return z, H
+
+
+def householder_qr(A):
+    A = _d(A)
+    rows, cols = A.shape
+    QR, tau, Q = np.empty((rows, cols)), np.empty(min(rows, cols)), np.empty((rows, cols))
+    lib().slo_householder_qr(rows, cols, _p(A), _p(QR), _p(tau), _p(Q))
+    return QR, tau, Q

@@ -281,6 +281,38 @@ int slo_ekf_clone(long long n, double *mu, double *err, double *P) {
     }
     return 0;
 }
+// f1: Msckf::update EKF flavour; same array conventions as slo_msckf_update
+int slo_msckf_update_ekf(int mm, int B, int k, double *mu, double *P, const double *landmarks, int m, const double *z,
+                         const double *R, int gate, int *outliers, int *status, int nthreads) {
+    const int N = 12 + 6 * k, q = 13 + 7 * k, nfeat = m / 2;
+    if (mm != SLB_MM_MSCKF_REPROJ) return -1;
+    parallel_for(B, nthreads, [&](int i) {
+        Msckf f(k, Vec(mu + (size_t)i * q, mu + (size_t)(i + 1) * q), load_mat(P + (size_t)i * N * N, N, N));
+        unsigned o = msckf_update_ekf(f, Vec(z + (size_t)i * m, z + (size_t)(i + 1) * m),
+                                      [=](const Vec &s, Mat &H) { return mm_msckf_reproj_jac(s, k, landmarks, nfeat, H); },
+                                      load_mat(R, m, m), gate != 0);
+        std::copy(f.mu.begin(), f.mu.end(), mu + (size_t)i * q);
+        store_mat(f.Pk, P + (size_t)i * N * N);
+        if (outliers) outliers[i] = (int)o;
+        if (status) status[i] = f.status;
+    });
+    return 0;
+}
+// measurement + Jacobian of the reprojection model for one state (H: m x N)
+void slo_msckf_reproj_jac(int k, const double *mu, const double *landmarks, int nfeat, double *z, double *H) {
+    Mat Hm;
+    Vec zz = mm_msckf_reproj_jac(Vec(mu, mu + 13 + 7 * k), k, landmarks, nfeat, Hm);
+    std::copy(zz.begin(), zz.end(), z);
+    store_mat(Hm, H);
+}
+void slo_householder_qr(int rows, int cols, const double *A, double *QR, double *tau, double *thinQ) {
+    Mat a = load_mat(A, rows, cols);
+    Vec t;
+    householder_qr(a, t);
+    store_mat(a, QR);
+    std::copy(t.begin(), t.end(), tau);
+    store_mat(householder_thin_q(a, t, cols), thinQ);
+}
 // f3: safeFusion, d = 3
 int slo_safe_fusion(long long n, const double *x1, const double *C1, const double *x2, const double *C2, double *xo,
                     double *Co, int nthreads) {

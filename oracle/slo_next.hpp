@@ -1,6 +1,7 @@
 // oracle/slo_next.hpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 //
 // CPU restatement of the SURVEY section 8(f) "next" rows:
+//   f1  Msckf::update, EKF flavour with QR compression  src/filters/Msckf.hpp:297-349,756-816
 //   f2  error-state EKF with Joseph-form update   src/filters/UsckfError.hpp:87-137,322-384,489-571,573-603
 //   f3  DataModel<double,3>::safeFusion            src/core/DataModel.hpp:62-130
 //   f4  DeadReckon::updateAttitude / updatePose and TransformWithUncertainty::operator*
@@ -8,6 +9,8 @@
 // PARITY UNPINNED (see slo_core.hpp): the reference asserts none of these outputs.  Third-party
 // algorithms restated from their published sources (Eigen 3.3 series; no version pinned by the
 // reference, src/CMakeLists.txt:26):
+//   * Eigen::HouseholderQR (makeHouseholderInPlace: beta = -sign(c0) |x|, tau = (beta - c0)/beta, tau = 0 for a
+//     zero tail; applyHouseholderOnTheLeft; householderQ() applied to a thin identity)  -- Msckf.hpp:799-805
 //   * Eigen::JacobiSVD for real square matrices (two-sided Jacobi, sweep order p = 1.., q < p,
 //     threshold 2 eps max|diag|, sign fix-up on U, descending sort)  -- DataModel.hpp:83,97
 //   * Eigen::Quaternion(Matrix3) (Shoemake's trace method), Quaternion::toRotationMatrix,
@@ -19,8 +22,170 @@
 #include <cfloat>
 
 #include "slo_filters.hpp"
+#include "slo_models.hpp"
 
 namespace slo {
+
+// Eigen::Quaternion::toRotationMatrix (used by f1 and f4)
+inline Mat quat_to_rot_fwd(const double q[4]) {
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    Mat R(3, 3);
+    R(0, 0) = 1 - (tyy + tzz); R(0, 1) = txy - twz; R(0, 2) = txz + twy;
+    R(1, 0) = txy + twz; R(1, 1) = 1 - (txx + tzz); R(1, 2) = tyz - twx;
+    R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = 1 - (txx + tyy);
+    return R;
+}
+
+
+// ==========================================================================================
+// f1: Msckf::update, EKF flavour (Msckf.hpp:297-349) with removeOutliers on H (:756-792, index quirk Q6 and the
+// never-compacted `information` matrix reproduced) and reduceDimension (:794-816).
+// ==========================================================================================
+// Jacobian of mm_msckf_reproj with respect to the tangent perturbation of the multi-state (p' = p + dp,
+// q' = q exp(dtheta)):  pc' = pc - R^T dp + [pc]x dtheta,  z = (x/z, y/z).  The reference's EKF update receives H
+// from the caller's functor h(mu, H) (:311); this is the functor of the builder-defined reprojection model.
+inline Vec mm_msckf_reproj_jac(const Vec &s, int k, const double *lm, int nfeat, Mat &H) {
+    const int N = 12 + 6 * k;
+    H = Mat(2 * nfeat, N);
+    Vec z(2 * nfeat);
+    for (int f = 0; f < nfeat; ++f) {
+        const int j = f % k;
+        const double *p = &s[13 + 7 * j], *q = &s[13 + 7 * j + 3];
+        const double d[3] = {lm[3 * f] - p[0], lm[3 * f + 1] - p[1], lm[3 * f + 2] - p[2]};
+        double qc[4], pc[3];
+        quat_conj(q, qc);
+        quat_rotate(qc, d, pc);
+        z[2 * f] = pc[0] / pc[2];
+        z[2 * f + 1] = pc[1] / pc[2];
+        const Mat R = quat_to_rot_fwd(q);
+        double J[3][6];  // d pc / d (dp, dtheta)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) J[a][b] = -R(b, a);
+        J[0][3] = 0.0; J[0][4] = -pc[2]; J[0][5] = pc[1];
+        J[1][3] = pc[2]; J[1][4] = 0.0; J[1][5] = -pc[0];
+        J[2][3] = -pc[1]; J[2][4] = pc[0]; J[2][5] = 0.0;
+        const double iz = 1.0 / pc[2];
+        for (int c = 0; c < 6; ++c) {
+            H(2 * f, 12 + 6 * j + c) = iz * (J[0][c] - z[2 * f] * J[2][c]);
+            H(2 * f + 1, 12 + 6 * j + c) = iz * (J[1][c] - z[2 * f + 1] * J[2][c]);
+        }
+    }
+    return z;
+}
+
+// Eigen::HouseholderQR, in place: R in the upper triangle, essential parts below, coefficients in tau.
+inline void householder_qr(Mat &A, Vec &tau) {
+    const int rows = A.r, cols = A.c, size = std::min(rows, cols);
+    tau.assign(size, 0.0);
+    for (int k = 0; k < size; ++k) {
+        const double c0 = A(k, k);
+        double tail = 0.0;
+        for (int i = k + 1; i < rows; ++i) tail += A(i, k) * A(i, k);
+        double beta;
+        if (tail <= DBL_MIN) {
+            tau[k] = 0.0;
+            beta = c0;
+            for (int i = k + 1; i < rows; ++i) A(i, k) = 0.0;
+        } else {
+            beta = std::sqrt(c0 * c0 + tail);
+            if (c0 >= 0.0) beta = -beta;
+            for (int i = k + 1; i < rows; ++i) A(i, k) /= (c0 - beta);
+            tau[k] = (beta - c0) / beta;
+        }
+        A(k, k) = beta;
+        for (int j = k + 1; j < cols; ++j) {  // applyHouseholderOnTheLeft
+            double tmp = 0.0;
+            for (int i = k + 1; i < rows; ++i) tmp += A(i, k) * A(i, j);
+            tmp += A(k, j);
+            A(k, j) -= tau[k] * tmp;
+            for (int i = k + 1; i < rows; ++i) A(i, j) -= tau[k] * A(i, k) * tmp;
+        }
+    }
+}
+// householderQ() * Identity(rows, ncols): reflectors applied last to first
+inline Mat householder_thin_q(const Mat &QR, const Vec &tau, int ncols) {
+    const int rows = QR.r;
+    Mat Q(rows, ncols);
+    for (int i = 0; i < std::min(rows, ncols); ++i) Q(i, i) = 1.0;
+    for (int k = (int)tau.size() - 1; k >= 0; --k)
+        for (int j = 0; j < ncols; ++j) {
+            double tmp = 0.0;
+            for (int i = k + 1; i < rows; ++i) tmp += QR(i, k) * Q(i, j);
+            tmp += Q(k, j);
+            Q(k, j) -= tau[k] * tmp;
+            for (int i = k + 1; i < rows; ++i) Q(i, j) -= tau[k] * QR(i, k) * tmp;
+        }
+    return Q;
+}
+
+enum { ST_QR_ROWS = 16 };  // reduceDimension needs rows >= DOF (R.block(0,0,N,N), :808: out of range otherwise)
+
+// returns the outlier count (:349); hj(mu, H) is the measurement functor that also fills the Jacobian
+inline unsigned msckf_update_ekf(Msckf &f, const Vec &z, const std::function<Vec(const Vec &, Mat &)> &hj, const Mat &R0,
+                                 bool gate) {
+    const Layout lm = f.multi();
+    const int N = f.dof();
+    Mat H;
+    const Vec mean_z = hj(f.mu, H);                                                        // :311
+    Vec innov(z.size());
+    for (size_t i = 0; i < z.size(); ++i) innov[i] = z[i] - mean_z[i];                     // :313
+    Mat R = R0;
+    unsigned outliers = 0;
+    if (gate) {                                                                            // :315 -> :756-792
+        const Mat info = inverse_lu(add(matmul(matmul(H, f.Pk), H.transpose()), R));       // :765-766, never compacted
+        std::vector<int> kept(innov.size());
+        for (size_t i = 0; i < kept.size(); ++i) kept[i] = (int)i;
+        unsigned i = 0;
+        while (i < kept.size() / 2) {
+            const double v0 = innov[kept[2 * i]], v1 = innov[kept[2 * i + 1]];
+            const double i00 = info(2 * i, 2 * i), i01 = info(2 * i, 2 * i + 1), i10 = info(2 * i + 1, 2 * i),
+                         i11 = info(2 * i + 1, 2 * i + 1);
+            const double m2 = v0 * (i00 * v0 + i01 * v1) + v1 * (i10 * v0 + i11 * v1);     // :773
+            if (!accept_mahalanobis_distance(m2, 2)) {
+                Msckf::remove_at(kept, 2 * i);                                             // :778-781 (Q6)
+                Msckf::remove_at(kept, 2 * i + 1);
+                ++outliers;
+            } else {
+                ++i;
+            }
+        }
+        const int m = (int)kept.size();
+        Vec in2(m);
+        Mat H2(m, N), R2(m, m);
+        for (int p = 0; p < m; ++p) {
+            in2[p] = innov[kept[p]];
+            for (int c = 0; c < N; ++c) H2(p, c) = H(kept[p], c);
+            for (int q = 0; q < m; ++q) R2(p, q) = R(kept[p], kept[q]);
+        }
+        innov = in2; H = H2; R = R2;
+    }
+    if (!innov.empty()) {                                                                  // :322
+        if ((int)innov.size() < N) {
+            f.status |= ST_QR_ROWS;
+            return outliers;
+        }
+        Vec tau;                                                                           // :794-816
+        Mat QR = H;
+        householder_qr(QR, tau);
+        const Mat thinQ = householder_thin_q(QR, tau, N);
+        Mat Hr(N, N);
+        for (int i = 0; i < N; ++i)
+            for (int j = i; j < N; ++j) Hr(i, j) = QR(i, j);
+        const Mat Qt = thinQ.transpose();
+        innov = matvec(Qt, innov);
+        R = matmul(matmul(Qt, R), thinQ);
+        const Mat Ht = Hr.transpose();
+        const Mat S = add(matmul(matmul(Hr, f.Pk), Ht), R);                                // :330
+        const Mat K = matmul(matmul(f.Pk, Ht), inverse_lu(S));                             // :331
+        f.Pk = sub(f.Pk, matmul(matmul(K, S), K.transpose()));                             // :336
+        f.mu = boxplus(lm, f.mu, matvec(K, innov));                                        // :337
+    }
+    return outliers;
+}
 
 // ==========================================================================================
 // f2: error-state EKF (UsckfError.hpp).  Builder-defined 15-DOF single state (the reference's type is

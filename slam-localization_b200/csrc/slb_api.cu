@@ -569,6 +569,15 @@ int slb_msckf_update(slb_handle h, int mm, const double *params, int m, const do
     return launch_msckf_update(mm, a, S(stream));
 }
 
+int slb_msckf_update_ekf(slb_handle h, int mm, const double *params, int m, const double *z, const double *R, int gate,
+                         void *stream) {
+    if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_update_ekf: handle is not an MSCKF batch");
+    if (!params || !z || !R || m <= 0 || (m & 1)) return set_error(SLB_ERR_INVALID, "slb_msckf_update_ekf: bad arguments");
+    FilterArgs a = make_args(h);
+    a.params = params; a.m = m; a.z = z; a.R = R; a.gate = gate;
+    return launch_msckf_update_ekf(mm, a, S(stream));
+}
+
 // predict + update with HOST buffers (the end-to-end arm of bench.py): u | z staged on the device, the
 // posterior means copied back.  Q, R and the landmark parameters are small shared inputs.
 int slb_msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,

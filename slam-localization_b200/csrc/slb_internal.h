@@ -67,6 +67,7 @@ int launch_usckf_set_measurement(int mode, const FilterArgs &a, cudaStream_t s);
 // slb_msckf.cu
 int launch_msckf_predict(int pm, const FilterArgs &a, cudaStream_t s);
 int launch_msckf_update(int mm, const FilterArgs &a, cudaStream_t s);
+int launch_msckf_update_ekf(int mm, const FilterArgs &a, cudaStream_t s);
 // slb_fusion.cu
 int launch_fusion(int d, int64_t n, int op, const double *x1, const double *C1, const double *x2,
                   const double *C2, double *xo, double *Co, cudaStream_t s);

@@ -538,6 +538,420 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
     }
 }
 
+
+// =====================================================================================================
+// Msckf::update, EKF flavour (Msckf.hpp:297-349) -- h(mu, H) with its Jacobian, removeOutliers on
+// H (:756-792: information = (H P H^T + R)^-1 computed once and never compacted, row-index quirk Q6), reduceDimension
+// (:794-816: Householder QR of H, thin Q, H <- R(0:N,0:N), nu <- Q^T nu, R <- Q^T R Q), S = H P H^T + R,
+// K = P H^T S^-1, Pk -= K S K^T, mu = mu [+] K nu.  One instance per CTA, everything in shared memory:
+//   RA  2632 : Pk (packed lower), read-only
+//   RS  5056 : S100 -> L100 (information) ... later Rr -> S72 -> Ls
+//   RH  7600 : H (100 x 76) ... later thin Q ... later covXZ = P Hr^T -> Y = covXZ Ls^-T
+//   RQ  7600 : T = H P ... L100^-1 (packed) ... compacted H -> R1 (Householder QR in place)
+// Same algebra shortcuts as the UKF flavour (quirk Q9): the 2x2 diagonal blocks of the information matrix come from
+// the triangular inverse of chol(S100) (information_ff = W_f^T W_f), and with S = Ls Ls^T, Y = (P Hr^T) Ls^-T the
+// gain algebra is Pk -= Y Y^T, delta = Y (Ls^-1 nu).  The measurement model is SLB_MM_MSCKF_REPROJ with its analytic
+// Jacobian (d pc = -R^T dp + [pc]x dtheta); H has one 2 x 6 block per feature, which the H P H^T products exploit.
+// =====================================================================================================
+constexpr int ME_HS = 76;  // row stride of H / Q / covXZ (= 12 mod 16: conflict-free DMMA fragment loads)
+constexpr int ME_RA = 2632, ME_RS = 5056, ME_RH = MS_MMAX * ME_HS, ME_RQ = MS_MMAX * ME_HS, ME_RD = 2304;
+constexpr int ME_SMEM_DOUBLES = ME_RA + ME_RS + ME_RH + ME_RQ + ME_RD;
+static_assert(ME_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF EKF update working set exceeds shared memory");
+
+__global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double *RA = sm, *RS = RA + ME_RA, *RH = RS + ME_RS, *RQ = RH + ME_RH, *RD = RQ + ME_RQ;
+    double *mu = RD, *nu = mu + 84, *wv = nu + 100, *dl = wv + 100, *invd = dl + 72, *tau = invd + 104, *Hb = tau + 72,
+           *info = Hb + 600, *T3 = info + 152, *scal = T3 + 800;  // scal: 8
+    int *kept = reinterpret_cast<int *>(scal + 8);  // 100 ints
+    int *flags = kept + 100;                        // [0] chol ok, [1] kept count, [2] outliers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int k = a.k, N = 12 + 6 * k, QD = 13 + 7 * k, M = a.m, NF = M / 2, NB = 4 + 2 * k;
+    const int NP = N * (N + 1) / 2;
+    const int nrt = (N + 7) >> 3;
+    auto Psym = [&](int i, int j) { return i >= j ? RA[tri(i, j)] : RA[tri(j, i)]; };
+
+    for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
+        double *Pg = a.P + (size_t)inst * a.pstride;
+        double *mug = a.mu + (size_t)inst * a.qstride;
+        const double *zg = a.z + (size_t)inst * M;
+        __syncthreads();
+        for (int e = tid; e < NP; e += MS_T) RA[e] = Pg[e];
+        for (int e = tid; e < QD; e += MS_T) mu[e] = mug[e];
+        for (int e = tid; e < M * ME_HS; e += MS_T) RH[e] = 0.0;
+        if (tid == 0) { flags[0] = 1; flags[1] = M; flags[2] = 0; }
+        __syncthreads();
+        // ---- mean_z = h(mu, H), innovation (:311-313): thread per feature ---------------------------------------
+        if (tid < NF) {
+            const int f = tid, c = f % k;
+            const double *mp = mu + 13 + 7 * c, *q = mp + 3;
+            const double dv[3] = {__ldg(a.params + 3 * f) - mp[0], __ldg(a.params + 3 * f + 1) - mp[1],
+                                  __ldg(a.params + 3 * f + 2) - mp[2]};
+            double pc[3];
+            quat_rotate_inv(q, dv, pc);
+            const double iz = 1.0 / pc[2];
+            const double z0 = pc[0] * iz, z1 = pc[1] * iz;
+            nu[2 * f] = zg[2 * f] - z0;
+            nu[2 * f + 1] = zg[2 * f + 1] - z1;
+            // d pc / d(dp) = -R^T, d pc / d(dtheta) = [pc]x
+            const double w = q[0], x = q[1], y = q[2], zq = q[3];
+            const double tx = 2 * x, ty = 2 * y, tz = 2 * zq;
+            const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y,
+                         tyz = tz * y, tzz = tz * zq;
+            const double Rm[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx,
+                                  txz - twy,       tyz + twx, 1 - (txx + tyy)};
+            double J[3][6];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) J[r][cc] = -Rm[cc * 3 + r];
+            J[0][3] = 0.0; J[0][4] = -pc[2]; J[0][5] = pc[1];
+            J[1][3] = pc[2]; J[1][4] = 0.0; J[1][5] = -pc[0];
+            J[2][3] = -pc[1]; J[2][4] = pc[0]; J[2][5] = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) {
+                const double h0 = iz * (J[0][cc] - z0 * J[2][cc]), h1 = iz * (J[1][cc] - z1 * J[2][cc]);
+                Hb[(2 * f) * 6 + cc] = h0;
+                Hb[(2 * f + 1) * 6 + cc] = h1;
+                RH[(2 * f) * ME_HS + 12 + 6 * c + cc] = h0;
+                RH[(2 * f + 1) * ME_HS + 12 + 6 * c + cc] = h1;
+            }
+        }
+        __syncthreads();
+        int mk = M;
+        if (a.gate) {
+            // ---- information = (H P H^T + R)^-1 (:765-766).  T = H P over the clone columns (6 FMA per entry) ------
+            for (int e = tid; e < M * (N - 12); e += MS_T) {
+                const int r = e / (N - 12), j = 12 + (e - r * (N - 12));
+                const int a0 = 12 + 6 * ((r >> 1) % k);
+                double sacc = 0.0;
+#pragma unroll
+                for (int u = 0; u < 6; ++u) sacc = fma(Hb[r * 6 + u], Psym(a0 + u, j), sacc);
+                RQ[r * ME_HS + j] = sacc;
+            }
+            __syncthreads();
+            for (int e = tid; e < M * (M + 1) / 2; e += MS_T) {
+                int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                r += (tri(r + 1, 0) <= e) - (tri(r, 0) > e);
+                const int c = e - tri(r, 0);
+                const int a1 = 12 + 6 * ((c >> 1) % k);
+                double sacc = __ldg(a.R + r * M + c);
+#pragma unroll
+                for (int v = 0; v < 6; ++v) sacc = fma(RQ[r * ME_HS + a1 + v], Hb[c * 6 + v], sacc);
+                RS[e] = sacc;
+            }
+            __syncthreads();
+            chol_blocked(RS, M, flags, invd);
+            if (!flags[0]) {
+                if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
+                continue;
+            }
+            // W = L^-1, packed lower in RQ, one column per thread (4 partial sums shorten the dependent chain)
+            if (tid < M) {
+                const int c = tid;
+                for (int i = c; i < M; ++i) {
+                    double s0 = i == c ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    const double *Li = RS + tri(i, 0);
+                    int p = c;
+                    for (; p + 3 < i; p += 4) {
+                        s0 = fma(-Li[p], RQ[tri(p, c)], s0);
+                        s1 = fma(-Li[p + 1], RQ[tri(p + 1, c)], s1);
+                        s2 = fma(-Li[p + 2], RQ[tri(p + 2, c)], s2);
+                        s3 = fma(-Li[p + 3], RQ[tri(p + 3, c)], s3);
+                    }
+                    for (; p < i; ++p) s0 = fma(-Li[p], RQ[tri(p, c)], s0);
+                    RQ[tri(i, c)] = ((s0 + s1) + (s2 + s3)) * invd[i];
+                }
+            }
+            __syncthreads();
+            // 2x2 diagonal blocks of the information matrix: info_f = W[:, 2f:2f+2]^T W[:, 2f:2f+2]
+            bool rej = false;
+            if (tid < NF) {
+                const int ia = 2 * tid, ib = ia + 1;
+                double i00 = 0.0, i10 = 0.0, i11 = 0.0;
+                {
+                    const double wa = RQ[tri(ia, ia)];
+                    i00 = wa * wa;
+                }
+                for (int r = ib; r < M; ++r) {
+                    const double wa = RQ[tri(r, ia)], wb = RQ[tri(r, ib)];
+                    i00 = fma(wa, wa, i00);
+                    i10 = fma(wa, wb, i10);
+                    i11 = fma(wb, wb, i11);
+                }
+                info[3 * tid] = i00; info[3 * tid + 1] = i10; info[3 * tid + 2] = i11;
+                const double v0 = nu[ia], v1 = nu[ib];
+                const double m2 = v0 * (i00 * v0 + i10 * v1) + v1 * (i10 * v0 + i11 * v1);
+                rej = !(m2 < 5.99);
+            }
+            // while nothing is rejected the sequential scan keeps the identity indexing: "all accepted" needs no scan
+            if (__syncthreads_or(rej) && tid == 0) {
+                int len = M, out = 0, i = 0;
+                for (int e = 0; e < M; ++e) kept[e] = e;
+                while (i < len / 2) {
+                    const double v0 = nu[kept[2 * i]], v1 = nu[kept[2 * i + 1]];
+                    const double i00 = info[3 * i], i10 = info[3 * i + 1], i11 = info[3 * i + 2];  // position, not feature (:773)
+                    const double m2 = v0 * (i00 * v0 + i10 * v1) + v1 * (i10 * v0 + i11 * v1);
+                    if (!(m2 < 5.99)) {
+                        for (int pass = 0; pass < 2; ++pass) {  // removeRow(2i); removeRow(2i+1): not re-based (Q6)
+                            const int pos = 2 * i + pass, num = len - 1;
+                            if (pos < num)
+                                for (int e = pos; e < num; ++e) kept[e] = kept[e + 1];
+                            len = num;
+                        }
+                        ++out;
+                    } else {
+                        ++i;
+                    }
+                }
+                flags[1] = len;
+                flags[2] = out;
+            }
+            __syncthreads();
+            mk = flags[1];
+        }
+        if (tid == 0) a.outliers[inst] = flags[2];
+        if (mk <= 0) continue;  // :322 nothing left
+        if (mk < N) {           // :808 R.block(0,0,N,N) needs rows >= DOF
+            if (tid == 0) a.status[inst] |= SLB_ST_QR_ROWS;
+            continue;
+        }
+        const bool compact = mk < M;
+        // ---- compacted H -> RQ, compacted innovation -------------------------------------------------------------
+        for (int e = tid; e < mk * N; e += MS_T) {
+            const int r = e / N, c = e - r * N;
+            RQ[r * ME_HS + c] = RH[(compact ? kept[r] : r) * ME_HS + c];
+        }
+        if (tid < mk) wv[tid] = nu[compact ? kept[tid] : tid];
+        __syncthreads();
+        if (tid < mk) nu[tid] = wv[tid];
+        __syncthreads();
+        // ---- reduceDimension (:794-816): Householder QR of RQ (mk x N) in place; Q^T is applied to nu on the way ------
+        for (int kk = 0; kk < N; ++kk) {
+            if (warp == 0) {
+                double t = 0.0;
+                for (int i = kk + 1 + lane; i < mk; i += 32) {
+                    const double v = RQ[i * ME_HS + kk];
+                    t = fma(v, v, t);
+                }
+                t = warp_sum(t);
+                if (lane == 0) {
+                    const double c0 = RQ[kk * ME_HS + kk];
+                    if (t <= 2.2250738585072014e-308) {
+                        scal[0] = 0.0;  // tau
+                        scal[1] = 0.0;  // 1 / (c0 - beta)
+                        scal[2] = c0;   // beta
+                    } else {
+                        double beta = sqrt(fma(c0, c0, t));
+                        if (c0 >= 0.0) beta = -beta;
+                        scal[0] = (beta - c0) / beta;
+                        scal[1] = 1.0 / (c0 - beta);
+                        scal[2] = beta;
+                    }
+                    tau[kk] = scal[0];
+                }
+            }
+            __syncthreads();
+            const double tk = scal[0], sc = scal[1];
+            if (tk != 0.0) {
+                // essential part v = tail / (c0 - beta) is formed on the fly: column kk itself is rewritten last
+                const int j = kk + 1 + tid;  // columns kk+1 .. N-1, and the innovation as column N
+                if (j <= N) {
+                    double *col = j < N ? RQ + j : nu;
+                    const int cs = j < N ? ME_HS : 1;
+                    double t0 = col[kk * cs], t1 = 0.0;
+                    int i = kk + 1;
+                    for (; i + 1 < mk; i += 2) {
+                        t0 = fma(RQ[i * ME_HS + kk] * sc, col[i * cs], t0);
+                        t1 = fma(RQ[(i + 1) * ME_HS + kk] * sc, col[(i + 1) * cs], t1);
+                    }
+                    if (i < mk) t0 = fma(RQ[i * ME_HS + kk] * sc, col[i * cs], t0);
+                    const double tt = tk * (t0 + t1);
+                    col[kk * cs] -= tt;
+                    for (i = kk + 1; i < mk; ++i) col[i * cs] = fma(-tt, RQ[i * ME_HS + kk] * sc, col[i * cs]);
+                }
+                __syncthreads();
+                for (int i = kk + 1 + tid; i < mk; i += MS_T) RQ[i * ME_HS + kk] *= sc;
+            } else {
+                __syncthreads();
+                for (int i = kk + 1 + tid; i < mk; i += MS_T) RQ[i * ME_HS + kk] = 0.0;
+            }
+            if (tid == 0) RQ[kk * ME_HS + kk] = scal[2];
+            __syncthreads();
+        }
+        // ---- thin Q = householderQ() * Identity(mk, N) into RH (:802-803): reflectors last to first; column j < kk of
+        //      the partial product is still e_j, which reflector kk leaves alone ------------------------------------------
+        for (int e = tid; e < mk * ME_HS; e += MS_T) {
+            const int r = e / ME_HS, c = e - r * ME_HS;
+            RH[e] = (r == c && c < N) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        for (int kk = N - 1; kk >= 0; --kk) {
+            const double tk = tau[kk];
+            if (tk != 0.0) {
+                const int j = kk + tid;
+                if (j < N) {
+                    double t0 = RH[kk * ME_HS + j], t1 = 0.0;
+                    int i = kk + 1;
+                    for (; i + 1 < mk; i += 2) {
+                        t0 = fma(RQ[i * ME_HS + kk], RH[i * ME_HS + j], t0);
+                        t1 = fma(RQ[(i + 1) * ME_HS + kk], RH[(i + 1) * ME_HS + j], t1);
+                    }
+                    if (i < mk) t0 = fma(RQ[i * ME_HS + kk], RH[i * ME_HS + j], t0);
+                    const double tt = tk * (t0 + t1);
+                    RH[kk * ME_HS + j] -= tt;
+                    for (i = kk + 1; i < mk; ++i) RH[i * ME_HS + j] = fma(-tt, RQ[i * ME_HS + kk], RH[i * ME_HS + j]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- Rr = Q^T R' Q (:814) into RS (packed lower), 8 columns of Q at a time --------------------------------
+        for (int b0 = 0; b0 < N; b0 += 8) {
+            for (int e = tid; e < mk * 8; e += MS_T) {
+                const int i = e >> 3, b = e & 7;
+                const double *Rrow = a.R + (size_t)(compact ? kept[i] : i) * M;
+                double sacc = 0.0;
+                if (b0 + b < N)
+                    for (int j = 0; j < mk; ++j) sacc = fma(__ldg(Rrow + (compact ? kept[j] : j)), RH[j * ME_HS + b0 + b], sacc);
+                T3[e] = sacc;
+            }
+            __syncthreads();
+            for (int e = tid; e < N * 8; e += MS_T) {
+                const int r = e >> 3, c = b0 + (e & 7);
+                if (c < N && c <= r) {
+                    double sacc = 0.0;
+                    for (int i = 0; i < mk; ++i) sacc = fma(RH[i * ME_HS + r], T3[i * 8 + (e & 7)], sacc);
+                    RS[tri(r, c)] = sacc;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- covXZ = P Hr^T (N x N, row = state) into RH; Hr = upper triangle of RQ rows 0..N-1 (:808) --------------
+        for (int e = tid; e < N * N; e += MS_T) {
+            const int i = e / N, j = e - i * N;  // covXZ[j][i] = sum_{l >= i} Hr[i][l] P(l, j); a warp shares i (broadcast Hr)
+            double sacc = 0.0;
+            for (int l = i; l < N; ++l) sacc = fma(RQ[i * ME_HS + l], Psym(l, j), sacc);
+            RH[j * ME_HS + i] = sacc;
+        }
+        __syncthreads();
+        // ---- S = Hr covXZ + Rr (:330), packed lower in RS ---------------------------------------------------------
+        for (int e = tid; e < NP; e += MS_T) {
+            int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+            r += (tri(r + 1, 0) <= e) - (tri(r, 0) > e);
+            const int c = e - tri(r, 0);
+            double sacc = RS[e];
+            for (int l = r; l < N; ++l) sacc = fma(RQ[r * ME_HS + l], RH[l * ME_HS + c], sacc);
+            RS[e] = sacc;
+        }
+        __syncthreads();
+        chol_blocked(RS, N, flags, invd);
+        if (!flags[0]) {
+            if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
+            continue;
+        }
+        // ---- Y = covXZ Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates --------------
+        for (int p0 = 0; p0 < N; p0 += 8) {
+            const int pb = min(8, N - p0);
+            for (int i = tid; i < N; i += MS_T) {
+                double *row = RH + i * ME_HS + p0;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < pb) {
+                        double sv = row[c];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q < c) sv = fma(-x[q], RS[tri(p0 + c, p0 + q)], sv);
+                        x[c] = sv * invd[p0 + c];
+                        row[c] = x[c];
+                    }
+                }
+            }
+            __syncthreads();
+            const int j0 = p0 + pb, nct = (N - j0 + 7) >> 3;
+            for (int t = warp; t < nrt * nct; t += MS_W) {
+                const int tr = t / nct, tc = t - tr * nct;
+                const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < 8; k0 += 4) {
+                    const int kq = k0 + fk;
+                    const double av = (ai < N && kq < pb) ? RH[ai * ME_HS + p0 + kq] : 0.0;
+                    const double bv = (bj < N && kq < pb) ? RS[tri(bj, p0 + kq)] : 0.0;
+                    dmma884(d0, d1, av, bv);
+                }
+                const int oc = j0 + 8 * tc + 2 * fk;
+                if (ai < N) {
+                    if (oc < N) RH[ai * ME_HS + oc] -= d0;
+                    if (oc + 1 < N) RH[ai * ME_HS + oc + 1] -= d1;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- w = Ls^-1 nu' (warp 0), delta = Y w (:337) ----------------------------------------------------------
+        if (warp == 0) {
+            for (int q = 0; q < N; ++q) {
+                const double wq = nu[q] * invd[q];
+                __syncwarp();
+                if (lane == 0) wv[q] = wq;
+                for (int c = q + 1 + lane; c < N; c += 32) nu[c] -= RS[tri(c, q)] * wq;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = warp; i < N; i += MS_W) {
+            double sacc = 0.0;
+            for (int q = lane; q < N; q += 32) sacc += RH[i * ME_HS + q] * wv[q];
+            sacc = warp_sum(sacc);
+            if (lane == 0) dl[i] = sacc;
+        }
+        // ---- Pk -= K S K^T = Y Y^T (:336) straight to the HBM record: lower 8x8 tiles, K = N -----------------------
+        {
+            const int ntiles = nrt * (nrt + 1) / 2;
+            for (int t = warp; t < ntiles; t += MS_W) {
+                int tr, tc;
+                tri_tile(t, tr, tc);
+                const int ai = 8 * tr + fr, bj = 8 * tc + fr;
+                double d0 = 0.0, d1 = 0.0;
+                for (int k0 = 0; k0 < N; k0 += 4) {
+                    const int kq = k0 + fk;
+                    const double av = (ai < N && kq < N) ? RH[ai * ME_HS + kq] : 0.0;
+                    const double bv = (bj < N && kq < N) ? RH[bj * ME_HS + kq] : 0.0;
+                    dmma884(d0, d1, av, bv);
+                }
+                const int r = ai, c = 8 * tc + 2 * fk;
+                if (r < N) {
+                    if (c <= r) Pg[tri(r, c)] = RA[tri(r, c)] - d0;
+                    if (c + 1 <= r) Pg[tri(r, c + 1)] = RA[tri(r, c + 1)] - d1;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- mu = mu [+] K nu (:337), thread per block --------------------------------------------------------------
+        bool finite = true;
+        if (tid < NB) {
+            const int b = tid, qo = ms_qoff(b);
+            const double d[3] = {dl[3 * b], dl[3 * b + 1], dl[3 * b + 2]};
+            if (ms_so3(b)) {
+                double e[4], q[4];
+                so3_exp(d, 1.0, e);
+                quat_mul(mu + qo, e, q);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { mug[qo + c] = q[c]; finite = finite && isfinite(q[c]); }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double o = mu[qo + c] + d[c];
+                    mug[qo + c] = o;
+                    finite = finite && isfinite(o);
+                }
+            }
+        }
+        if (!finite) atomicOr(a.status + inst, SLB_ST_NONFINITE);
+    }
+}
+
 }  // namespace slbd
 
 namespace slb {
@@ -571,6 +985,22 @@ int launch_msckf_update(int mm, const FilterArgs &a, cudaStream_t s) {
     SLB_CUDA(cudaFuncSetAttribute(slbd::msckf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.B < sms ? a.B : sms;  // one persistent CTA per SM
     slbd::msckf_update_kernel<<<grid, slbd::MS_T, smem, s>>>(a);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+int launch_msckf_update_ekf(int mm, const FilterArgs &a, cudaStream_t s) {
+    if (mm != SLB_MM_MSCKF_REPROJ) return set_error(SLB_ERR_INVALID, "msckf: unsupported measurement model");
+    if (a.k < 1 || a.k > 10 || a.m > slbd::MS_MMAX || a.m < 2 || (a.m & 1))
+        return set_error(SLB_ERR_INVALID, "msckf EKF update: needs 1..10 clones and an even 2 <= m <= 100");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = (size_t)slbd::ME_SMEM_DOUBLES * sizeof(double);
+    SLB_CUDA(cudaFuncSetAttribute(slbd::msckf_ekf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = a.B < sms ? a.B : sms;  // one persistent CTA per SM
+    slbd::msckf_ekf_update_kernel<<<grid, slbd::MS_T, smem, s>>>(a);
     count_launch();
     SLB_CUDA(cudaGetLastError());
     return SLB_OK;

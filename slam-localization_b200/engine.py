@@ -19,7 +19,7 @@ PM_UKFOM_IMU, PM_UKFOM_IMU_REFBUG, PM_POSE6_ODOM, PM_USCKF_TEST, PM_MSCKF_DELTAP
 MM_GPS_POS, MM_USCKF_VO, MM_MSCKF_REPROJ = 101, 102, 103
 STATEK, STATEK_L, STATEK_I = 1, 2, 3
 FIELD_MU, FIELD_P, FIELD_STATUS, FIELD_OUTLIERS = 1, 2, 3, 4
-ST_CHOL_FAIL, ST_MEAN_NOCONV, ST_GATE_REJECT, ST_NONFINITE = 1, 2, 4, 8
+ST_CHOL_FAIL, ST_MEAN_NOCONV, ST_GATE_REJECT, ST_NONFINITE, ST_QR_ROWS = 1, 2, 4, 8, 16
 
 EXPORTS = [
     "slb_version", "slb_last_error", "slb_create", "slb_destroy", "slb_dof", "slb_qdim", "slb_upload",
@@ -29,7 +29,7 @@ EXPORTS = [
     "slb_datamodel_addsub", "slb_datamodel_fuse_host", "slb_status", "slb_clear_status", "slb_ensemble_stats",
     "slb_launch_count", "slb_bench_fp64_peak", "slb_replicate", "slb_dev_alloc", "slb_dev_free", "slb_dev_copy",
     "slb_msckf_step_host", "slb_ekf_predict", "slb_ekf_update", "slb_ekf_single_update", "slb_ekf_clone",
-    "slb_datamodel_safe_fuse", "slb_transform_compose", "slb_deadreckon_update_pose",
+    "slb_datamodel_safe_fuse", "slb_msckf_update_ekf", "slb_transform_compose", "slb_deadreckon_update_pose",
 ]
 
 
@@ -75,6 +75,7 @@ def lib():
         L.slb_usckf_set_measurement.argtypes = [vp, i32, dp, dp, vp]
         L.slb_msckf_predict.argtypes = [vp, i32, dp, dbl, dp, vp]
         L.slb_msckf_update.argtypes = [vp, i32, dp, i32, dp, dp, i32, vp]
+        L.slb_msckf_update_ekf.argtypes = [vp, i32, dp, i32, dp, dp, i32, vp]
         L.slb_msckf_step_host.argtypes = [vp, i32, i32, dp, dbl, dp, dp, i32, i32, dp, dp, i32, dp, vp]
         L.slb_datamodel_fuse.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp, vp]
         L.slb_datamodel_addsub.argtypes = [i32, i64, i32, dp, dp, dp, dp, dp, dp, vp]
@@ -293,6 +294,12 @@ class Msckf(Batch):
         params, z, R = dev(params), dev(z), dev(R)
         m = z.t.shape[1]
         check(lib().slb_msckf_update(self.h, mm, params.ptr, m, z.ptr, R.ptr, int(gate), _stream()))
+
+    def update_ekf(self, mm, params, z, R, gate=True):
+        """update(z, h, H, R[, mt]) -- the EKF flavour with QR compression (Msckf.hpp:285-349)."""
+        params, z, R = dev(params), dev(z), dev(R)
+        m = z.t.shape[1]
+        check(lib().slb_msckf_update_ekf(self.h, mm, params.ptr, m, z.ptr, R.ptr, int(gate), _stream()))
 
     def step_host(self, pm, mm, u, dt, Q, params, z, R, gate=True, mu_out=None):
         """predict + update with HOST arrays (numpy or pinned torch); fills the posterior means."""

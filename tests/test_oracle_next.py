@@ -191,3 +191,68 @@ def test_dead_reckon_update_pose(slo):
     post2, pcov2, _, _ = slo.dr_update_pose(sc["dt"], sc["vel0"], sc["vel1"], sc["velcov"], sc["prev_pose"], sc["prev_cov"], nthreads=4)
     np.testing.assert_array_equal(post, post2)
     np.testing.assert_array_equal(pcov, pcov2)
+
+
+# ---- f1: Msckf::update, EKF flavour with QR compression (Msckf.hpp:297-349,756-816) -------------------------------
+MS_BLOCKS = [0, 1, 0, 0] + [0, 1] * 10
+
+
+def test_householder_qr_restatement(slo):
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(40, 12))
+    A[:, 3] = 0.0                                         # a zero column: tau = 0, R(3,3) = 0 (Eigen's convention)
+    QR, tau, Q = slo.householder_qr(A)
+    R = np.triu(QR)[:12]
+    np.testing.assert_allclose(Q @ R, A, atol=1e-13)
+    np.testing.assert_allclose(Q.T @ Q, np.eye(12), atol=1e-14)
+    assert tau[3] != 0.0 or R[3, 3] == 0.0
+    # sign convention: beta = -sign(c0) |x|
+    QR2, tau2, _ = slo.householder_qr(np.array([[3.0], [4.0]]))
+    assert QR2[0, 0] == -5.0 and abs(tau2[0] - 1.6) < 1e-15
+
+
+def test_reproj_jacobian_matches_finite_differences(slo):
+    sc = synth.msckf_scenario(2, seed=1, k=10, nfeat=50)
+    z, H = slo.msckf_reproj_jac(10, sc["mu"][0], sc["landmarks"])
+    Hn = np.zeros_like(H)
+    for c in range(72):
+        d = np.zeros(72)
+        d[c] = 1e-6
+        zp, _ = slo.msckf_reproj_jac(10, slo.boxplus(MS_BLOCKS, sc["mu"][0], d), sc["landmarks"])
+        zm, _ = slo.msckf_reproj_jac(10, slo.boxplus(MS_BLOCKS, sc["mu"][0], -d), sc["landmarks"])
+        Hn[:, c] = (zp - zm) / 2e-6
+    assert np.abs(H - Hn).max() < 1e-8
+    assert not H[:, :12].any()                          # statek is not observed by this model
+
+
+def test_msckf_ekf_update_equals_plain_kalman_update_without_outliers(slo):
+    """With R = sigma^2 I the QR compression is lossless: the update equals K = P H^T (H P H^T + R)^-1 on the
+    uncompressed rows (the discarded rows are orthogonal to range(H) and uncorrelated with the kept ones)."""
+    sc = synth.msckf_scenario(6, seed=3, k=10, nfeat=50)
+    mu, P, out, st = slo.msckf_update_ekf(slo.MM_MSCKF_REPROJ, 10, sc["mu"], sc["P"], sc["landmarks"], sc["z"], sc["R"], gate=False)
+    assert not out.any() and not st.any()
+    for i in range(6):
+        z, H = slo.msckf_reproj_jac(10, sc["mu"][i], sc["landmarks"])
+        P0 = sc["P"][i]
+        S = H @ P0 @ H.T + sc["R"]
+        K = P0 @ H.T @ np.linalg.inv(S)
+        np.testing.assert_allclose(P[i], P0 - K @ S @ K.T, rtol=1e-8, atol=1e-14)
+        np.testing.assert_allclose(mu[i], slo.boxplus(MS_BLOCKS, sc["mu"][i], K @ (sc["z"][i] - z)), rtol=1e-9, atol=1e-12)
+
+
+def test_msckf_ekf_update_outliers_and_row_shortage(slo):
+    sc = synth.msckf_scenario(16, seed=2, k=10, nfeat=50, outlier_frac=0.1)
+    mu, P, out, st = slo.msckf_update_ekf(slo.MM_MSCKF_REPROJ, 10, sc["mu"], sc["P"], sc["landmarks"], sc["z"], sc["R"], gate=True)
+    assert out.max() >= 15 and (st == 16).any() and (st == 0).any()
+    # fewer than DOF rows left: reduceDimension cannot run (Msckf.hpp:808) -> flagged and left unchanged
+    short = st == 16
+    assert np.all(2 * (50 - out[short]) + out[short] * 0 < 72 + 2 * out[short])   # each outlier removes two rows
+    np.testing.assert_array_equal(mu[short], sc["mu"][short])
+    np.testing.assert_array_equal(P[short], sc["P"][short])
+    ok = st == 0
+    assert np.linalg.eigvalsh(P[ok]).min() > 0
+    # threads do not change results
+    mu2, P2, out2, st2 = slo.msckf_update_ekf(slo.MM_MSCKF_REPROJ, 10, sc["mu"], sc["P"], sc["landmarks"], sc["z"], sc["R"],
+                                              gate=True, nthreads=4)
+    np.testing.assert_array_equal(mu, mu2)
+    np.testing.assert_array_equal(out, out2)
