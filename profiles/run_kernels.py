@@ -54,4 +54,15 @@ if "msckf" in which:
         f.predict(engine.PM_MSCKF_DELTAPOSE, u, 0.0, Q)
         f.update(engine.MM_MSCKF_REPROJ, lm, z, R)
     torch.cuda.synchronize()
+if "msckf_ekf" in which:
+    B = 2048
+    sc = synth.msckf_scenario(256, seed=3)
+    f = engine.Msckf(B, nclones=10)
+    f.set_state(sc["mu"], sc["P"], replicate=True)
+    rep = B // 256
+    z = engine.DeviceArray(np.tile(sc["z"], (rep, 1)))
+    R, lm = engine.DeviceArray(sc["R"]), engine.DeviceArray(sc["landmarks"])
+    for _ in range(2):
+        f.update_ekf(engine.MM_MSCKF_REPROJ, lm, z, R)
+    torch.cuda.synchronize()
 print("ok")

@@ -201,6 +201,7 @@ static FilterArgs make_args(slb_handle h) {
     a.mu = h->mu; a.P = h->P; a.status = h->status; a.outliers = h->outliers;
     a.B = h->B; a.stride = h->stride; a.pstride = h->pstride; a.qstride = h->qstride;
     a.nk = h->cfg.nk; a.nl = h->cfg.nl; a.k = h->cfg.nclones;
+    a.misc = h->misc_dev;
     return a;
 }
 
@@ -282,6 +283,7 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->stage, h->stage_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->shared_small, 128 * 1024);
     if (e == cudaSuccess) e = cudaMalloc(&h->counts_dev, 4 * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&h->misc_dev, 16 * sizeof(int32_t));
     for (int i = 0; i < SLB_NXS && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&h->xs[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
@@ -302,7 +304,7 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
 int slb_destroy(slb_handle h) {
     if (!h) return SLB_OK;
     cudaFree(h->mu); cudaFree(h->P); cudaFree(h->status); cudaFree(h->outliers);
-    cudaFree(h->stage); cudaFree(h->shared_small); cudaFree(h->counts_dev);
+    cudaFree(h->stage); cudaFree(h->shared_small); cudaFree(h->counts_dev); cudaFree(h->misc_dev);
     for (int i = 0; i < SLB_NXS; ++i) {
         if (h->xs[i]) cudaStreamDestroy(h->xs[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);

@@ -23,6 +23,13 @@ namespace slbd {
 constexpr int EKF_NS = 15, EKF_NA = 45, EKF_QS = 16, EKF_QA = 48;
 constexpr unsigned EKF_FULL = 0xffffffffu;
 
+// 8-byte LDGSTS: the loads of a record are all issued before the first one lands (instance records are only 8-byte
+// aligned -- 2025 doubles -- so the 16-byte form does not apply); one wait for the lot.
+SLB_DEV void ekf_cp8(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+SLB_DEV void ekf_cp_wait() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory"); }
+
 // closed-form inverse of a general 3x3 (Eigen's fixed-size path: cofactors / determinant)
 SLB_DEV void inv3(const double *A, double *C) {
     auto a = [&](int i, int j) { return A[i * 3 + j]; };
@@ -43,19 +50,21 @@ SLB_DEV void inv3(const double *A, double *C) {
 // block row i = rows 30..44:  [P_ik P_il P_ii] <- F [P_ik P_il P_ii],  P_ii <- (F P_ii) F^T + Q,  columns 30..44 of
 // rows 0..29 by symmetry (the reference updates P_ki = P_ki F^T separately, :109-116: the same numbers for a
 // symmetric Pk_error).
-constexpr int EKP_SM = 15 * 16 + 15 * 46 + 15 * 46;  // F (row stride 16) | block row (stride 46) | result (stride 46)
+constexpr int EKP_FS = 17;  // odd row stride of F: the Y_ii F^T product reads 15 different rows of F at once
+constexpr int EKP_SM = 15 * EKP_FS + 1 + 15 * 46 + 15 * 46;  // F | block row (stride 46) | result (stride 46)
 template <int WPB>
 __global__ void __launch_bounds__(WPB * 32) ekf_predict_kernel(int64_t n, double *err, double *P, const double *F, const double *Q) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t inst = (int64_t)blockIdx.x * WPB + w;
     if (inst >= n) return;
-    double *Fs = sm + (size_t)w * EKP_SM, *Rs = Fs + 15 * 16, *Ys = Rs + 15 * 46;
+    double *Fs = sm + (size_t)w * EKP_SM, *Rs = Fs + 15 * EKP_FS + 1, *Ys = Rs + 15 * 46;
     double *Pg = P + inst * (EKF_NA * EKF_NA);
     const double *Fg = F + inst * (EKF_NS * EKF_NS);
-    for (int e = lane; e < 225; e += 32) Fs[(e / 15) * 16 + e % 15] = Fg[e];
-    for (int e = lane; e < 675; e += 32) Rs[(e / 45) * 46 + e % 45] = Pg[30 * 45 + e];
+    for (int e = lane; e < 225; e += 32) ekf_cp8(Fs + (e / 15) * EKP_FS + e % 15, Fg + e);
+    for (int e = lane; e < 675; e += 32) ekf_cp8(Rs + (e / 45) * 46 + e % 45, Pg + 30 * 45 + e);
     double ei = lane < 15 ? err[inst * EKF_NA + 30 + lane] : 0.0;
+    ekf_cp_wait();
     __syncwarp();
     // mu_error.statek_i <- F mu_error.statek_i (:93)
     {
@@ -63,7 +72,7 @@ __global__ void __launch_bounds__(WPB * 32) ekf_predict_kernel(int64_t n, double
 #pragma unroll
         for (int k = 0; k < 15; ++k) {
             const double ek = __shfl_sync(EKF_FULL, ei, k);
-            if (lane < 15) s += Fs[lane * 16 + k] * ek;
+            if (lane < 15) s += Fs[lane * EKP_FS + k] * ek;
         }
         if (lane < 15) err[inst * EKF_NA + 30 + lane] = s;
     }
@@ -79,7 +88,7 @@ __global__ void __launch_bounds__(WPB * 32) ekf_predict_kernel(int64_t n, double
             for (int r = 0; r < 15; ++r) {  // rolled: unrolled, ptxas hoists all 225 F entries into registers and spills
                 double s = 0.0;
 #pragma unroll
-                for (int k = 0; k < 15; ++k) s += Fs[r * 16 + k] * col[k];
+                for (int k = 0; k < 15; ++k) s += Fs[r * EKP_FS + k] * col[k];
                 Ys[r * 46 + c] = s;
             }
         }
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(WPB * 32) ekf_predict_kernel(int64_t n, double
         const int r = e / 15, c = e - r * 15;
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 15; ++k) s += Ys[r * 46 + 30 + k] * Fs[c * 16 + k];
+        for (int k = 0; k < 15; ++k) s += Ys[r * 46 + 30 + k] * Fs[c * EKP_FS + k];
         Rs[r * 46 + 30 + c] = s + __ldg(Q + e);
     }
     __syncwarp();
@@ -238,13 +247,14 @@ __global__ void __launch_bounds__(WPB * 32) ekf_update_kernel(int64_t n, const d
     double *Pl = sm + (size_t)w * (C::SM + N + 1) , *rows = Pl + C::NP, *Hs = rows + N * C::ROW, *xh = sm + (size_t)w * (C::SM + N + 1) + C::SM;
     double *Pg = P + inst * (N * N);
     for (int i = 0; i < N; ++i)
-        for (int j = lane; j <= i; j += 32) Pl[tri(i, j)] = Pg[i * N + j];
+        for (int j = lane; j <= i; j += 32) ekf_cp8(Pl + tri(i, j), Pg + i * N + j);
     for (int e = lane; e < M * N; e += 32) Hs[e] = __ldg(H + e);
     // x_hat = mu_state vectorised with the error-quaternion convention (:331)
     for (int e = lane; e < N; e += 32) {
         const int s = e / EKF_NS, c = e - s * EKF_NS;
         xh[e] = mu[inst * EKF_QA + s * EKF_QS + (c < 6 ? c : c + 1)];
     }
+    ekf_cp_wait();
     __syncwarp();
     double innov[M];
     const bool ok = joseph_update<N, M>(Pl, rows, Hs, xh, z + inst * M, R, gate, lane, innov);
@@ -274,10 +284,11 @@ __global__ void __launch_bounds__(WPB * 32) ekf_single_update_kernel(int64_t n, 
     double *Pg = P + inst * (EKF_NA * EKF_NA);
     for (int e = lane; e < N * N; e += 32) {
         const int i = e / N, j = e - i * N;
-        if (j <= i) Pl[tri(i, j)] = Pg[(30 + i) * EKF_NA + 30 + j];
+        if (j <= i) ekf_cp8(Pl + tri(i, j), Pg + (30 + i) * EKF_NA + 30 + j);
     }
     for (int e = lane; e < M * N; e += 32) Hs[e] = __ldg(H + e);
     if (lane < N) xk[lane] = err[inst * EKF_NA + 30 + lane];
+    ekf_cp_wait();
     __syncwarp();
     double innov[M];
     const bool ok = joseph_update<N, M>(Pl, rows, Hs, xk, z + inst * M, R, gate, lane, innov);

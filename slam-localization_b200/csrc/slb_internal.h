@@ -25,6 +25,7 @@ struct slb_batch_s {
     size_t stage_bytes;
     double *shared_small; // device copy of Q / R / params passed from host pointers
     int64_t *counts_dev;  // 4 counters for slb_status
+    int32_t *misc_dev;    // 16 ints of per-launch scratch flags (e.g. "R is diagonal" for the MSCKF EKF update)
     cudaStream_t xs[SLB_NXS];  // chunk ring of the *_step_host entry points
     cudaEvent_t ev_start, ev_done[SLB_NXS];
 };
@@ -56,6 +57,7 @@ struct FilterArgs {
     int m;
     int gate;
     int nk, nl, k;
+    int32_t *misc;
 };
 
 // slb_ukf.cu

@@ -558,6 +558,19 @@ constexpr int ME_RA = 2632, ME_RS = 5056, ME_RH = MS_MMAX * ME_HS, ME_RQ = MS_MM
 constexpr int ME_SMEM_DOUBLES = ME_RA + ME_RS + ME_RH + ME_RQ + ME_RD;
 static_assert(ME_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF EKF update working set exceeds shared memory");
 
+// flag[0] = 1 when the shared m x m measurement noise matrix is diagonal
+__global__ void msckf_rdiag_kernel(const double *R, int m, int32_t *flag) {
+    __shared__ int off;
+    if (threadIdx.x == 0) off = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x)
+        if (e / m != e % m && R[e] != 0.0) mine = 1;
+    if (mine) off = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) flag[0] = off ? 0 : 1;
+}
+
 __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterArgs a) {
     extern __shared__ __align__(16) double sm[];
     double *RA = sm, *RS = RA + ME_RA, *RH = RS + ME_RS, *RQ = RH + ME_RH, *RD = RQ + ME_RQ;
@@ -647,21 +660,25 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
                 continue;
             }
-            // W = L^-1, packed lower in RQ, one column per thread (4 partial sums shorten the dependent chain)
-            if (tid < M) {
-                const int c = tid;
-                for (int i = c; i < M; ++i) {
-                    double s0 = i == c ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                    const double *Li = RS + tri(i, 0);
-                    int p = c;
-                    for (; p + 3 < i; p += 4) {
-                        s0 = fma(-Li[p], RQ[tri(p, c)], s0);
-                        s1 = fma(-Li[p + 1], RQ[tri(p + 1, c)], s1);
-                        s2 = fma(-Li[p + 2], RQ[tri(p + 2, c)], s2);
-                        s3 = fma(-Li[p + 3], RQ[tri(p + 3, c)], s3);
+            // W = L^-1, packed lower in RQ: column c is a forward substitution; two lanes share a column (even / odd
+            // terms of the inner product, combined with one shuffle), two partial sums each shorten the dependent chain
+            {
+                const int c = tid >> 1, half = tid & 1;
+                for (int i = 0; i < M; ++i) {   // uniform trip count: the shuffle below needs every lane
+                    double s0 = 0.0, s1 = 0.0;
+                    if (c < M && i >= c) {
+                        const double *Li = RS + tri(i, 0);
+                        int p = c + half;
+                        for (; p + 2 < i; p += 4) {
+                            s0 = fma(-Li[p], RQ[tri(p, c)], s0);
+                            s1 = fma(-Li[p + 2], RQ[tri(p + 2, c)], s1);
+                        }
+                        for (; p < i; p += 2) s0 = fma(-Li[p], RQ[tri(p, c)], s0);
                     }
-                    for (; p < i; ++p) s0 = fma(-Li[p], RQ[tri(p, c)], s0);
-                    RQ[tri(i, c)] = ((s0 + s1) + (s2 + s3)) * invd[i];
+                    double sacc = s0 + s1;
+                    sacc += __shfl_xor_sync(FULL, sacc, 1);
+                    if (c < M && i >= c && half == 0) RQ[tri(i, c)] = ((i == c ? 1.0 : 0.0) + sacc) * invd[i];
+                    __syncwarp();
                 }
             }
             __syncthreads();
@@ -755,21 +772,30 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             __syncthreads();
             const double tk = scal[0], sc = scal[1];
             if (tk != 0.0) {
-                // essential part v = tail / (c0 - beta) is formed on the fly: column kk itself is rewritten last
-                const int j = kk + 1 + tid;  // columns kk+1 .. N-1, and the innovation as column N
-                if (j <= N) {
-                    double *col = j < N ? RQ + j : nu;
-                    const int cs = j < N ? ME_HS : 1;
-                    double t0 = col[kk * cs], t1 = 0.0;
-                    int i = kk + 1;
-                    for (; i + 1 < mk; i += 2) {
-                        t0 = fma(RQ[i * ME_HS + kk] * sc, col[i * cs], t0);
-                        t1 = fma(RQ[(i + 1) * ME_HS + kk] * sc, col[(i + 1) * cs], t1);
+                // essential part v = tail / (c0 - beta) is formed on the fly: column kk itself is rewritten last.
+                // Columns kk+1 .. N-1 and the innovation (as column N); three threads share a column (rows i = kk+1+part
+                // mod 3), partial dot products meet in T3.
+                const int part = tid / 80, jj = tid - part * 80, j = kk + 1 + jj;
+                const bool act = part < 3 && j <= N;
+                double *col = j < N ? RQ + j : nu;
+                const int cs = j < N ? ME_HS : 1;
+                if (act) {
+                    double t0 = 0.0, t1 = 0.0;
+                    int i = kk + 1 + part;
+                    for (; i + 3 < mk; i += 6) {
+                        t0 = fma(RQ[i * ME_HS + kk], col[i * cs], t0);
+                        t1 = fma(RQ[(i + 3) * ME_HS + kk], col[(i + 3) * cs], t1);
                     }
-                    if (i < mk) t0 = fma(RQ[i * ME_HS + kk] * sc, col[i * cs], t0);
-                    const double tt = tk * (t0 + t1);
-                    col[kk * cs] -= tt;
-                    for (i = kk + 1; i < mk; ++i) col[i * cs] = fma(-tt, RQ[i * ME_HS + kk] * sc, col[i * cs]);
+                    if (i < mk) t0 = fma(RQ[i * ME_HS + kk], col[i * cs], t0);
+                    T3[part * 80 + jj] = t0 + t1;
+                    if (part == 0) T3[240 + jj] = col[kk * cs];  // row kk is rewritten by part 0 below
+                }
+                __syncthreads();
+                if (act) {
+                    const double tt = tk * fma(sc, (T3[jj] + T3[80 + jj]) + T3[160 + jj], T3[240 + jj]);
+                    const double ts = tt * sc;
+                    for (int i = kk + 1 + part; i < mk; i += 3) col[i * cs] = fma(-ts, RQ[i * ME_HS + kk], col[i * cs]);
+                    if (part == 0) col[kk * cs] -= tt;
                 }
                 __syncthreads();
                 for (int i = kk + 1 + tid; i < mk; i += MS_T) RQ[i * ME_HS + kk] *= sc;
@@ -789,24 +815,49 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         __syncthreads();
         for (int kk = N - 1; kk >= 0; --kk) {
             const double tk = tau[kk];
-            if (tk != 0.0) {
-                const int j = kk + tid;
-                if (j < N) {
-                    double t0 = RH[kk * ME_HS + j], t1 = 0.0;
-                    int i = kk + 1;
-                    for (; i + 1 < mk; i += 2) {
+            if (tk != 0.0) {   // uniform
+                const int part = tid / 80, jj = tid - part * 80, j = kk + jj;
+                const bool act = part < 3 && j < N;
+                if (act) {
+                    double t0 = 0.0, t1 = 0.0;
+                    int i = kk + 1 + part;
+                    for (; i + 3 < mk; i += 6) {
                         t0 = fma(RQ[i * ME_HS + kk], RH[i * ME_HS + j], t0);
-                        t1 = fma(RQ[(i + 1) * ME_HS + kk], RH[(i + 1) * ME_HS + j], t1);
+                        t1 = fma(RQ[(i + 3) * ME_HS + kk], RH[(i + 3) * ME_HS + j], t1);
                     }
                     if (i < mk) t0 = fma(RQ[i * ME_HS + kk], RH[i * ME_HS + j], t0);
-                    const double tt = tk * (t0 + t1);
-                    RH[kk * ME_HS + j] -= tt;
-                    for (i = kk + 1; i < mk; ++i) RH[i * ME_HS + j] = fma(-tt, RQ[i * ME_HS + kk], RH[i * ME_HS + j]);
+                    T3[part * 80 + jj] = t0 + t1;
+                    if (part == 0) T3[240 + jj] = RH[kk * ME_HS + j];
                 }
+                __syncthreads();
+                if (act) {
+                    const double tt = tk * ((T3[jj] + T3[80 + jj]) + T3[160 + jj] + T3[240 + jj]);
+                    for (int i = kk + 1 + part; i < mk; i += 3) RH[i * ME_HS + j] = fma(-tt, RQ[i * ME_HS + kk], RH[i * ME_HS + j]);
+                    if (part == 0) RH[kk * ME_HS + j] -= tt;
+                }
+                __syncthreads();
+            }
+        }
+        // ---- Rr = Q^T R' Q (:814) into RS (packed lower).  A diagonal R (flagged once per launch by
+        //      msckf_rdiag_kernel) makes R' Q a row scaling: Rr = sum_i r_i q_i q_i^T -----------------------------------------
+        if (a.misc[0]) {
+            if (tid < mk) wv[tid] = __ldg(a.R + (size_t)(compact ? kept[tid] : tid) * (M + 1));
+            __syncthreads();
+            for (int e = tid; e < NP; e += MS_T) {
+                int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                r += (tri(r + 1, 0) <= e) - (tri(r, 0) > e);
+                const int c = e - tri(r, 0);
+                double s0 = 0.0, s1 = 0.0;
+                int i = 0;
+                for (; i + 1 < mk; i += 2) {
+                    s0 = fma(RH[i * ME_HS + r] * wv[i], RH[i * ME_HS + c], s0);
+                    s1 = fma(RH[(i + 1) * ME_HS + r] * wv[i + 1], RH[(i + 1) * ME_HS + c], s1);
+                }
+                if (i < mk) s0 = fma(RH[i * ME_HS + r] * wv[i], RH[i * ME_HS + c], s0);
+                RS[e] = s0 + s1;
             }
             __syncthreads();
-        }
-        // ---- Rr = Q^T R' Q (:814) into RS (packed lower), 8 columns of Q at a time --------------------------------
+        } else
         for (int b0 = 0; b0 < N; b0 += 8) {
             for (int e = tid; e < mk * 8; e += MS_T) {
                 const int i = e >> 3, b = e & 7;
@@ -1000,8 +1051,9 @@ int launch_msckf_update_ekf(int mm, const FilterArgs &a, cudaStream_t s) {
     const size_t smem = (size_t)slbd::ME_SMEM_DOUBLES * sizeof(double);
     SLB_CUDA(cudaFuncSetAttribute(slbd::msckf_ekf_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.B < sms ? a.B : sms;  // one persistent CTA per SM
+    slbd::msckf_rdiag_kernel<<<1, 256, 0, s>>>(a.R, a.m, a.misc);
     slbd::msckf_ekf_update_kernel<<<grid, slbd::MS_T, smem, s>>>(a);
-    count_launch();
+    count_launch(2);
     SLB_CUDA(cudaGetLastError());
     return SLB_OK;
 }
