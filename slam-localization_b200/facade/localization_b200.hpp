@@ -51,6 +51,26 @@ class DevBuf {
     const double *get() const { return static_cast<const double *>(p_); }
 };
 
+// RAII device buffer that is written by a kernel and read back
+class DevOut {
+    void *p_ = nullptr;
+    size_t n_ = 0;
+  public:
+    explicit DevOut(size_t n) : n_(n) { check(slb_dev_alloc(n * sizeof(double), &p_), "slb_dev_alloc"); }
+    DevOut(const Vec &init) : n_(init.size()) {
+        check(slb_dev_alloc(n_ * sizeof(double), &p_), "slb_dev_alloc");
+        check(slb_dev_copy(p_, init.data(), n_ * sizeof(double), 1, nullptr), "slb_dev_copy");
+    }
+    DevOut(const DevOut &) = delete;
+    DevOut &operator=(const DevOut &) = delete;
+    ~DevOut() { slb_dev_free(p_); }
+    double *get() { return static_cast<double *>(p_); }
+    void download(Vec &v) {
+        v.resize(n_);
+        check(slb_dev_copy(v.data(), p_, n_ * sizeof(double), 2, nullptr), "slb_dev_copy");
+    }
+};
+
 // Common part: the device-resident batch (mu_state / Pk of every instance, Usckf.hpp:77-78)
 class Batch {
   protected:
@@ -221,6 +241,16 @@ class Msckf : public Batch {
         check(slb_download(h_, SLB_FIELD_OUTLIERS, out.data(), out.size(), nullptr), "slb_download(outliers)");
         return out;
     }
+    // unsigned update(z, h, H, R[, mt]) (Msckf.hpp:285-349): the EKF flavour -- h also supplies its Jacobian H, outliers
+    // are removed on the information matrix (:756-792), (H, innovation, R) are QR-compressed (:794-816)
+    std::vector<int32_t> updateEKF(const Vec &z, int h, const Vec &params, const Vec &R, bool gate = true) {
+        const int m = (int)(z.size() / B_);
+        DevBuf dz(z), dp(params), dR(R);
+        check(slb_msckf_update_ekf(h_, h, dp.get(), m, dz.get(), dR.get(), gate ? 1 : 0, nullptr), "slb_msckf_update_ekf");
+        std::vector<int32_t> out(B_);
+        check(slb_download(h_, SLB_FIELD_OUTLIERS, out.data(), out.size(), nullptr), "slb_download(outliers)");
+        return out;
+    }
     Vec getPk() const { return Pk(); }                                                    // Msckf.hpp:386
     Vec muSingleState() const {                                                           // Msckf.hpp:356
         const Vec mu = muState();
@@ -259,6 +289,15 @@ struct DataModel {
         data.swap(xo);
         Cov.swap(Co);
     }
+    void safeFusion(const DataModel &o) {                                                    // :62-130 (D = 3, :104)
+        if (D != 3) throw Error(SLB_ERR_INVALID, "safeFusion is only defined for D = 3 (DataModel.hpp:104)");
+        DevBuf a(data), b(Cov), c(o.data), d(o.Cov);
+        DevOut xo(data.size()), Co(Cov.size());
+        check(slb_datamodel_safe_fuse((int64_t)n, a.get(), b.get(), c.get(), d.get(), xo.get(), Co.get(), nullptr),
+              "slb_datamodel_safe_fuse");
+        xo.download(data);
+        Co.download(Cov);
+    }
     DataModel operator+(const DataModel &o) const { return addsub(o, +1); }                  // :132-141
     DataModel operator-(const DataModel &o) const { return addsub(o, -1); }                  // :143-152 (Cov adds)
   private:
@@ -274,6 +313,85 @@ struct DataModel {
         slb_dev_free(xo);
         slb_dev_free(Co);
         check(rc, "slb_datamodel_addsub");
+        return r;
+    }
+};
+
+// ---- the error-state `Usckf` of src/filters/UsckfError.hpp over n instances -------------------
+// 3 x 15-DOF augmented state; mu_state as q-vectors (n x 48: per single state pos vel quat(w,x,y,z) gbias abias),
+// mu_error vectorised (n x 45), Pk_error dense (n x 45 x 45), all device-resident between calls.
+class UsckfError {
+    size_t n_;
+    DevOut mu_, err_, P_;
+  public:
+    UsckfError(const Vec &state, const Vec &error, const Vec &P0)                        // UsckfError.hpp:72-75
+        : n_(state.size() / 48), mu_(state), err_(error), P_(P0) {}
+    void ekfPredict(const Vec &F, const Vec &Q) {                                         // :87-137, F: n x 15 x 15
+        DevBuf dF(F), dQ(Q);
+        check(slb_ekf_predict((int64_t)n_, err_.get(), P_.get(), dF.get(), dQ.get(), nullptr), "slb_ekf_predict");
+    }
+    // ekfUpdate(z, H, R[, mt]) :322-384: returns the reference's return value per instance (zeros when accepted)
+    Vec ekfUpdate(const Vec &z, const Vec &H, const Vec &R, bool gate = true) {
+        const int m = (int)(z.size() / n_);
+        DevBuf dz(z), dH(H), dR(R);
+        DevOut ret(z.size());
+        void *acc = nullptr;
+        check(slb_dev_alloc(n_ * sizeof(int32_t), &acc), "slb_dev_alloc");
+        const int rc = slb_ekf_update((int64_t)n_, m, mu_.get(), P_.get(), dz.get(), dH.get(), dR.get(), gate ? 1 : 0, ret.get(),
+                                      (int32_t *)acc, nullptr);
+        slb_dev_free(acc);
+        check(rc, "slb_ekf_update");
+        Vec out;
+        ret.download(out);
+        return out;
+    }
+    void ekfSingleUpdate(const Vec &z, const Vec &H, const Vec &R, bool gate = true) {   // :489-571, H: m x 15
+        const int m = (int)(z.size() / n_);
+        DevBuf dz(z), dH(H), dR(R);
+        void *acc = nullptr;
+        check(slb_dev_alloc(n_ * sizeof(int32_t), &acc), "slb_dev_alloc");
+        const int rc = slb_ekf_single_update((int64_t)n_, m, mu_.get(), err_.get(), P_.get(), dz.get(), dH.get(), dR.get(),
+                                             gate ? 1 : 0, (int32_t *)acc, nullptr);
+        slb_dev_free(acc);
+        check(rc, "slb_ekf_single_update");
+    }
+    void cloning() { check(slb_ekf_clone((int64_t)n_, mu_.get(), err_.get(), P_.get(), nullptr), "slb_ekf_clone"); }  // :573-603
+    Vec muState() { Vec v; mu_.download(v); return v; }                                   // :606
+    Vec muError() { Vec v; err_.download(v); return v; }                                  // :611
+    Vec PkAugmentedState() { Vec v; P_.download(v); return v; }                           // :616
+};
+
+// ---- DeadReckon::updatePose with uncertainty over n poses (DeadReckon.hpp:30-79) ----------------
+// pose = pos(3) quat(w,x,y,z); covariance 6 x 6 over [r t]
+struct PoseWithUncertainty {
+    Vec pose, cov;  // n x 7, n x 6 x 6
+};
+struct DeadReckon {
+    // returns deltaPose; postPose = prevPose * deltaPose (TransformWithUncertainty::operator*, Transform.cpp:215-254)
+    static PoseWithUncertainty updatePose(double delta_t, const Vec &vel0, const Vec &vel1, const Vec &velCov,
+                                          const PoseWithUncertainty &prev, PoseWithUncertainty &post) {
+        const size_t n = vel0.size() / 6;
+        DevBuf v0(vel0), v1(vel1), vc(velCov), pp(prev.pose), pc(prev.cov);
+        DevOut op(n * 7), oc(n * 36), dp(n * 7), dc(n * 36);
+        check(slb_deadreckon_update_pose((int64_t)n, delta_t, v0.get(), v1.get(), vc.get(), pp.get(), pc.get(), op.get(), oc.get(),
+                                         dp.get(), dc.get(), nullptr),
+              "slb_deadreckon_update_pose");
+        op.download(post.pose);
+        oc.download(post.cov);
+        PoseWithUncertainty delta;
+        dp.download(delta.pose);
+        dc.download(delta.cov);
+        return delta;
+    }
+    static PoseWithUncertainty compose(const PoseWithUncertainty &t2, const PoseWithUncertainty &t1) {   // t2 * t1
+        const size_t n = t2.pose.size() / 7;
+        DevBuf a(t2.pose), b(t2.cov), c(t1.pose), d(t1.cov);
+        DevOut op(n * 7), oc(n * 36);
+        check(slb_transform_compose((int64_t)n, a.get(), b.get(), c.get(), d.get(), op.get(), oc.get(), nullptr),
+              "slb_transform_compose");
+        PoseWithUncertainty r;
+        op.download(r.pose);
+        oc.download(r.cov);
         return r;
     }
 };

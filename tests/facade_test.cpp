@@ -32,6 +32,10 @@ int main() {
             data3.fusion(data2);
             print("dm_fusion_x", data3.data, 3);
             print("dm_fusion_C", data3.Cov, 9);
+            data3 = data1;                                   // test/DataModelUnitTest.cpp:72-76
+            data3.safeFusion(data2);
+            print("dm_safe_x", data3.data, 3);
+            print("dm_safe_C", data3.Cov, 9);
         }
         {   // UKFOM
             Vec mu0 = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0}, P0(81, 0.0), Q(81, 0.0), R(9, 0.0);
@@ -89,6 +93,28 @@ int main() {
             for (int i = 0; i < 2; ++i) filter.predict(SLB_PM_MSCKF_DELTAPOSE, u, 0.0, Q);
             print("msckf_mu", filter.muSingleState(), 13);
             print("msckf_P", filter.getPkSingleState(), 144);
+        }
+        {   // SURVEY 8f rows f2 / f4 through the facade: one error-state EKF cycle, one dead-reckoning step
+            Vec state(48, 0.0), error(45, 0.0), P0(45 * 45, 0.0), F(225, 0.0), Q(225, 0.0), H(3 * 45, 0.0), R(9, 0.0);
+            for (int s3 = 0; s3 < 3; ++s3) state[16 * s3 + 6] = 1.0;
+            state[32] = 1.0;  // statek_i.pos.x
+            for (int i = 0; i < 45; ++i) P0[i * 45 + i] = 0.01;
+            for (int i = 0; i < 15; ++i) { F[i * 15 + i] = 1.0; Q[i * 15 + i] = 1e-4; }
+            for (int i = 0; i < 3; ++i) { F[i * 15 + 3 + i] = 0.01; H[i * 45 + 15 + i] = -1.0; H[i * 45 + 30 + i] = 1.0; R[i * 3 + i] = 0.0025; }
+            UsckfError filter(state, error, P0);
+            filter.ekfPredict(F, Q);
+            Vec ret = filter.ekfUpdate({1.02, 0.01, -0.01}, H, R, true);
+            print("ekf_ret", ret, 3);
+            print("ekf_P", filter.PkAugmentedState(), 45 * 45);
+            PoseWithUncertainty prev, post;
+            prev.pose = {1, 2, 3, 1, 0, 0, 0};
+            prev.cov.assign(36, 0.0);
+            Vec velcov(36, 0.0);
+            for (int i = 0; i < 6; ++i) { prev.cov[i * 6 + i] = 1e-3; velcov[i * 6 + i] = i < 3 ? 1e-2 : 1e-3; }
+            PoseWithUncertainty delta = DeadReckon::updatePose(0.01, {1, 0, 0, 0, 0, 0.1}, {1, 0, 0, 0, 0, 0.1}, velcov, prev, post);
+            print("dr_post", post.pose, 7);
+            print("dr_post_cov", post.cov, 36);
+            print("dr_delta", delta.pose, 7);
         }
         std::printf("OK\n");
         return 0;

@@ -58,6 +58,9 @@ def test_facade_replays_reference_tests(slo):
     np.testing.assert_array_equal(v("dm_fusion_x"), xr[0])
     np.testing.assert_array_equal(v("dm_fusion_C"), Cr[0].ravel())
     np.testing.assert_allclose(v("dm_fusion_x"), [0.0146635, 0.0011758085, -0.0187294], rtol=1e-9)
+    xs, Cs = slo.safe_fusion(fx["x1"], fx["C1"], fx["x2"], fx["C2"])                 # :72-76
+    np.testing.assert_array_equal(v("dm_safe_x"), xs[0])
+    np.testing.assert_array_equal(v("dm_safe_C"), Cs[0].ravel())
     # UKFOM (test/UKFoMUnitTest.cpp:93-117)
     ux = synth.ukfom_fixture()
     mu, P, st, _ = slo.ukf_step(9, slo.PM_UKFOM_IMU_REFBUG, slo.MM_GPS_POS, ux["mu"], ux["P"], ux["u"], ux["dt"], ux["Q"],
@@ -80,3 +83,24 @@ def test_facade_replays_reference_tests(slo):
         m, Pm, st = slo.msckf_predict(slo.PM_MSCKF_DELTAPOSE, k, m, Pm, u, 0.0, 0.01 * np.eye(12))
     parity.assert_parity(slo, synth.STATE_BLOCKS, v("msckf_mu")[None], v("msckf_P").reshape(1, 12, 12), m[:, :13],
                          parity.symmetrize_lower(Pm)[:, :12, :12])
+    # SURVEY 8f rows f2 / f4 through the facade
+    state = np.zeros((1, 48))
+    state[0, [6, 22, 38]] = 1.0
+    state[0, 32] = 1.0
+    P0 = 0.01 * np.eye(45)[None]
+    F = np.eye(15)
+    F[0:3, 3:6] = 0.01 * np.eye(3)
+    H = np.zeros((3, 45))
+    H[:, 15:18] = -np.eye(3)
+    H[:, 30:33] = np.eye(3)
+    err1, P1 = slo.ekf_predict(np.zeros((1, 45)), P0, F[None], 1e-4 * np.eye(15))
+    P2, ret, acc = slo.ekf_update(state, P1, np.array([[1.02, 0.01, -0.01]]), H, 0.0025 * np.eye(3), gate=1)
+    assert acc[0] == 1
+    np.testing.assert_array_equal(v("ekf_ret"), ret[0])
+    assert parity.cov_error(v("ekf_P").reshape(1, 45, 45), P2) <= parity.STEP_TOL
+    velcov = np.diag([1e-2] * 3 + [1e-3] * 3)
+    vel = np.array([[1, 0, 0, 0, 0, 0.1]])
+    post, pcov, dpose, dcov = slo.dr_update_pose(0.01, vel, vel, velcov, np.array([[1., 2, 3, 1, 0, 0, 0]]), 1e-3 * np.eye(6)[None])
+    np.testing.assert_allclose(v("dr_post"), post[0], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(v("dr_delta"), dpose[0], rtol=1e-12, atol=1e-15)
+    assert parity.cov_error(v("dr_post_cov").reshape(1, 6, 6), pcov) <= parity.STEP_TOL
