@@ -207,20 +207,24 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             for (int c = lane; c < M; c += 32)
                 RC[j * MS_ZS + c] = 0.5 * (RB[(1 + 2 * j) * MS_ZS + c] - RB[(2 + 2 * j) * MS_ZS + c]);
         __syncthreads();
-        // centre Z for the covariance
-        for (int s = warp; s < NS; s += MS_W)
-            for (int c = lane; c < M; c += 32) RB[s * MS_ZS + c] -= zbar[c];
+        // centre Z for the covariance; the pad rows NS..NSPAD-1 are zeroed so the k-loop of S needs no bound check
+        for (int s = warp; s < MS_NSPAD; s += MS_W)
+            for (int c = lane; c < M; c += 32) RB[s * MS_ZS + c] = s < NS ? RB[s * MS_ZS + c] - zbar[c] : 0.0;
         // ---- covXZ = L W (:239 -> :635-657): in-place TRMM on region C.  A warp owns an 8-column strip and
         //      walks the row tiles bottom-up (row tile tr reads only rows <= 8 tr + 7 of its own strip) ------
         for (int tc = warp; tc < ((M + 7) >> 3); tc += MS_W) {
-            const int bc = 8 * tc + fr;
+            const int bc = min(8 * tc + fr, M - 1);   // clamped: columns >= M are never stored
             for (int tr = nrt - 1; tr >= 0; --tr) {
-                const int ai = 8 * tr + fr;
+                const int ai = 8 * tr + fr, aic = min(ai, N - 1);
+                const double *pa = RA + tri(aic, 0) + fk, *pb = RC + fk * MS_ZS + bc;
                 double d0 = 0.0, d1 = 0.0;
-                for (int k0 = 0; k0 < 8 * tr + 8; k0 += 4) {
+#pragma unroll 4
+                for (int k0 = 0; k0 < 8 * tr; k0 += 4) dmma884(d0, d1, pa[k0], pb[k0 * MS_ZS]);  // kk < 8 tr <= ai: inside L
+#pragma unroll
+                for (int k0 = 8 * tr; k0 < 8 * tr + 8; k0 += 4) {                                 // the diagonal tile
                     const int kk = k0 + fk;
-                    const double av = (ai < N && kk <= ai) ? RA[tri(ai, kk)] : 0.0;
-                    const double bv = (kk < N && bc < M) ? RC[kk * MS_ZS + bc] : 0.0;
+                    const double av = kk <= aic ? pa[k0] : 0.0;
+                    const double bv = kk < N ? pb[k0 * MS_ZS] : 0.0;
                     dmma884(d0, d1, av, bv);
                 }
                 __syncwarp();
@@ -239,15 +243,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             for (int t = warp; t < ntiles; t += MS_W) {
                 int tr, tc;
                 tri_tile(t, tr, tc);
-                const int ar = 8 * tr + fr, bc = 8 * tc + fr;
-                const bool av_ok = ar < M, bv_ok = bc < M;
+                // rows / columns beyond M only feed outputs that are dropped below (D(i,j) uses row i of A and column j
+                // of B only), so their addresses are merely clamped into the buffer: the loop is 2 LDS + 1 DMMA
+                const double *pa = RB + fk * MS_ZS + min(8 * tr + fr, M - 1), *pb = RB + fk * MS_ZS + min(8 * tc + fr, M - 1);
                 double d0 = 0.0, d1 = 0.0;
-                for (int k0 = 0; k0 < NS; k0 += 4) {
-                    const int kk = k0 + fk;
-                    const double av = (av_ok && kk < NS) ? RB[kk * MS_ZS + ar] : 0.0;
-                    const double bv = (bv_ok && kk < NS) ? RB[kk * MS_ZS + bc] : 0.0;
-                    dmma884(d0, d1, av, bv);
-                }
+#pragma unroll 4
+                for (int k0 = 0; k0 < MS_NSPAD; k0 += 4) dmma884(d0, d1, pa[k0 * MS_ZS], pb[k0 * MS_ZS]);
                 const int r = 8 * tr + fr, c = 8 * tc + 2 * fk;
                 if (r < M) {
                     if (c <= r) RA[tri(r, c)] = 0.5 * d0 + __ldg(a.R + r * M + c);
@@ -386,13 +387,15 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             for (int t = warp; t < ntiles; t += MS_W) {
                 int tr, tc;
                 tri_tile(t, tr, tc);
-                const int ai = 8 * tr + fr, bj = 8 * tc + fr;
+                const int ai = 8 * tr + fr;
+                const double *pa = Xz + min(ai, N - 1) * MS_ZS + fk, *pb = Xz + min(8 * tc + fr, N - 1) * MS_ZS + fk;
                 double d0 = 0.0, d1 = 0.0;
-                for (int k0 = 0; k0 < mk; k0 += 4) {
-                    const int kk = k0 + fk;
-                    const double av = (ai < N && kk < mk) ? Xz[ai * MS_ZS + kk] : 0.0;
-                    const double bv = (bj < N && kk < mk) ? Xz[bj * MS_ZS + kk] : 0.0;
-                    dmma884(d0, d1, av, bv);
+                const int kfull = mk & ~3;   // mk is even: at most one ragged k-step
+#pragma unroll 4
+                for (int k0 = 0; k0 < kfull; k0 += 4) dmma884(d0, d1, pa[k0], pb[k0]);
+                if (kfull < mk) {
+                    const bool in = kfull + fk < mk;
+                    dmma884(d0, d1, in ? pa[kfull] : 0.0, in ? pb[kfull] : 0.0);
                 }
                 const int r = ai, c = 8 * tc + 2 * fk;
                 if (r < N) {
@@ -489,7 +492,9 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             if (!flags[3]) break;
         }
         if (flags[4] >= 10000) st |= SLB_ST_MEAN_NOCONV;
-        // deviations d_s = X_s [-] mean, in place (72 <= 83 slots per sigma point)
+        // deviations d_s = X_s [-] mean, in place (72 <= 83 slots per sigma point); the pad rows NS..NSPAD-1 are zeroed
+        if (tid >= NS && tid < MS_NSPAD)
+            for (int e = 0; e < N; ++e) RB[tid * MS_QS + e] = 0.0;
         if (tid < NS) {
             double *X = RB + tid * MS_QS;
             for (int b = 0; b < NB; ++b) {
@@ -513,14 +518,11 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             for (int t = warp; t < ntiles; t += MS_W) {
                 int tr, tc;
                 tri_tile(t, tr, tc);
-                const int ar = 8 * tr + fr, bc = 8 * tc + fr;
+                const int ar = 8 * tr + fr;
+                const double *pa = RB + fk * MS_QS + min(ar, N - 1), *pb = RB + fk * MS_QS + min(8 * tc + fr, N - 1);
                 double d0 = 0.0, d1 = 0.0;
-                for (int k0 = 0; k0 < NS; k0 += 4) {
-                    const int kk = k0 + fk;
-                    const double av = (ar < N && kk < NS) ? RB[kk * MS_QS + ar] : 0.0;
-                    const double bv = (bc < N && kk < NS) ? RB[kk * MS_QS + bc] : 0.0;
-                    dmma884(d0, d1, av, bv);
-                }
+#pragma unroll 4
+                for (int k0 = 0; k0 < MS_NSPAD; k0 += 4) dmma884(d0, d1, pa[k0 * MS_QS], pb[k0 * MS_QS]);  // pad rows are zero
                 const int r = ar, c = 8 * tc + 2 * fk;
                 if (r < N) {
                     if (c <= r) Pg[tri(r, c)] = 0.5 * d0;
@@ -963,13 +965,15 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             for (int t = warp; t < ntiles; t += MS_W) {
                 int tr, tc;
                 tri_tile(t, tr, tc);
-                const int ai = 8 * tr + fr, bj = 8 * tc + fr;
+                const int ai = 8 * tr + fr;
+                const double *pa = RH + min(ai, N - 1) * ME_HS + fk, *pb = RH + min(8 * tc + fr, N - 1) * ME_HS + fk;
                 double d0 = 0.0, d1 = 0.0;
-                for (int k0 = 0; k0 < N; k0 += 4) {
-                    const int kq = k0 + fk;
-                    const double av = (ai < N && kq < N) ? RH[ai * ME_HS + kq] : 0.0;
-                    const double bv = (bj < N && kq < N) ? RH[bj * ME_HS + kq] : 0.0;
-                    dmma884(d0, d1, av, bv);
+                const int kfull = N & ~3;   // N is even: at most one ragged k-step
+#pragma unroll 4
+                for (int k0 = 0; k0 < kfull; k0 += 4) dmma884(d0, d1, pa[k0], pb[k0]);
+                if (kfull < N) {
+                    const bool in = kfull + fk < N;
+                    dmma884(d0, d1, in ? pa[kfull] : 0.0, in ? pb[kfull] : 0.0);
                 }
                 const int r = ai, c = 8 * tc + 2 * fk;
                 if (r < N) {

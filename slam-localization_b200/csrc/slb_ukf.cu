@@ -210,23 +210,30 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
     const bool valid = inst < a.B;
 
     // ---- stage the 8 records of this warp: lane -> (instance lane % IPW, fields lane / IPW + G k) ----
+    // 8-byte LDGSTS: all ~14 loads of a lane are in flight before the first one lands (the staging loop used to
+    // wait for each load in turn: 20 % of the kernel's stall samples)
     {
         const int li = lane % IPW, e0 = lane / IPW;
         const bool lv = wbase + li < a.B;
         double *dst = wsm + li * R::IS;
 #pragma unroll 4
         for (int e = e0; e < QD + NP; e += G) {
-            double v = 0.0;
-            if (lv) v = e < QD ? a.mu[(size_t)e * a.stride + wbase + li] : a.P[(size_t)(e - QD) * a.stride + wbase + li];
-            dst[e < QD ? R::MU + e : R::PS + (e - QD)] = v;
+            double *d = dst + (e < QD ? R::MU + e : R::PS + (e - QD));
+            if (lv) {
+                const double *src = e < QD ? a.mu + (size_t)e * a.stride + wbase + li : a.P + (size_t)(e - QD) * a.stride + wbase + li;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(src) : "memory");
+            } else {
+                *d = 0.0;
+            }
         }
         if (PRED) {
             for (int e = lane; e < NP; e += 32) {
-                int r = 0;
-                while (tri(r + 1, 0) <= e) ++r;
+                int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);  // packed index -> (r, c), exact for e < 2^20
+                r += (tri(r + 1, 0) <= e) - (tri(r, 0) > e);
                 Qp[e] = __ldg(a.Q + r * N + (e - tri(r, 0)));
             }
         }
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
     }
     __syncwarp();
     double *sig = rec + R::SIG, *lf = rec + R::LF, *ps = rec + R::PS;
