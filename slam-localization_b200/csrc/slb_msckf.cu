@@ -39,13 +39,6 @@ static_assert(MS_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF update working set excee
 static_assert(MS_NSPAD * MS_QS <= MS_B, "sigma points do not fit region B");
 static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_B, "compacted S does not fit region B");
 
-// D(8x8) += A(8x4) B(4x8): lane holds a = A[lane>>2][lane&3], b = B[lane&3][lane>>2] and the accumulator
-// pair d0 = D[lane>>2][2*(lane&3)], d1 = D[lane>>2][2*(lane&3)+1].
-SLB_DEV void dmma884(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
 // linear index of a lower-triangular tile -> (tr, tc), tc <= tr
 SLB_DEV void tri_tile(int t, int &tr, int &tc) {
     int r = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);

@@ -25,7 +25,7 @@ namespace slbd {
 // update with the VO measurement model of test/UsckfUnitTest.cpp:62-86 (m = NK)
 // =====================================================================================================
 template <int NK, int NL>
-struct UpdCfg {
+struct UpdCfg : CycCfg<36 + NK + NL> {
     static constexpr int N = 36 + NK + NL;
     static constexpr int NP = N * (N + 1) / 2;
     static constexpr int JM = 36 + NK;          // columns j >= JM cannot move h
@@ -37,80 +37,6 @@ struct UpdCfg {
     static constexpr int KK = 2 * N * NK;
     static constexpr int SCR = ZW > KK ? ZW : KK;  // Z | W, later overlaid by K | KS
     static constexpr int SM = (LS + SCR + N + 1) / 2 * 2;
-    // first element of column k of the packed column-major factor; L(i,k) = Ls[cb(k) - k + i], i >= k
-    SLB_HD static constexpr int cb(int k) { return k * N - k * (k - 1) / 2; }
-    // tile (r,c) of the 2D-cyclic register layout holds at least one lower-triangular entry
-    SLB_HD static constexpr bool exists(int r, int c) { return 4 * r < N && 8 * c < N && 4 * r + 3 >= 8 * c; }
-    // ... and at least one entry (i,j) with j > k (hence i > k): it takes part in the trailing update of step k
-    SLB_HD static constexpr bool live(int k, int r, int c) { return exists(r, c) && 8 * c + 7 > k && 4 * r + 3 > k; }
-    SLB_HD static constexpr bool row_live(int k, int r) {
-        for (int c = 0; c < CT; ++c)
-            if (live(k, r, c)) return true;
-        return false;
-    }
-    SLB_HD static constexpr bool col_live(int k, int c) {
-        for (int r = 0; r < RT; ++r)
-            if (live(k, r, c)) return true;
-        return false;
-    }
-};
-
-// Right-looking factorisation of the N x N covariance held 2D-cyclically in registers: lane (a, b), a = lane & 3,
-// b = lane >> 2, owns the entries (a + 4r, b + 8c).  It is computed in the square-root-free form Pk = U D^-1 U^T
-// (U = L sqrt(D), unit-free "unscaled" columns: U(i,k) is the Schur-complement entry (i,k) at step k, D = diag U):
-// Eigen::LLT's factor is L(:,k) = U(:,k) / sqrt(d_k), a per-column scale that the consumers (sigma points, L W)
-// fold into their own per-column coefficients.  What this buys is the length of the serial chain per column: the
-// pivot's 1/sqrt no longer sits between the previous trailing update and the publication of the column.  Step K
-// (compile-time, fully unrolled by recursion): the 4 lanes holding column K publish it to shared memory as it is
-// (column-major packed: exactly the layout the sigma points and L W need afterwards), every lane rank-1-updates
-// its live tiles with U(i,K) and -U(j,K)/d_K read back from that column.  -1/d_K arrives from the previous step
-// (look-ahead: d_{K+1} = T(K+1,K+1) - U(K+1,K)^2/d_K is formed redundantly by all lanes from one broadcast of
-// the old diagonal entry, with the same operations as the owner's tile update so both agree bitwise), so the
-// reciprocal's latency overlaps the trailing update.  Entries of finished columns / of the upper triangle are
-// never read again, so the update needs no predicate at all: whole tiles are pruned at compile time and the rest
-// is plain DFMA.
-template <class C, int K>
-struct CholStep {
-    template <class Tile>
-    SLB_DEV static void run(Tile &T, double *Ls, int a_, int b_, bool &ok, double x, double nrcp) {
-        constexpr int N = C::N, RT = C::RT, CT = C::CT;
-        constexpr int rk = K >> 2, bk = K & 7, ck = K >> 3;
-        constexpr int K1 = K + 1 < N ? K + 1 : K;
-        constexpr int owner1 = (K1 & 3) + 4 * (K1 & 7);
-        constexpr int base = C::cb(K) - K;
-        ok = ok && (x > 0.0);
-        const double xn_old = __shfl_sync(FULL, T[K1 >> 2][K1 >> 3], owner1);
-#pragma unroll
-        for (int r = rk; r < RT; ++r) {
-            const int i = a_ + 4 * r;
-            if (b_ == bk && i >= K && i < N) Ls[base + i] = T[r][ck];
-        }
-        __syncwarp();
-        double li[RT], lj[CT];
-#pragma unroll
-        for (int r = 0; r < RT; ++r)
-            if (C::row_live(K, r)) li[r] = Ls[base + a_ + 4 * r];
-#pragma unroll
-        for (int c = 0; c < CT; ++c)
-            if (C::col_live(K, c)) lj[c] = Ls[base + b_ + 8 * c] * nrcp;
-        double xn = x, nrcpn = nrcp;
-        if (K + 1 < N) {
-            const double u1 = Ls[base + K + 1];
-            xn = fma(u1, u1 * nrcp, xn_old);
-            nrcpn = -rcp_fast(xn);
-        }
-#pragma unroll
-        for (int r = 0; r < RT; ++r)
-#pragma unroll
-            for (int c = 0; c < CT; ++c)
-                if (C::live(K, r, c)) T[r][c] = fma(li[r], lj[c], T[r][c]);
-        CholStep<C, K + 1>::run(T, Ls, a_, b_, ok, xn, nrcpn);
-    }
-};
-template <class C>
-struct CholStep<C, C::N> {
-    template <class Tile>
-    SLB_DEV static void run(Tile &, double *, int, int, bool &, double, double) {}
 };
 
 template <int NK, int NL, int WPB, int MINB>
