@@ -1,4 +1,12 @@
-set -x
-timeout 900 python -m pytest tests/test_gpu_usckf.py -m gpu -x -q 2>&1 | tail -4
-timeout 600 python bench.py --workload usckf --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r01y_bench_usckf.json 2> gpurun_out/r01y_bench_usckf.err
-tail -2 gpurun_out/r01y_bench_usckf.err; cut -c1-220 gpurun_out/r01y_bench_usckf.json
+for n in 1 2 3 4 6; do
+SLB_HOST_CHUNKS=$n timeout 600 python bench.py --workload ukfom --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/tmp_bench.json 2>/dev/null
+python -c "
+import json
+d=json.loads(open('gpurun_out/tmp_bench.json').read().strip().splitlines()[-1]); print('chunks $n', 'e2e %.4g'%d['e2e']['value'], 'us/step %.1f'%(65536/d['e2e']['value']*1e6))"
+done
+for n in 2 4 8; do
+SLB_HOST_CHUNKS=$n timeout 600 python bench.py --workload usckf --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/tmp_bench.json 2>/dev/null
+python -c "
+import json
+d=json.loads(open('gpurun_out/tmp_bench.json').read().strip().splitlines()[-1]); print('usckf chunks $n', 'e2e %.4g'%d['e2e']['value'])"
+done

@@ -1,6 +1,7 @@
 // slb_api.cu -- the extern "C" surface declared in include/slb.h: batch lifetime, host<->device
 // state transfer (layout conversion kernels), dispatch to the filter kernels, diagnostics.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <new>
@@ -289,6 +290,7 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMemset(h->mu, 0, mu_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->P, 0, P_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->status, 0, (size_t)h->B * 4);
@@ -310,6 +312,8 @@ int slb_destroy(slb_handle h) {
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
     if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->step_exec) cudaGraphExecDestroy(h->step_exec);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     delete h;
     return SLB_OK;
 }
@@ -463,13 +467,8 @@ static int launch_chunk(slb_handle h, const HostStep &hs, int b0, int cnt, const
     }
 }
 
-static int step_host(slb_handle h, const HostStep &hs, void *stream) {
-    if (!h || !hs.u || !hs.Q || !hs.z || !hs.R) return set_error(SLB_ERR_INVALID, "slb_*_step_host: null argument");
-    cudaStream_t s = S(stream);
-    const size_t ub = (size_t)h->B * hs.nu * 8, zb = (size_t)h->B * hs.m * 8, mub = (size_t)h->B * h->QD * 8;
-    const size_t small = (size_t)(hs.nq * hs.nq + hs.m * hs.m + hs.nparams) * 8;
-    if (ub + zb + mub > h->stage_bytes || small > 128 * 1024)
-        return set_error(SLB_ERR_INVALID, "slb_*_step_host: batch / shared inputs too large for the staging buffers");
+// Enqueues one predict+update step with host buffers on `s` (and the chunk ring forked from it): no synchronisation.
+static int step_host_enqueue(slb_handle h, const HostStep &hs, cudaStream_t s) {
     double *du = h->stage, *dz = du + (size_t)h->B * hs.nu, *dmu = dz + (size_t)h->B * hs.m;
     double *dQ = h->shared_small, *dp = dQ + hs.nq * hs.nq, *dR = dp + hs.nparams;
     SLB_CUDA(cudaMemcpyAsync(dQ, hs.Q, (size_t)hs.nq * hs.nq * 8, cudaMemcpyHostToDevice, s));
@@ -477,8 +476,17 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream) {
     SLB_CUDA(cudaMemcpyAsync(dR, hs.R, (size_t)hs.m * hs.m * 8, cudaMemcpyHostToDevice, s));
     SLB_CUDA(cudaEventRecord(h->ev_start, s));
     // chunks of >= 8192 instances (multiples of 32 so no warp straddles a chunk), at most 8
-    int nchunk = h->B / 16384;
-    nchunk = nchunk < 1 ? 1 : nchunk > 8 ? 8 : nchunk;
+    // The UKF step is short (a 65 536-instance fleet is 4.6 waves of CTAs, ~30 us per wave) and its PCIe traffic takes
+    // as long as the kernel: fine chunks pay a whole wave each, so three chunks overlap best (measured on B200: 1 / 2 /
+    // 3 / 4 / 6 / 8 chunks -> 391 / 417 / 317 / 378 / 390 / 364 us per step).  The USCKF / MSCKF steps are kernel-bound:
+    // more, smaller chunks hide the transfers better (2 / 4 / 8 chunks -> 4.1e7 / 4.5e7 / 5.3e7 steps/s).
+    int nchunk = h->cfg.kind == SLB_KIND_UKF ? h->B / 20000 : h->B / 8192;
+    const int cmax = h->cfg.kind == SLB_KIND_UKF ? 3 : 8;
+    nchunk = nchunk < 1 ? 1 : nchunk > cmax ? cmax : nchunk;
+    {
+        static const int forced = [] { const char *e = getenv("SLB_HOST_CHUNKS"); return e ? atoi(e) : 0; }();
+        if (forced > 0) nchunk = forced;
+    }
     const int per = ((h->B + nchunk - 1) / nchunk + 31) / 32 * 32;
     const bool soa = h->cfg.kind == SLB_KIND_UKF;
     int used = 0;
@@ -504,6 +512,67 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream) {
         SLB_CUDA(cudaEventRecord(h->ev_done[i], h->xs[i]));
         SLB_CUDA(cudaStreamWaitEvent(s, h->ev_done[i], 0));
     }
+    return SLB_OK;
+}
+
+static bool is_pinned(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int step_host(slb_handle h, const HostStep &hs, void *stream) {
+    if (!h || !hs.u || !hs.Q || !hs.z || !hs.R) return set_error(SLB_ERR_INVALID, "slb_*_step_host: null argument");
+    cudaStream_t s = S(stream);
+    const size_t ub = (size_t)h->B * hs.nu * 8, zb = (size_t)h->B * hs.m * 8, mub = (size_t)h->B * h->QD * 8;
+    const size_t small = (size_t)(hs.nq * hs.nq + hs.m * hs.m + hs.nparams) * 8;
+    if (ub + zb + mub > h->stage_bytes || small > 128 * 1024)
+        return set_error(SLB_ERR_INVALID, "slb_*_step_host: batch / shared inputs too large for the staging buffers");
+    // With page-locked host buffers the whole pipeline is captured once and replayed (pageable copies cannot be captured).
+    const bool graphable = is_pinned(hs.u) && is_pinned(hs.z) && is_pinned(hs.Q) && is_pinned(hs.R) && is_pinned(hs.params) &&
+                           is_pinned(hs.mu_out);
+    if (!graphable) {
+        const int rc = step_host_enqueue(h, hs, s);
+        if (rc != SLB_OK) return rc;
+        SLB_CUDA(cudaStreamSynchronize(s));
+        return SLB_OK;
+    }
+    const int ki[8] = {hs.pm, hs.mm, hs.nu, hs.m, hs.nq, hs.nparams, hs.gate, 0};
+    const void *kp[6] = {hs.u, hs.Q, hs.params, hs.z, hs.R, hs.mu_out};
+    bool same = h->step_exec != nullptr && h->step_key_dt == hs.dt;
+    for (int i = 0; i < 8 && same; ++i) same = h->step_key_i[i] == ki[i];
+    for (int i = 0; i < 6 && same; ++i) same = h->step_key_p[i] == kp[i];
+    if (!same) {
+        if (h->step_exec) { cudaGraphExecDestroy(h->step_exec); h->step_exec = nullptr; }
+        const int64_t n0 = slb_launch_count();
+        SLB_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = step_host_enqueue(h, hs, h->cap_stream);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
+        const int nk = (int)(slb_launch_count() - n0);
+        count_launch(-nk);  // captured, not executed
+        if (rc != SLB_OK || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            return rc != SLB_OK ? rc : set_error(SLB_ERR_CUDA, "slb_*_step_host: stream capture failed", ce);
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&h->step_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) {
+            h->step_exec = nullptr;
+            return set_error(SLB_ERR_CUDA, "slb_*_step_host: cudaGraphInstantiate", ie);
+        }
+        h->step_kernels = nk;
+        h->step_key_dt = hs.dt;
+        for (int i = 0; i < 8; ++i) h->step_key_i[i] = ki[i];
+        for (int i = 0; i < 6; ++i) h->step_key_p[i] = kp[i];
+    }
+    SLB_CUDA(cudaGraphLaunch(h->step_exec, s));
+    count_launch(h->step_kernels);
     SLB_CUDA(cudaStreamSynchronize(s));
     return SLB_OK;
 }

@@ -27,6 +27,14 @@ struct slb_batch_s {
     int64_t *counts_dev;  // 4 counters for slb_status
     int32_t *misc_dev;    // 16 ints of per-launch scratch flags (e.g. "R is diagonal" for the MSCKF EKF update)
     cudaStream_t xs[SLB_NXS];  // chunk ring of the *_step_host entry points
+    // the *_step_host pipeline captured as a CUDA graph (replayed while the caller keeps passing the same pinned
+    // buffers and parameters: one cudaGraphLaunch instead of ~30 stream calls per step)
+    cudaStream_t cap_stream;
+    cudaGraphExec_t step_exec;
+    int step_kernels;          // kernel launches inside the captured step
+    int step_key_i[8];
+    double step_key_dt;
+    const void *step_key_p[6];
     cudaEvent_t ev_start, ev_done[SLB_NXS];
 };
 

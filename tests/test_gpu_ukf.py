@@ -166,3 +166,36 @@ def test_ukf_step_host_chunked_pipeline_is_bitwise_the_device_path(B):
     np.testing.assert_array_equal(out, a.mu())
     np.testing.assert_array_equal(b.P(), a.P())
     np.testing.assert_array_equal(b.status(), a.status())
+
+
+def test_ukf_step_host_graph_replay_with_pinned_buffers():
+    """With page-locked host buffers slb_ukf_step_host captures its H2D / kernel / D2H pipeline into a CUDA graph and
+    replays it while the same buffers are passed: three steps (capture + two replays, new inputs written into the same
+    pinned buffers) must equal three device-path steps bit for bit; changing a parameter re-captures."""
+    import torch
+    B = 40000
+    sc = synth.ukfom_scenario(B, seed=38)
+    a, b = engine.Ukf(B), engine.Ukf(B)
+    a.set_state(sc["mu"], sc["P"])
+    b.set_state(sc["mu"], sc["P"])
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    hu, hz, hQ, hR = pin(sc["u"]), pin(sc["z"]), pin(sc["Q"]), pin(sc["R"])
+    hout = torch.empty((B, 10), dtype=torch.float64).pin_memory()
+    n0 = engine.launch_count()
+    for k in range(3):
+        u, z = sc["u"] * (1.0 + 0.1 * k), sc["z"] + 0.01 * k
+        hu.copy_(torch.from_numpy(u))
+        hz.copy_(torch.from_numpy(z))
+        a.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, u, sc["dt"], sc["Q"], z, sc["R"])
+        b.step_host(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, hu, sc["dt"], hQ, hz, hR, mu_out=hout)
+        np.testing.assert_array_equal(hout.numpy(), a.mu())
+    np.testing.assert_array_equal(b.P(), a.P())
+    assert engine.launch_count() - n0 >= 3 * 3        # replays count the kernels they launch
+    # a different gate re-captures and still matches
+    a.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"] + 5.0, sc["R"], gate_dof=3)
+    hu.copy_(torch.from_numpy(sc["u"]))
+    hz.copy_(torch.from_numpy(sc["z"] + 5.0))
+    b.step_host(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, hu, sc["dt"], hQ, hz, hR, gate_dof=3, mu_out=hout)
+    np.testing.assert_array_equal(hout.numpy(), a.mu())
+    np.testing.assert_array_equal(b.status(), a.status())
+    assert (a.status() & engine.ST_GATE_REJECT).any()
