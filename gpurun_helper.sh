@@ -1,12 +1,6 @@
-for n in 1 2 3 4 6; do
-SLB_HOST_CHUNKS=$n timeout 600 python bench.py --workload ukfom --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/tmp_bench.json 2>/dev/null
+set -x
+timeout 900 python -m pytest tests/test_gpu_next.py tests/test_facade.py -m gpu -x -q 2>&1 | tail -4
+timeout 600 python bench.py --workload safefusion --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/r02b_bench_safefusion.json 2> gpurun_out/r02b_bench_safefusion.err
 python -c "
 import json
-d=json.loads(open('gpurun_out/tmp_bench.json').read().strip().splitlines()[-1]); print('chunks $n', 'e2e %.4g'%d['e2e']['value'], 'us/step %.1f'%(65536/d['e2e']['value']*1e6))"
-done
-for n in 2 4 8; do
-SLB_HOST_CHUNKS=$n timeout 600 python bench.py --workload usckf --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/tmp_bench.json 2>/dev/null
-python -c "
-import json
-d=json.loads(open('gpurun_out/tmp_bench.json').read().strip().splitlines()[-1]); print('usckf chunks $n', 'e2e %.4g'%d['e2e']['value'])"
-done
+d=json.loads(open('gpurun_out/r02b_bench_safefusion.json').read().strip().splitlines()[-1]); print('safefusion', d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'])"

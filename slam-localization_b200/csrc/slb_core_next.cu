@@ -121,40 +121,64 @@ SLB_DEV JRot make_jacobi(double x, double y, double z) {
     const double n = 1.0 / sqrt(t * t + 1.0);
     return {n, -sign_t * (y / fabs(y)) * fabs(t) * n};
 }
-// runtime (p, q) in {(1,0), (2,0), (2,1)}: accessed through selects so the 3x3 stays in registers
+// pick3 is still used by rot_to_quat's largest-diagonal branch (runtime index through selects)
 SLB_DEV double pick3(const Mx<3, 3> &M, int i, int j) {
     double v = M.a[0];
 #pragma unroll
     for (int e = 1; e < 9; ++e) v = (i * 3 + j == e) ? M.a[e] : v;
     return v;
 }
-SLB_DEV void rot_rows3(Mx<3, 3> &M, int p, int q, JRot j) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double x = pick3(M, p, i), y = pick3(M, q, i);
-        const double nx = j.c * x + j.s * y, ny = -j.s * x + j.c * y;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            if (r == p) M(r, i) = nx;
-            if (r == q) M(r, i) = ny;
+// One (p, q) step of a Jacobi sweep with compile-time indices: everything stays in named registers.
+template <int P, int Q>
+SLB_DEV void jacobi_pair(Mx<3, 3> &W, Mx<3, 3> &U, double &max_diag, bool &finished) {
+    const double precision = 2.0 * DBL_EPSILON, consider_zero = DBL_MIN;
+    const double thr = fmax(consider_zero, precision * max_diag);
+    if (fabs(W(P, Q)) > thr || fabs(W(Q, P)) > thr) {
+        finished = false;
+        // internal::real_2x2_jacobi_svd
+        double m00 = W(P, P), m01 = W(P, Q), m10 = W(Q, P), m11 = W(Q, Q);
+        JRot rot1;
+        const double t = m00 + m11, d = m10 - m01;
+        if (fabs(d) < DBL_MIN) {
+            rot1 = {1.0, 0.0};
+        } else {
+            const double u = t / d;
+            const double tmp = sqrt(1.0 + u * u);
+            rot1 = {u / tmp, 1.0 / tmp};
         }
-    }
-}
-SLB_DEV void rot_cols3(Mx<3, 3> &M, int p, int q, JRot j) {  // applyOnTheRight(p, q, j): rotates with j^T
-    const double tc = j.c, ts = -j.s;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double x = pick3(M, i, p), y = pick3(M, i, q);
-        const double nx = tc * x + ts * y, ny = -ts * x + tc * y;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            if (c == p) M(i, c) = nx;
-            if (c == q) M(i, c) = ny;
+        {
+            const double a0 = rot1.c * m00 + rot1.s * m10, a1 = rot1.c * m01 + rot1.s * m11;
+            const double b1 = -rot1.s * m01 + rot1.c * m11;
+            m00 = a0; m01 = a1; m11 = b1;
         }
+        const JRot jr = make_jacobi(m00, m01, m11);
+        const JRot jrt = {jr.c, -jr.s};
+        const JRot jl = {rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};
+        // m_workMatrix.applyOnTheLeft(p, q, j_left)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double x = W(P, i), y = W(Q, i);
+            W(P, i) = jl.c * x + jl.s * y;
+            W(Q, i) = -jl.s * x + jl.c * y;
+        }
+        // m_matrixU.applyOnTheRight(p, q, j_left.transpose()): rotates the columns with j_left
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double x = U(i, P), y = U(i, Q);
+            U(i, P) = jl.c * x + jl.s * y;
+            U(i, Q) = -jl.s * x + jl.c * y;
+        }
+        // m_workMatrix.applyOnTheRight(p, q, j_right): rotates the columns with j_right^T
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double x = W(i, P), y = W(i, Q);
+            W(i, P) = jr.c * x - jr.s * y;
+            W(i, Q) = jr.s * x + jr.c * y;
+        }
+        max_diag = fmax(max_diag, fmax(fabs(W(P, P)), fabs(W(Q, Q))));
     }
 }
 SLB_DEV void jacobi_svd3(const Mx<3, 3> &A, Mx<3, 3> &U, double *sv) {
-    const double precision = 2.0 * DBL_EPSILON, consider_zero = DBL_MIN;
     double scale = 0.0;
 #pragma unroll
     for (int e = 0; e < 9; ++e) scale = fmax(scale, fabs(A.a[e]));
@@ -166,41 +190,11 @@ SLB_DEV void jacobi_svd3(const Mx<3, 3> &A, Mx<3, 3> &U, double *sv) {
     double max_diag = fmax(fmax(fabs(W(0, 0)), fabs(W(1, 1))), fabs(W(2, 2)));
     bool finished = false;
     int guard = 0;
-    while (!finished && guard++ < 64) {
+    while (!finished && guard++ < 64) {   // sweep order p = 1.., q < p: (1,0) (2,0) (2,1)
         finished = true;
-#pragma unroll 1
-        for (int pq = 0; pq < 3; ++pq) {
-            const int p = pq == 0 ? 1 : 2, q = pq == 2 ? 1 : 0;
-            const double thr = fmax(consider_zero, precision * max_diag);
-            const double wpq = pick3(W, p, q), wqp = pick3(W, q, p);
-            if (fabs(wpq) > thr || fabs(wqp) > thr) {
-                finished = false;
-                // internal::real_2x2_jacobi_svd
-                double m00 = pick3(W, p, p), m01 = wpq, m10 = wqp, m11 = pick3(W, q, q);
-                JRot rot1;
-                const double t = m00 + m11, d = m10 - m01;
-                if (fabs(d) < DBL_MIN) {
-                    rot1 = {1.0, 0.0};
-                } else {
-                    const double u = t / d;
-                    const double tmp = sqrt(1.0 + u * u);
-                    rot1 = {u / tmp, 1.0 / tmp};
-                }
-                {
-                    const double a0 = rot1.c * m00 + rot1.s * m10, a1 = rot1.c * m01 + rot1.s * m11;
-                    const double b0 = -rot1.s * m00 + rot1.c * m10, b1 = -rot1.s * m01 + rot1.c * m11;
-                    m00 = a0; m01 = a1; m10 = b0; m11 = b1;
-                }
-                (void)m10;
-                const JRot jr = make_jacobi(m00, m01, m11);
-                const JRot jrt = {jr.c, -jr.s};
-                const JRot jl = {rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};
-                rot_rows3(W, p, q, jl);
-                rot_cols3(U, p, q, JRot{jl.c, -jl.s});
-                rot_cols3(W, p, q, jr);
-                max_diag = fmax(max_diag, fmax(fabs(pick3(W, p, p)), fabs(pick3(W, q, q))));
-            }
-        }
+        jacobi_pair<1, 0>(W, U, max_diag, finished);
+        jacobi_pair<2, 0>(W, U, max_diag, finished);
+        jacobi_pair<2, 1>(W, U, max_diag, finished);
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
