@@ -120,7 +120,8 @@ template <int N, int M>
 struct EkuCfg {
     static constexpr int NP = N * (N + 1) / 2;
     static constexpr int ROW = 12;  // K(3) A(3) G(3) + pad: 16-byte aligned rows
-    static constexpr int SM = (NP + N * ROW + M * N + 1) / 2 * 2;
+    static constexpr int RO = (NP + 1) / 2 * 2;  // offset of the rows (even: 16-byte aligned for the vector loads)
+    static constexpr int SM = (RO + N * ROW + M * N + 1) / 2 * 2;
 };
 
 // Joseph-form update of the packed lower triangle Pl (N x N) held in shared memory; H (M x N) in shared memory.
@@ -131,11 +132,13 @@ SLB_DEV bool joseph_update(double *Pl, double *rows, const double *Hs, const dou
     typedef EkuCfg<N, M> C;
     static_assert(M == 3, "S^-1 is the closed-form 3x3 inverse");
     static_assert(N <= 64, "two rows per lane");
-    // A = P H^T: lane owns rows lane, lane + 32
+    // A = P H^T: lane owns rows lane, lane + 32 (one joint loop over j: per-lane split loops over the packed row and
+    // column parts diverge -- every lane a different trip count -- and measured slower)
     double A0[M], A1[M];
 #pragma unroll
     for (int c = 0; c < M; ++c) A0[c] = A1[c] = 0.0;
     const int i0 = lane, i1 = lane + 32;
+#pragma unroll 3
     for (int j = 0; j < N; ++j) {
         const double p0 = i0 < N ? Pl[i0 >= j ? tri(i0, j) : tri(j, i0)] : 0.0;
         const double p1 = i1 < N ? Pl[i1 >= j ? tri(i1, j) : tri(j, i1)] : 0.0;
@@ -155,26 +158,23 @@ SLB_DEV bool joseph_update(double *Pl, double *rows, const double *Hs, const dou
         for (int c = 0; c < M; ++c) rows[i1 * C::ROW + 3 + c] = A1[c];
     }
     __syncwarp();
-    // S = H A + R, H x_hat: every lane redundantly (broadcast reads)
+    // S = H A + R and H x_hat: each lane adds the terms of its own rows, one butterfly reduction for the 12 sums
     double S[M * M], hx[M];
 #pragma unroll
     for (int r = 0; r < M; ++r) {
-        hx[r] = 0.0;
+        const double h0 = i0 < N ? Hs[r * N + i0] : 0.0, h1 = i1 < N ? Hs[r * N + i1] : 0.0;
+        double t = fma(h0, i0 < N ? xhat[i0] : 0.0, h1 * (i1 < N ? xhat[i1] : 0.0));
 #pragma unroll
-        for (int c = 0; c < M; ++c) S[r * M + c] = 0.0;
-    }
-    for (int i = 0; i < N; ++i) {
-        const double x = xhat[i];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(EKF_FULL, t, o);
+        hx[r] = t;
 #pragma unroll
-        for (int r = 0; r < M; ++r) {
-            const double h = Hs[r * N + i];
-            hx[r] = fma(h, x, hx[r]);
+        for (int c = 0; c < M; ++c) {
+            double v = fma(h0, A0[c], h1 * A1[c]);
 #pragma unroll
-            for (int c = 0; c < M; ++c) S[r * M + c] = fma(h, rows[i * C::ROW + 3 + c], S[r * M + c]);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(EKF_FULL, v, o);
+            S[r * M + c] = v + __ldg(Rg + r * M + c);
         }
     }
-#pragma unroll
-    for (int e = 0; e < M * M; ++e) S[e] += __ldg(Rg + e);
     double Si[M * M];
     inv3(S, Si);
     double m2 = 0.0;
@@ -218,17 +218,20 @@ SLB_DEV bool joseph_update(double *Pl, double *rows, const double *Hs, const dou
         double Ki[M], Ai[M], Gi[M];
 #pragma unroll
         for (int c = 0; c < M; ++c) { Ki[c] = rows[i * C::ROW + c]; Ai[c] = rows[i * C::ROW + 3 + c]; Gi[c] = rows[i * C::ROW + 6 + c]; }
+        double *pij = Pl + tri(i, 0);
         for (int j = 0; j <= i; ++j) {
+            const double2 *rj = reinterpret_cast<const double2 *>(rows + j * C::ROW);  // K0 K1 | K2 A0 | A1 A2 | G0 G1 | G2 -
+            const double2 q0 = rj[0], q1 = rj[1], q2 = rj[2], q3 = rj[3], q4 = rj[4];
+            const double Kj[3] = {q0.x, q0.y, q1.x}, Aj[3] = {q1.y, q2.x, q2.y}, Gj[3] = {q3.x, q3.y, q4.x};
             double ka = 0.0, gk = 0.0;
 #pragma unroll
             for (int c = 0; c < M; ++c) {
-                const double Kj = rows[j * C::ROW + c], Aj = rows[j * C::ROW + 3 + c], Gj = rows[j * C::ROW + 6 + c];
-                ka = fma(Ki[c], Aj, ka);
-                ka = fma(Kj, Ai[c], ka);
-                gk = fma(Gi[c], Kj, gk);
-                gk = fma(Gj, Ki[c], gk);
+                ka = fma(Ki[c], Aj[c], ka);
+                ka = fma(Kj[c], Ai[c], ka);
+                gk = fma(Gi[c], Kj[c], gk);
+                gk = fma(Gj[c], Ki[c], gk);
             }
-            Pl[tri(i, j)] = Pl[tri(i, j)] + 0.5 * (gk - ka);
+            pij[j] = pij[j] + 0.5 * (gk - ka);
         }
     }
     __syncwarp();
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(WPB * 32) ekf_update_kernel(int64_t n, const d
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t inst = (int64_t)blockIdx.x * WPB + w;
     if (inst >= n) return;
-    double *Pl = sm + (size_t)w * (C::SM + N + 1) , *rows = Pl + C::NP, *Hs = rows + N * C::ROW, *xh = sm + (size_t)w * (C::SM + N + 1) + C::SM;
+    double *Pl = sm + (size_t)w * (C::SM + N + 1) , *rows = Pl + C::RO, *Hs = rows + N * C::ROW, *xh = sm + (size_t)w * (C::SM + N + 1) + C::SM;
     double *Pg = P + inst * (N * N);
     for (int i = 0; i < N; ++i)
         for (int j = lane; j <= i; j += 32) ekf_cp8(Pl + tri(i, j), Pg + i * N + j);
@@ -264,9 +267,13 @@ __global__ void __launch_bounds__(WPB * 32) ekf_update_kernel(int64_t n, const d
         for (int c = 0; c < M; ++c) ret[inst * M + c] = ok ? 0.0 : innov[c];  // :361 / :371
     }
     if (!ok) return;
-    for (int e = lane; e < N * N; e += 32) {
-        const int i = e / N, j = e - i * N;
-        Pg[e] = Pl[i >= j ? tri(i, j) : tri(j, i)];
+    {   // dense rows out, coalesced; (i, j) advance incrementally instead of a division per element
+        int i = 0, j = lane;
+        for (int e = lane; e < N * N; e += 32) {
+            Pg[e] = Pl[i >= j ? tri(i, j) : tri(j, i)];
+            j += 32;
+            if (j >= N) { j -= N; ++i; }
+        }
     }
 }
 
@@ -280,7 +287,7 @@ __global__ void __launch_bounds__(WPB * 32) ekf_single_update_kernel(int64_t n, 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t inst = (int64_t)blockIdx.x * WPB + w;
     if (inst >= n) return;
-    double *Pl = sm + (size_t)w * (C::SM + N + 1), *rows = Pl + C::NP, *Hs = rows + N * C::ROW, *xk = sm + (size_t)w * (C::SM + N + 1) + C::SM;
+    double *Pl = sm + (size_t)w * (C::SM + N + 1), *rows = Pl + C::RO, *Hs = rows + N * C::ROW, *xk = sm + (size_t)w * (C::SM + N + 1) + C::SM;
     double *Pg = P + inst * (EKF_NA * EKF_NA);
     for (int e = lane; e < N * N; e += 32) {
         const int i = e / N, j = e - i * N;
