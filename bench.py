@@ -116,7 +116,7 @@ class UkfomWorkload:
     kernel = "slbd::ukf_kernel<MTK9, IMU, GPS, G=4, fused>"
     phases = ("ukf_kernel",)
     dominant = 0
-    traffic = 33.7e6 + 0.07e6       # ncu dram read+write per launch (profiles/r01_ncu_full_summary.txt); the 36 MB
+    traffic = 33.7e6 + 0.07e6       # ncu dram read+write per launch (profiles/r01_ncu_full_summary_final.txt); the 36 MB
                                     # fleet fits L2, so the write-back of a lone profiled launch is not counted
 
     def __init__(self, rank, seed=1234):
@@ -194,7 +194,7 @@ class FusionWorkload:
     kernel = "slbd::datamodel_kernel<6, fusion>"
     phases = ("datamodel_kernel",)
     dominant = 0
-    traffic = 704.7e6 + 319.5e6     # ncu dram read+write per launch (profiles/r01_ncu_full_summary.txt)
+    traffic = 704.8e6 + 322.3e6     # ncu dram read+write per launch (profiles/r01_ncu_full_summary_final.txt)
 
     def __init__(self, rank, seed=99):
         self.sc = synth.fusion_scenario(self.B, d=self.d, seed=seed + rank)
@@ -282,7 +282,8 @@ class UsckfWorkload:
 
     phases = ("predict12_kernel", "usckf_update_kernel")
     dominant = 1
-    traffic = 18.9e3 * 524288       # ncu dram read+write of usckf_update_kernel, profiles/r01_ncu_full_summary.txt
+    traffic = (649.7e6 + 618.4e6) / 65536 * 524288  # ncu dram read+write of usckf_update_kernel (65 536-instance launch,
+                                                    # profiles/r01_ncu_full_summary_final.txt) scaled to this fleet
 
     def step_phase(self, k, p):
         e = self.engine
@@ -375,7 +376,7 @@ class MsckfWorkload:
 
     phases = ("predict12_kernel", "msckf_update_kernel")
     dominant = 1
-    traffic = None
+    traffic = (92.7e6 + 37.0e6) / 4096 * 16384   # ncu dram read+write of msckf_update_kernel (4096-instance launch) scaled
 
     def step_phase(self, k, p):
         e = self.engine

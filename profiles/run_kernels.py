@@ -65,4 +65,24 @@ if "msckf_ekf" in which:
     for _ in range(2):
         f.update_ekf(engine.MM_MSCKF_REPROJ, lm, z, R)
     torch.cuda.synchronize()
+if "ekf" in which:
+    n = 65536
+    sc = synth.ekf_scenario(1024, seed=1)
+    rep = n // 1024
+    f = engine.ErrorStateEkf(np.tile(sc["mu"], (rep, 1)), np.tile(sc["err"], (rep, 1)), np.tile(sc["P"], (rep, 1, 1)))
+    F, Q, z, H, R = (engine.DeviceArray(x) for x in (np.tile(sc["F"], (rep, 1, 1)), sc["Q"], np.tile(sc["z"], (rep, 1)), sc["H"], sc["R"]))
+    for _ in range(2):
+        f.ekf_predict(F, Q)
+        f.ekf_update(z, H, R, gate=False)
+    torch.cuda.synchronize()
+if "next" in which:
+    n = 1 << 20
+    sf = synth.safe_fusion_scenario(n, log_spread=1.5)
+    a = [engine.DeviceArray(sf[k]) for k in ("x1", "C1", "x2", "C2")]
+    for _ in range(2):
+        engine.DataModel.safe_fuse(*a)
+    dr = synth.deadreckon_scenario(n)
+    for _ in range(2):
+        engine.DeadReckon.update_pose(dr["dt"], dr["vel0"], dr["vel1"], dr["velcov"], dr["prev_pose"], dr["prev_cov"])
+    torch.cuda.synchronize()
 print("ok")
