@@ -406,33 +406,49 @@ SLB_DEV Mx<3, 3> drx_by_dr(const double *q, const double *x) {
 }
 
 // result = t2 * t1 (Transform.cpp:215-254); poses are pos(3) quat(w,x,y,z), covariances 6x6 over [r t]
-SLB_DEV void transform_compose(const double *pose2, const Mx<6, 6> &cov2, const double *pose1, const Mx<6, 6> &cov1, double *pose_out,
-                               Mx<6, 6> &cov_out) {
+// cov2 / cov1 / cov_out point at row-major 6x6 matrices in global memory: 3x3 blocks are fetched and stored on demand, so
+// no 6x6 matrix is ever live in registers.
+SLB_DEV void transform_compose(const double *pose2, const double *cov2, const double *pose1, const double *cov1, double *pose_out,
+                               double *cov_out) {
     const Mx<3, 3> R1 = quat_to_rot(pose1 + 3), R2 = quat_to_rot(pose2 + 3);
     double q1[4], q2[4], q[4];
     rot_to_quat(R1, q1);
     rot_to_quat(R2, q2);
     quat_mul(q2, q1, q);
-    Mx<6, 6> J1, J2;
-    J1.zero();
-    J2.zero();
+    // J1 = [A1 0; 0 R2], J2 = [A2 0; B2 I] (Transform.cpp:233-247): the two 6x6 sandwiches J c J^T are evaluated on
+    // their 3x3 blocks.  The skipped terms are exact zeros of the dense products, so the sums (and their order) are the
+    // reference's; half the multiplications and a third of the live registers of the dense form.
     {
         const Mx<3, 4> a = dr_by_dq(q);
-        const Mx<3, 3> j1 = mul(mul(a, dq2q1_by(q2, 1.0)), dq_by_dr(q1));
-        const Mx<3, 3> j2 = mul(mul(a, dq2q1_by(q1, -1.0)), dq_by_dr(q2));
-        const Mx<3, 3> j3 = drx_by_dr(q2, pose1);
+        const Mx<3, 3> A1 = mul(mul(a, dq2q1_by(q2, 1.0)), dq_by_dr(q1));
+        const Mx<3, 3> A2 = mul(mul(a, dq2q1_by(q1, -1.0)), dq_by_dr(q2));
+        const Mx<3, 3> B2 = drx_by_dr(q2, pose1);
+        auto blk = [](const double *c, int bi, int bj) {
+            Mx<3, 3> o;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                J1(i, j) = j1(i, j);
-                J1(3 + i, 3 + j) = R2(i, j);
-                J2(i, j) = j2(i, j);
-                J2(3 + i, j) = j3(i, j);
-                J2(3 + i, 3 + j) = i == j ? 1.0 : 0.0;
-            }
+                for (int j = 0; j < 3; ++j) o(i, j) = c[(3 * bi + i) * 6 + 3 * bj + j];
+            return o;
+        };
+        auto put = [&](int bi, int bj, const Mx<3, 3> &x, const Mx<3, 3> &y) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) cov_out[(3 * bi + i) * 6 + 3 * bj + j] = x(i, j) + y(i, j);
+        };
+        const Mx<3, 3> A1t = tr(A1), A2t = tr(A2), B2t = tr(B2), R2t = tr(R2);
+        // (J1 c1) blocks and (J2 c2) blocks
+        const Mx<3, 3> p_rr = mul(A1, blk(cov1, 0, 0)), p_rt = mul(A1, blk(cov1, 0, 1));
+        const Mx<3, 3> p_tr = mul(R2, blk(cov1, 1, 0)), p_tt = mul(R2, blk(cov1, 1, 1));
+        const Mx<3, 3> c2rr = blk(cov2, 0, 0), c2rt = blk(cov2, 0, 1);
+        const Mx<3, 3> s_rr = mul(A2, c2rr), s_rt = mul(A2, c2rt);
+        const Mx<3, 3> s_tr = addm(mul(B2, c2rr), blk(cov2, 1, 0)), s_tt = addm(mul(B2, c2rt), blk(cov2, 1, 1));
+        put(0, 0, mul(p_rr, A1t), mul(s_rr, A2t));
+        put(0, 1, mul(p_rt, R2t), addm(mul(s_rr, B2t), s_rt));
+        put(1, 0, mul(p_tr, A1t), mul(s_tr, A2t));
+        put(1, 1, mul(p_tt, R2t), addm(mul(s_tr, B2t), s_tt));
     }
-    cov_out = addm(mul(mul(J1, cov1), tr(J1)), mul(mul(J2, cov2), tr(J2)));
     const Mx<3, 3> R = mul(R2, R1);
 #pragma unroll
     for (int i = 0; i < 3; ++i) pose_out[i] = R2(i, 0) * pose1[0] + R2(i, 1) * pose1[1] + R2(i, 2) * pose1[2] + pose2[i];
@@ -444,16 +460,11 @@ __global__ void __launch_bounds__(64) transform_compose_kernel(int64_t n, const 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double p2[7], p1[7], po[7];
-    Mx<6, 6> c2, c1, co;
 #pragma unroll
     for (int e = 0; e < 7; ++e) { p2[e] = pose2[i * 7 + e]; p1[e] = pose1[i * 7 + e]; }
-#pragma unroll
-    for (int e = 0; e < 36; ++e) { c2.a[e] = cov2[i * 36 + e]; c1.a[e] = cov1[i * 36 + e]; }
-    transform_compose(p2, c2, p1, c1, po, co);
+    transform_compose(p2, cov2 + i * 36, p1, cov1 + i * 36, po, cov_out + i * 36);
 #pragma unroll
     for (int e = 0; e < 7; ++e) pose_out[i * 7 + e] = po[e];
-#pragma unroll
-    for (int e = 0; e < 36; ++e) cov_out[i * 36 + e] = co.a[e];
 }
 
 // DeadReckon::updateAttitude (DeadReckon.hpp:246-286)
@@ -528,15 +539,14 @@ __global__ void __launch_bounds__(64) dr_update_pose_kernel(int64_t n, double dt
             dc(r, c) = __ldg(velcov + (3 + r) * 6 + 3 + c) * dt * dt;
             dc(3 + r, 3 + c) = __ldg(velcov + r * 6 + c) * dt * dt;
         }
-    const Mx<6, 6> dcov = llt_llt6(dc);
-    Mx<6, 6> pc, oc;
+    {   // deltaPose's covariance goes to its output array first; the composition reads it back block by block
+        const Mx<6, 6> dcov = llt_llt6(dc);
 #pragma unroll
-    for (int e = 0; e < 36; ++e) pc.a[e] = prev_cov[i * 36 + e];
-    transform_compose(pp, pc, dp, dcov, po, oc);
+        for (int e = 0; e < 36; ++e) delta_cov[i * 36 + e] = dcov.a[e];
+    }
+    transform_compose(pp, prev_cov + i * 36, dp, delta_cov + i * 36, po, post_cov + i * 36);
 #pragma unroll
     for (int e = 0; e < 7; ++e) { post_pose[i * 7 + e] = po[e]; delta_pose[i * 7 + e] = dp[e]; }
-#pragma unroll
-    for (int e = 0; e < 36; ++e) { post_cov[i * 36 + e] = oc.a[e]; delta_cov[i * 36 + e] = dcov.a[e]; }
 }
 
 }  // namespace slbd
