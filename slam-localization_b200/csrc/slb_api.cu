@@ -541,6 +541,23 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream) {
         SLB_CUDA(cudaStreamSynchronize(s));
         return SLB_OK;
     }
+    // UKF: zero-copy.  The step is as short as its PCIe transfers, so instead of staging copies the kernel reads u / z
+    // from the mapped (page-locked, UVA) host buffers and writes the posterior means straight back: transfers overlap
+    // compute warp by warp.  Only the small shared Q / R are copied.  (SLB_ZERO_COPY=0 selects the copy pipeline.)
+    static const bool zero_copy = [] { const char *e = getenv("SLB_ZERO_COPY"); return !e || atoi(e) != 0; }();
+    if (zero_copy && (h->cfg.kind == SLB_KIND_UKF || h->cfg.kind == SLB_KIND_USCKF)) {
+        double *dQ = h->shared_small, *dR = dQ + hs.nq * hs.nq;
+        SLB_CUDA(cudaMemcpyAsync(dQ, hs.Q, (size_t)hs.nq * hs.nq * 8, cudaMemcpyHostToDevice, s));
+        SLB_CUDA(cudaMemcpyAsync(dR, hs.R, (size_t)hs.m * hs.m * 8, cudaMemcpyHostToDevice, s));
+        FilterArgs a = make_args(h);
+        a.u = hs.u; a.dt = hs.dt; a.Q = dQ; a.z = hs.z; a.R = dR; a.gate = hs.gate; a.m = hs.m;
+        a.mu_out = hs.mu_out;
+        const int rc = h->cfg.kind == SLB_KIND_UKF ? launch_ukf(h->cfg.layout, hs.pm, hs.mm, true, true, a, s)
+                                                   : launch_usckf(hs.pm, hs.mm, true, true, a, s);
+        if (rc != SLB_OK) return rc;
+        SLB_CUDA(cudaStreamSynchronize(s));
+        return SLB_OK;
+    }
     const int ki[8] = {hs.pm, hs.mm, hs.nu, hs.m, hs.nq, hs.nparams, hs.gate, 0};
     const void *kp[6] = {hs.u, hs.Q, hs.params, hs.z, hs.R, hs.mu_out};
     bool same = h->step_exec != nullptr && h->step_key_dt == hs.dt;

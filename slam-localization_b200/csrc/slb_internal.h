@@ -66,6 +66,7 @@ struct FilterArgs {
     int gate;
     int nk, nl, k;
     int32_t *misc;
+    double *mu_out;   // optional instance-major copy of the posterior means (may be mapped host memory), B x QD
 };
 
 // slb_ukf.cu

@@ -74,6 +74,8 @@ struct Rec {
     static constexpr int A0 = NS * QD > UPD_SCR ? NS * QD : UPD_SCR;
     static constexpr int SIGSZ = A0 > G * NP ? A0 : G * NP;  // also the covariance reduction scratch
     static constexpr int SIG = 0, LF = SIGSZ, PS = LF + NP, MU = PS + NP, FLAG = MU + QD;
+    static constexpr int UZ = SIG;        // control input u (<= 6) and measurement z (M) are staged in the (not yet live)
+                                          // sigma-point area and picked up into registers before it is first written
     static constexpr int RAW = FLAG + 1;
     static constexpr int IS = RAW + ((G - RAW % 16) % 16 + 16) % 16;
     // update scratch inside SIG
@@ -226,6 +228,23 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
                 *d = 0.0;
             }
         }
+        // u and z ride along: when they live in mapped host memory (zero-copy *_step_host) their PCIe latency is paid
+        // once, together with the record's, instead of twice in the middle of the step
+        {
+            constexpr int NU = ProcessModel<PM>::NU, PERI = NU + M;
+            static_assert(NU <= 6, "record slot for u");
+            for (int e = lane; e < IPW * PERI; e += 32) {
+                const int li2 = e / PERI, c = e - li2 * PERI;
+                double *d = wsm + li2 * R::IS + R::UZ + c;
+                const bool need = c < NU ? PRED : UPD;
+                if (need && wbase + li2 < a.B) {
+                    const double *src = c < NU ? a.u + (size_t)(wbase + li2) * NU + c : a.z + (size_t)(wbase + li2) * M + (c - NU);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(src) : "memory");
+                } else {
+                    *d = 0.0;
+                }
+            }
+        }
         if (PRED) {
             for (int e = lane; e < NP; e += 32) {
                 int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);  // packed index -> (r, c), exact for e < 2^20
@@ -237,6 +256,12 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
     }
     __syncwarp();
     double *sig = rec + R::SIG, *lf = rec + R::LF, *ps = rec + R::PS;
+    double ureg[ProcessModel<PM>::NU], zreg[MM::M];
+#pragma unroll
+    for (int c = 0; c < ProcessModel<PM>::NU; ++c) ureg[c] = rec[R::UZ + c];
+#pragma unroll
+    for (int c = 0; c < MM::M; ++c) zreg[c] = rec[R::UZ + ProcessModel<PM>::NU + c];
+    __syncwarp();
     if (!valid && sub == 0) {  // tail of the batch: a benign identity prior keeps the idle lanes finite
 #pragma unroll
         for (int r = 0; r < N; ++r) ps[tri(r, r)] = 1.0;
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
         {
             double u[ProcessModel<PM>::NU];
 #pragma unroll
-            for (int c = 0; c < ProcessModel<PM>::NU; ++c) u[c] = valid ? a.u[(size_t)inst * ProcessModel<PM>::NU + c] : 0.0;
+            for (int c = 0; c < ProcessModel<PM>::NU; ++c) u[c] = ureg[c];
             g.prepare(u, a.dt);
         }
 #pragma unroll 1
@@ -336,7 +361,7 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
         auto SAt = [&](int r, int c) { return r >= c ? S[tri(r, c)] : S[tri(c, r)]; };
         double innov[M], m2 = 0.0;
 #pragma unroll
-        for (int c = 0; c < M; ++c) innov[c] = (valid ? a.z[(size_t)inst * M + c] : 0.0) - zbar[c];
+        for (int c = 0; c < M; ++c) innov[c] = zreg[c] - zbar[c];
 #pragma unroll
         for (int r = 0; r < M; ++r) {
             double s = 0.0;
@@ -457,6 +482,18 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
             for (int e = e0; e < QD + NP; e += G) {
                 if (e < QD) a.mu[(size_t)e * a.stride + wbase + li] = src[R::MU + e];
                 else a.P[(size_t)(e - QD) * a.stride + wbase + li] = src[R::PS + (e - QD)];
+            }
+        }
+    }
+    // Optional instance-major copy of the posterior means (the *_step_host entry points pass mapped host memory here:
+    // the warp's 8 q-vectors are 640 contiguous bytes, written with full-width coalesced stores straight over PCIe).
+    if (a.mu_out) {
+        for (int e = lane; e < IPW * QD; e += 32) {
+            const int li = e / QD, c = e - li * QD;
+            if (wbase + li < a.B) {
+                const double *src = wsm + li * R::IS;
+                // a failed instance keeps its prior, which is what the state arrays still hold
+                a.mu_out[(size_t)(wbase + li) * QD + c] = src[R::FLAG] != 0.0 ? src[R::MU + c] : a.mu[(size_t)c * a.stride + wbase + li];
             }
         }
     }

@@ -36,7 +36,7 @@ struct UpdCfg : CycCfg<36 + NK + NL> {
     static constexpr int ZW = NSIG * NK + JM * NK;
     static constexpr int KK = 2 * N * NK;
     static constexpr int SCR = ZW > KK ? ZW : KK;  // Z | W, later overlaid by K | KS
-    static constexpr int SM = (LS + SCR + N + 1) / 2 * 2;
+    static constexpr int SM = (LS + SCR + N + 1) / 2 * 2 + 4;  // + measurement slot (NK <= 3)
 };
 
 // one instance, one warp; `smem` is the warp's private slice
@@ -53,6 +53,14 @@ SLB_DEV void usckf_update_one(const slb::FilterArgs &a, int inst, double *smem_w
            *dl = Zs + C::SCR;
     double *Pg = a.P + (size_t)inst * a.pstride;
     double *mug = a.mu + (size_t)inst * a.qstride;
+    // the measurement is fetched now (LDGSTS into the slot after the record scratch): with zero-copy *_step_host it
+    // lives in mapped host memory and its PCIe latency must not sit in the middle of the update
+    double *zs = smem + C::SM - 4;
+    if (lane < NK) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n cp.async.commit_group;\n" ::"r"((unsigned)__cvta_generic_to_shared(zs + lane)),
+                     "l"(a.z + (size_t)inst * NK + lane)
+                     : "memory");
+    }
 
     // ---- the lower triangle of Pk straight from the HBM record into the 2D-cyclic register tiles ----------
     // (for a fixed tile the 32 lanes read 4 rows x 8 consecutive doubles: full 32-byte sectors)
@@ -238,7 +246,10 @@ SLB_DEV void usckf_update_one(const slb::FilterArgs &a, int inst, double *smem_w
     auto SAt = [&](int r, int c) { return r >= c ? S[tri(r, c)] : S[tri(c, r)]; };
     double nu[NK], m2 = 0.0;
 #pragma unroll
-    for (int c = 0; c < NK; ++c) nu[c] = a.z[(size_t)inst * NK + c] - zbar[c];
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NK; ++c) nu[c] = zs[c] - zbar[c];
 #pragma unroll
     for (int r = 0; r < NK; ++r) {
         double s = 0.0;
@@ -335,6 +346,14 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_update_kernel(slb::Filte
     const int inst = blockIdx.x * WPB + w;
     if (inst >= a.B) return;
     usckf_update_one<NK, NL>(a, inst, smem + (size_t)w * C::SM, lane);
+    // optional instance-major copy of the posterior mean (mapped host memory in the zero-copy *_step_host): whatever the
+    // update decided (accepted, gated, factorisation failed) the record now holds the posterior
+    if (a.mu_out) {
+        __syncwarp();
+        const double *mug = a.mu + (size_t)inst * a.qstride;
+        constexpr int QD = 39 + NK + NL;
+        for (int e = lane; e < QD; e += 32) a.mu_out[(size_t)inst * QD + e] = mug[e];
+    }
 }
 
 // =====================================================================================================

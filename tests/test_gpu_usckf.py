@@ -214,6 +214,30 @@ def test_usckf_step_host_chunked_pipeline_is_bitwise_the_device_path():
     np.testing.assert_array_equal(b.status(), a.status())
 
 
+def test_usckf_step_host_zero_copy_with_pinned_buffers():
+    """Page-locked host buffers: the kernels read u / z from mapped host memory and write the posterior means straight
+    back (no staging copies).  Must equal the device path bit for bit, including gated instances (mean unchanged)."""
+    import torch
+    B, npri = 5000, 250
+    sc = synth.usckf_scenario(npri, seed=78)
+    rep = -(-B // npri)
+    u, z = np.tile(sc["u"], (rep, 1))[:B].copy(), np.tile(sc["z"], (rep, 1))[:B].copy()
+    z[::7] += 4.0                                          # some measurements fail the 3-dof gate
+    a, b = engine.Usckf(B), engine.Usckf(B)
+    for f in (a, b):
+        f.set_state(sc["mu"], sc["P"], replicate=True)
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    hu, hz, hQ, hR = pin(u), pin(z), pin(sc["Q"]), pin(sc["R"])
+    hout = torch.empty((B, 51), dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        a.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u, sc["dt"], sc["Q"], z, sc["R"], gate_dof=3)
+        b.step_host(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, hu, sc["dt"], hQ, hz, hR, gate_dof=3, mu_out=hout)
+        np.testing.assert_array_equal(hout.numpy(), a.mu())
+    np.testing.assert_array_equal(b.P(first=512), a.P(first=512))
+    np.testing.assert_array_equal(b.status(), a.status())
+    assert (a.status() & engine.ST_GATE_REJECT).any() and not (a.status() & engine.ST_GATE_REJECT).all()
+
+
 def test_usckf_config1_10k_steps_free_running(slo):
     """BASELINE configs[0]: USCKF, 12-dof IMU-driven state + cloned poses, 1 kHz inputs, 10,000 free-running
     steps (predict every step, VO update every 3rd, the clone / setMeasurement cycle every 12th) on the GPU and
