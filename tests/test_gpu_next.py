@@ -178,3 +178,47 @@ def test_next_rows_against_committed_golden():
     out = engine.DeadReckon.update_pose(float(g["dt"]), g["vel0"], g["vel1"], g["velcov"], g["prev_pose"], g["prev_cov"])
     for a, k in zip(out, ("post", "pcov", "dpose", "dcov")):
         assert _rel(a.numpy(), g[k]) <= STEP_TOL, k
+
+
+def test_ekf_full_size_properties(slo):
+    """SURVEY 8f row f2 at its bench size (262,144 instances): Joseph update keeps every covariance exactly symmetric
+    and PSD; a strided sample must match the oracle; instances are independent of the batch they sit in."""
+    n, npri = 262144, 1024
+    sc = synth.ekf_scenario(npri, seed=91)
+    rep = n // npri
+    f = engine.ErrorStateEkf(np.tile(sc["mu"], (rep, 1)), np.tile(sc["err"], (rep, 1)), np.tile(sc["P"], (rep, 1, 1)))
+    F, z = np.tile(sc["F"], (rep, 1, 1)), np.tile(sc["z"], (rep, 1))
+    f.ekf_predict(F, sc["Q"])
+    f.ekf_update(z, sc["H"], sc["R"], gate=True)
+    assert int(f.accepted.sum().item()) == rep * int(slo.ekf_update(sc["mu"], slo.ekf_predict(sc["err"], sc["P"], sc["F"], sc["Q"])[1],
+                                                                    sc["z"], sc["H"], sc["R"], gate=1)[2].sum())
+    P = f.P.t[::4099].cpu().numpy()
+    np.testing.assert_array_equal(P, P.transpose(0, 2, 1))
+    assert np.linalg.eigvalsh(P).min() > 0
+    # replicas of the same prior give bitwise the same posterior wherever they sit in the batch
+    Pall = f.P.t
+    assert bool((Pall[:npri] == Pall[-npri:]).all().item())
+    err_r, P_r = slo.ekf_predict(sc["err"], sc["P"], sc["F"], sc["Q"])
+    P_r, _, _ = slo.ekf_update(sc["mu"], P_r, sc["z"], sc["H"], sc["R"], gate=1)
+    assert cov_error(Pall[:npri].cpu().numpy(), P_r) <= STEP_TOL
+
+
+def test_msckf_ekf_full_size(slo):
+    """SURVEY 8f row f1 at the config-3 size (16,384 instances, 10 clones, 50 features)."""
+    from parity import assert_parity, symmetrize_lower
+    B, npri, k = 16384, 256, 10
+    sc = synth.msckf_scenario(npri, seed=92, k=k, nfeat=50, outlier_frac=0.03)
+    f = engine.Msckf(B, nclones=k)
+    f.set_state(sc["mu"], sc["P"], replicate=True)
+    z = np.tile(sc["z"], (B // npri, 1))
+    f.update_ekf(engine.MM_MSCKF_REPROJ, sc["landmarks"], z, sc["R"], gate=True)
+    mu_r, P_r, out_r, st_r = slo.msckf_update_ekf(slo.MM_MSCKF_REPROJ, k, sc["mu"], symmetrize_lower(sc["P"]), sc["landmarks"], sc["z"],
+                                                  sc["R"], gate=True, nthreads=8)
+    out, st = f.outliers(), f.status()
+    np.testing.assert_array_equal(out.reshape(-1, npri), np.tile(out_r, (B // npri, 1)))   # every replica agrees with the oracle
+    np.testing.assert_array_equal(st.reshape(-1, npri), np.tile(st_r, (B // npri, 1)))
+    ok = st_r == 0
+    mu, P = f.mu(first=npri), f.P(first=npri)
+    assert_parity(slo, [0, 1, 0, 0] + [0, 1] * k, mu, symmetrize_lower(P), mu_r, symmetrize_lower(P_r), mask=ok)
+    mu_all = f.mu()
+    np.testing.assert_array_equal(mu_all[:npri], mu_all[-npri:])
