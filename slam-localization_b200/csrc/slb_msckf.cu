@@ -655,28 +655,56 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
                 continue;
             }
-            // W = L^-1, packed lower in RQ: column c is a forward substitution; two lanes share a column (even / odd
-            // terms of the inner product, combined with one shuffle), two partial sums each shorten the dependent chain
+            // W = L^-1, packed lower in RQ, by 8-row blocks: W(I,:) = L_II^-1 (E(I,:) - sum_{K<I} L(I,K) W(K,:)).  The sum is
+            // 8x8x4 DMMA tiles over all warps; the 8x8 forward substitution with L_II is one thread per column.
             {
-                const int c = tid >> 1, half = tid & 1;
-                for (int i = 0; i < M; ++i) {   // uniform trip count: the shuffle below needs every lane
-                    double s0 = 0.0, s1 = 0.0;
-                    if (c < M && i >= c) {
-                        const double *Li = RS + tri(i, 0);
-                        int p = c + half;
-                        for (; p + 2 < i; p += 4) {
-                            s0 = fma(-Li[p], RQ[tri(p, c)], s0);
-                            s1 = fma(-Li[p + 2], RQ[tri(p + 2, c)], s1);
+                const int nbr = (M + 7) >> 3;
+                for (int I = 0; I < nbr; ++I) {
+                    // tiles (I, J), J < I:  T = sum_{K=J}^{I-1} L(I,K) W(K,J), stored negated in place of W(I,J)
+                    for (int J = warp; J < I; J += MS_W) {
+                        double d0 = 0.0, d1 = 0.0;
+                        const int ar = min(8 * I + fr, M - 1);   // rows >= M only feed accumulator rows that are dropped
+                        const int bc = 8 * J + fr;
+                        for (int K = J; K < I; ++K) {
+#pragma unroll
+                            for (int k0 = 0; k0 < 8; k0 += 4) {
+                                const int kk = 8 * K + k0 + fk;   // < 8 I <= M
+                                const double av = RS[tri(ar, kk)];
+                                const double bv = kk >= bc ? RQ[tri(kk, bc)] : 0.0;   // W is lower triangular
+                                dmma884(d0, d1, av, bv);
+                            }
                         }
-                        for (; p < i; p += 2) s0 = fma(-Li[p], RQ[tri(p, c)], s0);
+                        const int r = 8 * I + fr, c = 8 * J + 2 * fk;
+                        if (r < M) {
+                            RQ[tri(r, c)] = -d0;
+                            RQ[tri(r, c + 1)] = -d1;
+                        }
                     }
-                    double sacc = s0 + s1;
-                    sacc += __shfl_xor_sync(FULL, sacc, 1);
-                    if (c < M && i >= c && half == 0) RQ[tri(i, c)] = ((i == c ? 1.0 : 0.0) + sacc) * invd[i];
-                    __syncwarp();
+                    __syncthreads();
+                    // columns 0 .. 8I+7 of block row I: x = L_II^-1 r  (r = the negated sums above, e_c on the diagonal tile)
+                    {
+                        const int c = tid, i0 = 8 * I;
+                        if (c < min(i0 + 8, M)) {
+                            double x[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int i = i0 + q;
+                                if (i < M && i >= c) {
+                                    double sv = c >= i0 ? (i == c ? 1.0 : 0.0) : RQ[tri(i, c)];
+#pragma unroll
+                                    for (int p = 0; p < 8; ++p)
+                                        if (p < q && i0 + p >= c) sv = fma(-RS[tri(i, i0 + p)], x[p], sv);
+                                    x[q] = sv * invd[i];
+                                    RQ[tri(i, c)] = x[q];
+                                } else {
+                                    x[q] = 0.0;
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
                 }
             }
-            __syncthreads();
             // 2x2 diagonal blocks of the information matrix: info_f = W[:, 2f:2f+2]^T W[:, 2f:2f+2]
             bool rej = false;
             if (tid < NF) {
