@@ -49,20 +49,30 @@ SLB_DEV void inv3(const double *A, double *C) {
 // ---- ekfPredict ---------------------------------------------------------------------------------------
 // block row i = rows 30..44:  [P_ik P_il P_ii] <- F [P_ik P_il P_ii],  P_ii <- (F P_ii) F^T + Q,  columns 30..44 of
 // rows 0..29 by symmetry (the reference updates P_ki = P_ki F^T separately, :109-116: the same numbers for a
-// symmetric Pk_error).
-constexpr int EKP_FS = 17;  // odd row stride of F: the Y_ii F^T product reads 15 different rows of F at once
-constexpr int EKP_SM = 15 * EKP_FS + 1 + 15 * 46 + 15 * 46;  // F | block row (stride 46) | result (stride 46)
+// symmetric Pk_error).  Both products are 8x8x4 FP64 DMMA tiles fed from shared memory: Y = F * [block row] is
+// column-wise independent, so each 8-column strip is computed into registers and written back in place.
+constexpr int EKP_FS = 20, EKP_RS = 52;   // row strides of F (16 x 16 padded) and of the block row (16 x 48 padded):
+                                          // = 4 (mod 16) doubles, so a 4 x 8 fragment load touches 32 distinct banks
+constexpr int EKP_SM = 16 * EKP_FS + 16 * EKP_RS;
+SLB_DEV void ekf_dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 template <int WPB>
 __global__ void __launch_bounds__(WPB * 32) ekf_predict_kernel(int64_t n, double *err, double *P, const double *F, const double *Q) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t inst = (int64_t)blockIdx.x * WPB + w;
     if (inst >= n) return;
-    double *Fs = sm + (size_t)w * EKP_SM, *Rs = Fs + 15 * EKP_FS + 1, *Ys = Rs + 15 * 46;
+    const int fr = lane >> 2, fk = lane & 3;   // DMMA fragment coordinates
+    double *Fs = sm + (size_t)w * EKP_SM, *Rs = Fs + 16 * EKP_FS;
     double *Pg = P + inst * (EKF_NA * EKF_NA);
     const double *Fg = F + inst * (EKF_NS * EKF_NS);
     for (int e = lane; e < 225; e += 32) ekf_cp8(Fs + (e / 15) * EKP_FS + e % 15, Fg + e);
-    for (int e = lane; e < 675; e += 32) ekf_cp8(Rs + (e / 45) * 46 + e % 45, Pg + 30 * 45 + e);
+    for (int e = lane; e < 675; e += 32) ekf_cp8(Rs + (e / 45) * EKP_RS + e % 45, Pg + 30 * 45 + e);
+    // zero padding of the k-dimension (column 15 of F, row 15 of the block row) and of the unused columns 45..47
+    if (lane < 16) { Fs[lane * EKP_FS + 15] = 0.0; Fs[15 * EKP_FS + lane] = 0.0; }
+    for (int e = lane; e < 48; e += 32) Rs[15 * EKP_RS + e] = 0.0;
+    for (int e = lane; e < 48; e += 32) Rs[(e / 3) * EKP_RS + 45 + e % 3] = 0.0;
     double ei = lane < 15 ? err[inst * EKF_NA + 30 + lane] : 0.0;
     ekf_cp_wait();
     __syncwarp();
@@ -76,41 +86,61 @@ __global__ void __launch_bounds__(WPB * 32) ekf_predict_kernel(int64_t n, double
         }
         if (lane < 15) err[inst * EKF_NA + 30 + lane] = s;
     }
-    // Y = F * block row: lane owns column c (and c + 32)
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        const int c = lane + 32 * pass;
-        if (c < 45) {
-            double col[15];
+    // A fragments of F: A[m][k] = F[8I + fr][k0 + fk]
+    double fa[2][4];
 #pragma unroll
-            for (int k = 0; k < 15; ++k) col[k] = Rs[k * 46 + c];
-#pragma unroll 1
-            for (int r = 0; r < 15; ++r) {  // rolled: unrolled, ptxas hoists all 225 F entries into registers and spills
-                double s = 0.0;
+    for (int I = 0; I < 2; ++I)
 #pragma unroll
-                for (int k = 0; k < 15; ++k) s += Fs[r * EKP_FS + k] * col[k];
-                Ys[r * 46 + c] = s;
-            }
+        for (int kq = 0; kq < 4; ++kq) fa[I][kq] = Fs[(8 * I + fr) * EKP_FS + 4 * kq + fk];
+    // Y = F * block row, strip by strip (8 columns), in place
+#pragma unroll 2
+    for (int J = 0; J < 6; ++J) {
+        double y0[2] = {0.0, 0.0}, y1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+            const double bv = Rs[(4 * kq + fk) * EKP_RS + 8 * J + fr];   // B[k][n] = row k, column 8J + n
+            ekf_dmma(y0[0], y0[1], fa[0][kq], bv);
+            ekf_dmma(y1[0], y1[1], fa[1][kq], bv);
         }
+        __syncwarp();
+        Rs[fr * EKP_RS + 8 * J + 2 * fk] = y0[0];
+        Rs[fr * EKP_RS + 8 * J + 2 * fk + 1] = y0[1];
+        Rs[(8 + fr) * EKP_RS + 8 * J + 2 * fk] = y1[0];
+        Rs[(8 + fr) * EKP_RS + 8 * J + 2 * fk + 1] = y1[1];
     }
     __syncwarp();
-    // P_ii = Y_ii F^T + Q (:96)
-    for (int e = lane; e < 225; e += 32) {
-        const int r = e / 15, c = e - r * 15;
-        double s = 0.0;
+    // P_ii = Y_ii F^T + Q (:96): A = Y[:, 30 + k], B[k][n] = F[n][k] (the A-fragment pattern of F)
+    {
+        double c[2][2][2];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) s += Ys[r * 46 + 30 + k] * Fs[c * EKP_FS + k];
-        Rs[r * 46 + 30 + c] = s + __ldg(Q + e);
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int J = 0; J < 2; ++J) c[I][J][0] = c[I][J][1] = 0.0;
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+            const double a0 = Rs[fr * EKP_RS + 30 + 4 * kq + fk], a1 = Rs[(8 + fr) * EKP_RS + 30 + 4 * kq + fk];
+            ekf_dmma(c[0][0][0], c[0][0][1], a0, fa[0][kq]);
+            ekf_dmma(c[0][1][0], c[0][1][1], a0, fa[1][kq]);
+            ekf_dmma(c[1][0][0], c[1][0][1], a1, fa[0][kq]);
+            ekf_dmma(c[1][1][0], c[1][1][1], a1, fa[1][kq]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int I = 0; I < 2; ++I)
+#pragma unroll
+            for (int J = 0; J < 2; ++J)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = 8 * I + fr, cc = 8 * J + 2 * fk + h;
+                    if (r < 15 && cc < 15) Rs[r * EKP_RS + 30 + cc] = c[I][J][h] + __ldg(Q + r * 15 + cc);
+                }
     }
     __syncwarp();
-    for (int e = lane; e < 675; e += 32) {
-        const int r = e / 45, c = e - r * 45;
-        Pg[30 * 45 + e] = c < 30 ? Ys[r * 46 + c] : Rs[r * 46 + c];
-    }
+    for (int e = lane; e < 675; e += 32) Pg[30 * 45 + e] = Rs[(e / 45) * EKP_RS + e % 45];
     // mirrored blocks: row k < 30, columns 30..44
     for (int e = lane; e < 450; e += 32) {
         const int k = e / 15, c = e - k * 15;
-        Pg[k * 45 + 30 + c] = Ys[c * 46 + k];
+        Pg[k * 45 + 30 + c] = Rs[c * EKP_RS + k];
     }
 }
 
