@@ -162,30 +162,40 @@ SLB_DEV bool joseph_update(double *Pl, double *rows, const double *Hs, const dou
     typedef EkuCfg<N, M> C;
     static_assert(M == 3, "S^-1 is the closed-form 3x3 inverse");
     static_assert(N <= 64, "two rows per lane");
-    // A = P H^T: lane owns rows lane, lane + 32 (one joint loop over j: per-lane split loops over the packed row and
-    // column parts diverge -- every lane a different trip count -- and measured slower)
-    double A0[M], A1[M];
-#pragma unroll
-    for (int c = 0; c < M; ++c) A0[c] = A1[c] = 0.0;
+    // A = P H^T as 8x8x4 FP64 DMMA tiles: M-dim = rows of P, K-dim = columns j (padded to a multiple of 4, H = 0
+    // there), N-dim = measurement index (3 of 8 columns used).  P is symmetric packed: entry (i,j) = Pl[tri(max,min)].
     const int i0 = lane, i1 = lane + 32;
-#pragma unroll 3
-    for (int j = 0; j < N; ++j) {
-        const double p0 = i0 < N ? Pl[i0 >= j ? tri(i0, j) : tri(j, i0)] : 0.0;
-        const double p1 = i1 < N ? Pl[i1 >= j ? tri(i1, j) : tri(j, i1)] : 0.0;
+    {
+        const int fr = lane >> 2, fk = lane & 3;
+        constexpr int NT = (N + 7) / 8, KQ = (N + 3) / 4;
+        double hb[KQ];   // B[k = j][n = fr] = H[fr][j]
 #pragma unroll
-        for (int c = 0; c < M; ++c) {
-            const double h = Hs[c * N + j];
-            A0[c] = fma(p0, h, A0[c]);
-            A1[c] = fma(p1, h, A1[c]);
+        for (int kq = 0; kq < KQ; ++kq) {
+            const int j = 4 * kq + fk;
+            hb[kq] = (fr < M && j < N) ? Hs[fr * N + j] : 0.0;
+        }
+#pragma unroll 1
+        for (int I = 0; I < NT; ++I) {
+            const int ri = min(8 * I + fr, N - 1), tr0 = tri(ri, 0);
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int kq = 0; kq < KQ; ++kq) {
+                const int jc = min(4 * kq + fk, N - 1);
+                ekf_dmma(d0, d1, Pl[ri >= jc ? tr0 + jc : tri(jc, ri)], hb[kq]);
+            }
+            const int r = 8 * I + fr;
+            if (r < N) {
+                if (fk == 0) { rows[r * C::ROW + 3] = d0; rows[r * C::ROW + 4] = d1; }
+                if (fk == 1) rows[r * C::ROW + 5] = d0;
+            }
         }
     }
-    if (i0 < N) {
+    __syncwarp();
+    double A0[M], A1[M];
 #pragma unroll
-        for (int c = 0; c < M; ++c) rows[i0 * C::ROW + 3 + c] = A0[c];
-    }
-    if (i1 < N) {
-#pragma unroll
-        for (int c = 0; c < M; ++c) rows[i1 * C::ROW + 3 + c] = A1[c];
+    for (int c = 0; c < M; ++c) {
+        A0[c] = i0 < N ? rows[i0 * C::ROW + 3 + c] : 0.0;
+        A1[c] = i1 < N ? rows[i1 * C::ROW + 3 + c] : 0.0;
     }
     __syncwarp();
     // S = H A + R and H x_hat: each lane adds the terms of its own rows, one butterfly reduction for the 12 sums
@@ -241,27 +251,40 @@ SLB_DEV bool joseph_update(double *Pl, double *rows, const double *Hs, const dou
     if (i1 < N) finish(A1, i1);
     __syncwarp();
     if (!accept) return false;
-    // P'_ij = P_ij - 0.5 (K_i.A_j + K_j.A_i) + 0.5 (G_i.K_j + G_j.K_i): lane l takes rows l and N-1-l (N+1 entries)
-    for (int half = 0; half < 2; ++half) {
-        const int i = half == 0 ? lane : N - 1 - lane;
-        if (lane >= (N + 1) / 2 || (half == 1 && i == lane)) continue;
-        double Ki[M], Ai[M], Gi[M];
+    // P'_ij = P_ij - 0.5 (K_i.A_j + A_i.K_j) + 0.5 (G_i.K_j + K_i.G_j) = P_ij + X_i . Y_j with the 12-vectors
+    // X = [-K/2 | -A/2 | G/2 | K/2], Y = [A | K | K | G]: a rank-12 update of the lower 8x8 tiles as FP64 DMMA,
+    // fragments picked straight out of the K | A | G rows (rows beyond N only feed accumulator entries that are dropped).
+    {
+        const int fr = lane >> 2, fk = lane & 3;
+        int xo[3], yo[3];
+        double xs[3];
 #pragma unroll
-        for (int c = 0; c < M; ++c) { Ki[c] = rows[i * C::ROW + c]; Ai[c] = rows[i * C::ROW + 3 + c]; Gi[c] = rows[i * C::ROW + 6 + c]; }
-        double *pij = Pl + tri(i, 0);
-        for (int j = 0; j <= i; ++j) {
-            const double2 *rj = reinterpret_cast<const double2 *>(rows + j * C::ROW);  // K0 K1 | K2 A0 | A1 A2 | G0 G1 | G2 -
-            const double2 q0 = rj[0], q1 = rj[1], q2 = rj[2], q3 = rj[3], q4 = rj[4];
-            const double Kj[3] = {q0.x, q0.y, q1.x}, Aj[3] = {q1.y, q2.x, q2.y}, Gj[3] = {q3.x, q3.y, q4.x};
-            double ka = 0.0, gk = 0.0;
-#pragma unroll
-            for (int c = 0; c < M; ++c) {
-                ka = fma(Ki[c], Aj[c], ka);
-                ka = fma(Kj[c], Ai[c], ka);
-                gk = fma(Gi[c], Kj[c], gk);
-                gk = fma(Gj[c], Ki[c], gk);
+        for (int kq = 0; kq < 3; ++kq) {
+            const int k = 4 * kq + fk;
+            xo[kq] = k < 9 ? k : k - 9;
+            xs[kq] = k < 6 ? -0.5 : 0.5;
+            yo[kq] = k < 3 ? 3 + k : (k < 6 ? k - 3 : (k < 9 ? k - 6 : k - 3));
+        }
+        constexpr int NT = (N + 7) / 8;
+#pragma unroll 1
+        for (int I = 0; I < NT; ++I) {
+            const double *ri = rows + min(8 * I + fr, N - 1) * C::ROW;
+            const double xa0 = ri[xo[0]] * xs[0], xa1 = ri[xo[1]] * xs[1], xa2 = ri[xo[2]] * xs[2];
+            const int r = 8 * I + fr;
+#pragma unroll 1
+            for (int J = 0; J <= I; ++J) {
+                const double *rj = rows + min(8 * J + fr, N - 1) * C::ROW;
+                double d0 = 0.0, d1 = 0.0;
+                ekf_dmma(d0, d1, xa0, rj[yo[0]]);
+                ekf_dmma(d0, d1, xa1, rj[yo[1]]);
+                ekf_dmma(d0, d1, xa2, rj[yo[2]]);
+                const int c = 8 * J + 2 * fk;
+                if (r < N) {
+                    double *pr = Pl + tri(r, 0);
+                    if (c <= r) pr[c] += d0;
+                    if (c + 1 <= r) pr[c + 1] += d1;
+                }
             }
-            pij[j] = pij[j] + 0.5 * (gk - ka);
         }
     }
     __syncwarp();
