@@ -197,6 +197,48 @@ inline Mat inverse_lu(const Mat &A) {
     return X;
 }
 
+// The same PartialPivLU inverse with the multiply-subtract steps of the elimination and of the two triangular solves
+// fused (std::fma), which is what Eigen's kernels do when the reference is built for an FMA-capable CPU (pmadd).
+// Used by DataModel::fusion for D > 3 so that the CUDA kernel -- FP64-issue-bound on its three 6x6 inverses -- can run
+// the identical sequence with DFMA and stay bit-exact at half the floating-point instructions.
+inline Mat inverse_lu_fma(const Mat &A) {
+    const int n = A.r;
+    Mat LU = A;
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        double best = std::fabs(LU(k, k));
+        for (int i = k + 1; i < n; ++i)
+            if (std::fabs(LU(i, k)) > best) { best = std::fabs(LU(i, k)); piv = i; }
+        if (piv != k) {
+            for (int j = 0; j < n; ++j) std::swap(LU(k, j), LU(piv, j));
+            std::swap(perm[k], perm[piv]);
+        }
+        const double d = LU(k, k);
+        for (int i = k + 1; i < n; ++i) LU(i, k) /= d;
+        for (int i = k + 1; i < n; ++i) {
+            const double lik = LU(i, k);
+            for (int j = k + 1; j < n; ++j) LU(i, j) = std::fma(-lik, LU(k, j), LU(i, j));
+        }
+    }
+    Mat X(n, n);
+    for (int col = 0; col < n; ++col) {
+        Vec y(n);
+        for (int i = 0; i < n; ++i) {
+            double s = (perm[i] == col) ? 1.0 : 0.0;
+            for (int p = 0; p < i; ++p) s = std::fma(-LU(i, p), y[p], s);
+            y[i] = s;
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = y[i];
+            for (int p = i + 1; p < n; ++p) s = std::fma(-LU(i, p), X(p, col), s);
+            X(i, col) = s / LU(i, i);
+        }
+    }
+    return X;
+}
+
 // Eigen's fixed-size inverse for 3x3: cofactors / determinant (used by DataModel<double,3>).
 inline Mat inverse_3x3_cofactor(const Mat &A) {
     Mat C(3, 3);
@@ -223,7 +265,7 @@ inline Mat inverse_fixed(const Mat &A) {
         return m;
     }
     if (A.r == 3) return inverse_3x3_cofactor(A);
-    return inverse_lu(A);  // D == 4 uses a cofactor kernel in Eigen; not on the hot path here
+    return inverse_lu_fma(A);  // D == 4 uses a cofactor kernel in Eigen; not on the hot path here
 }
 
 // ------------------------------------------------------------------------------------------

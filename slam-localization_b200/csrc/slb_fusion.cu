@@ -28,8 +28,10 @@ SLB_DEV double div_by(double a, double d, double r) {
     return __fma_rn(rem, r, q);
 }
 
-// Eigen PartialPivLU inverse restated (oracle/slo_core.hpp inverse_lu): same pivot choice, same
-// operation order, no FMA contraction, so the result is bit-identical to the CPU oracle.  Rows are
+// Eigen PartialPivLU inverse restated (oracle/slo_core.hpp inverse_lu_fma): same pivot choice, same operation
+// order, the multiply-subtract steps of the elimination and of both triangular solves fused (explicit __fma_rn here,
+// std::fma there -- what Eigen's pmadd does in an FMA build of the reference), everything else unfused (-fmad=false),
+// so the result is bit-identical to the CPU oracle.  Rows are
 // swapped with predicated moves so LU stays in registers; each finished column of the inverse is handed
 // to `sink(col, x)` instead of being kept (the caller stores or accumulates it), which keeps the live
 // state at LU + two D-vectors.
@@ -77,7 +79,7 @@ SLB_DEV void inverse_lu_cols(double *LU, Sink sink) {
                 const double lik = LU[i * D + k];
 #pragma unroll
                 for (int j = 0; j < D; ++j)
-                    if (j > k) LU[i * D + j] = LU[i * D + j] - lik * LU[k * D + j];
+                    if (j > k) LU[i * D + j] = __fma_rn(-lik, LU[k * D + j], LU[i * D + j]);
             }
         }
     }
@@ -91,7 +93,7 @@ SLB_DEV void inverse_lu_cols(double *LU, Sink sink) {
             double s = (perm[i] == col) ? 1.0 : 0.0;
 #pragma unroll
             for (int p = 0; p < D; ++p)
-                if (p < i) s = s - LU[i * D + p] * y[p];
+                if (p < i) s = __fma_rn(-LU[i * D + p], y[p], s);
             y[i] = s;
         }
 #pragma unroll
@@ -99,7 +101,7 @@ SLB_DEV void inverse_lu_cols(double *LU, Sink sink) {
             double s = y[i];
 #pragma unroll
             for (int p = 0; p < D; ++p)
-                if (p > i) s = s - LU[i * D + p] * x[p];
+                if (p > i) s = __fma_rn(-LU[i * D + p], x[p], s);
             x[i] = div_by(s, LU[i * D + i], rd[i]);
         }
         sink(col, x);
