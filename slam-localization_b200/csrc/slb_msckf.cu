@@ -108,13 +108,11 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
             tri_tile(t, tr, tc);
             const int i0 = r0 + 8 * tr, j0 = r0 + 8 * tc;
             double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-            for (int k0 = 0; k0 < 8; k0 += 4) {
-                const int kk = k0 + fk;
-                const double av = (i0 + fr < n && kk < pb) ? A[tri(i0 + fr, p0 + kk)] : 0.0;
-                const double bv = (j0 + fr < n && kk < pb) ? A[tri(j0 + fr, p0 + kk)] : 0.0;
-                dmma884(d0, d1, av, bv);
-            }
+            // rows beyond n only feed accumulator entries that are never stored: their addresses are clamped, not masked;
+            // a trailing update only exists after a full 8-wide panel (pb == 8), so the k-loop needs no bound either
+            const double *pa = A + tri(min(i0 + fr, n - 1), p0) + fk, *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
+            dmma884(d0, d1, pa[0], pb2[0]);
+            dmma884(d0, d1, pa[4], pb2[4]);
             const int i = i0 + fr, j = j0 + 2 * fk;
             if (i < n) {
                 if (j <= i) A[tri(i, j)] -= d0;
@@ -341,13 +339,10 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 const int tr = t / nct, tc = t - tr * nct;
                 const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
                 double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                for (int k0 = 0; k0 < 8; k0 += 4) {
-                    const int kk = k0 + fk;
-                    const double av = (ai < N && kk < pb) ? Xz[ai * MS_ZS + p0 + kk] : 0.0;
-                    const double bv = (bj < mk && kk < pb) ? Sp[tri(bj, p0 + kk)] : 0.0;
-                    dmma884(d0, d1, av, bv);
-                }
+                // tiles exist only after a full panel (pb == 8); rows / columns out of range are clamped (their outputs are dropped)
+                const double *pa = Xz + min(ai, N - 1) * MS_ZS + p0 + fk, *pb2 = Sp + tri(min(bj, mk - 1), p0) + fk;
+                dmma884(d0, d1, pa[0], pb2[0]);
+                dmma884(d0, d1, pa[4], pb2[4]);
                 const int oc = j0 + 8 * tc + 2 * fk;
                 if (ai < N) {
                     if (oc < mk) Xz[ai * MS_ZS + oc] -= d0;
@@ -948,13 +943,9 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 const int tr = t / nct, tc = t - tr * nct;
                 const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
                 double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                for (int k0 = 0; k0 < 8; k0 += 4) {
-                    const int kq = k0 + fk;
-                    const double av = (ai < N && kq < pb) ? RH[ai * ME_HS + p0 + kq] : 0.0;
-                    const double bv = (bj < N && kq < pb) ? RS[tri(bj, p0 + kq)] : 0.0;
-                    dmma884(d0, d1, av, bv);
-                }
+                const double *pa = RH + min(ai, N - 1) * ME_HS + p0 + fk, *pb2 = RS + tri(min(bj, N - 1), p0) + fk;
+                dmma884(d0, d1, pa[0], pb2[0]);
+                dmma884(d0, d1, pa[4], pb2[4]);
                 const int oc = j0 + 8 * tc + 2 * fk;
                 if (ai < N) {
                     if (oc < N) RH[ai * ME_HS + oc] -= d0;
