@@ -1,8 +1,6 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_msckf.py tests/test_gpu_msckf_ekf.py -m gpu -x -q 2>&1 | tail -3
-for w in msckf msckf_ekf; do
-timeout 600 python bench.py --workload $w --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r02l_bench_$w.json 2>/dev/null
+timeout 600 python bench.py --workload ekf --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/r02n_bench_ekf.json 2>gpurun_out/r02n_bench_ekf.err
+tail -2 gpurun_out/r02n_bench_ekf.err
 python -c "
 import json
-d=json.loads(open('gpurun_out/r02l_bench_$w.json').read().strip().splitlines()[-1]); print('$w', 'value %.4g'%d['value'], 'ms %.3f'%d['ms_per_step'])"
-done
+d=json.loads(open('gpurun_out/r02n_bench_ekf.json').read().strip().splitlines()[-1]); print('ekf', 'value %.4g'%d['value'], 'e2e %.4g'%d['e2e']['value'])"

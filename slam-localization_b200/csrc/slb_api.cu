@@ -699,6 +699,18 @@ int slb_datamodel_fuse_host(int d, int64_t n, const double *x1, const double *C1
         return set_error(SLB_ERR_NO_DEVICE, "slb_datamodel_fuse_host: no CUDA device (no CPU fallback)");
     }
     if (n == 0) return SLB_OK;
+    // Page-locked buffers: zero-copy.  The kernel stages its covariance tiles with coalesced LDGSTS and writes its
+    // results with coalesced stores, which work just as well against mapped host memory: the 1 GB of H2D / D2H
+    // traffic of a 1M-pair step overlaps in both directions and with the arithmetic, and nothing is allocated.
+    {
+        static const bool zero_copy = [] { const char *e = getenv("SLB_ZERO_COPY"); return !e || atoi(e) != 0; }();
+        if (zero_copy && is_pinned(x1) && is_pinned(C1) && is_pinned(x2) && is_pinned(C2) && is_pinned(xo) && is_pinned(Co)) {
+            const int rc = launch_fusion(d, n, 0, x1, C1, x2, C2, xo, Co, 0);
+            if (rc != SLB_OK) return rc;
+            SLB_CUDA(cudaStreamSynchronize(0));
+            return SLB_OK;
+        }
+    }
     const size_t xb = (size_t)n * d * 8, cb = (size_t)n * d * d * 8;
     double *buf = nullptr;
     SLB_CUDA(cudaMalloc(&buf, 2 * xb + 2 * cb));

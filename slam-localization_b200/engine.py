@@ -148,7 +148,19 @@ class DeviceArray:
 
 
 def dev(a):
-    return a if isinstance(a, DeviceArray) else DeviceArray(a)
+    """numpy -> a fresh device copy; DeviceArray -> itself; torch tensor (CUDA, or page-locked host memory, which the
+    kernels can read in place through unified addressing) -> wrapped without a copy."""
+    if isinstance(a, DeviceArray):
+        return a
+    if not isinstance(a, np.ndarray):
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            if not (a.is_cuda or a.is_pinned()):
+                raise SlbError("host tensors must be page-locked (pin_memory) to be passed without a copy")
+            w = DeviceArray.__new__(DeviceArray)
+            w.t = a.contiguous()
+            return w
+    return DeviceArray(a)
 
 
 class Batch:

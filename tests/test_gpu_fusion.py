@@ -73,3 +73,16 @@ def test_fusion_golden_fixture(d):
     xo, Co = engine.DataModel.fuse(g["x1"], g["C1"], g["x2"], g["C2"])
     np.testing.assert_array_equal(xo.numpy(), g["xo"])
     np.testing.assert_array_equal(Co.numpy(), g["Co"])
+
+
+def test_fuse_host_zero_copy_with_pinned_buffers(slo):
+    """Page-locked host arrays: slb_datamodel_fuse_host lets the kernel read and write them in place (mapped memory)."""
+    import torch
+    sc = synth.fusion_scenario(5000, d=6)
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    h = [pin(sc[k]) for k in ("x1", "C1", "x2", "C2")]
+    xo, Co = torch.empty((5000, 6), dtype=torch.float64).pin_memory(), torch.empty((5000, 6, 6), dtype=torch.float64).pin_memory()
+    engine.check(engine.lib().slb_datamodel_fuse_host(6, 5000, *[engine._ptr_of(t) for t in h], engine._ptr_of(xo), engine._ptr_of(Co)))
+    xr, Cr = slo.datamodel(0, sc["x1"], sc["C1"], sc["x2"], sc["C2"])
+    np.testing.assert_array_equal(xo.numpy(), xr)
+    np.testing.assert_array_equal(Co.numpy(), Cr)
