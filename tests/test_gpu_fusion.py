@@ -86,3 +86,18 @@ def test_fuse_host_zero_copy_with_pinned_buffers(slo):
     xr, Cr = slo.datamodel(0, sc["x1"], sc["C1"], sc["x2"], sc["C2"])
     np.testing.assert_array_equal(xo.numpy(), xr)
     np.testing.assert_array_equal(Co.numpy(), Cr)
+
+
+def test_device_api_accepts_pinned_and_cuda_tensors(slo):
+    """engine.dev() wraps torch tensors (CUDA or page-locked host) without a copy: the C ABI only sees pointers."""
+    import torch
+    sc = synth.fusion_scenario(777, d=3)
+    xr, Cr = slo.datamodel(0, sc["x1"], sc["C1"], sc["x2"], sc["C2"])
+    pinned = [torch.from_numpy(sc[k]).pin_memory() for k in ("x1", "C1", "x2", "C2")]
+    xo, Co = engine.DataModel.fuse(*pinned)
+    np.testing.assert_array_equal(xo.numpy(), xr)
+    on_gpu = [t.cuda() for t in pinned]
+    xo, Co = engine.DataModel.fuse(*on_gpu)
+    np.testing.assert_array_equal(Co.numpy(), Cr)
+    with pytest.raises(engine.SlbError):
+        engine.DataModel.fuse(torch.from_numpy(sc["x1"]), *on_gpu[1:])      # pageable host tensor: refused, not copied silently
