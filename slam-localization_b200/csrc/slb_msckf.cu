@@ -758,72 +758,86 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             const int r = e / N, c = e - r * N;
             RQ[r * ME_HS + c] = RH[(compact ? kept[r] : r) * ME_HS + c];
         }
-        if (tid < mk) wv[tid] = nu[compact ? kept[tid] : tid];
+        // the innovation rides along as column N of RQ (the row stride leaves room): Q^T is applied to it with the same
+        // code as to the matrix columns
+        if (tid < mk) RQ[tid * ME_HS + N] = nu[compact ? kept[tid] : tid];
         __syncthreads();
-        if (tid < mk) nu[tid] = wv[tid];
+        // ---- reduceDimension (:794-816): Householder QR of RQ (mk x N) in place.  Per column: partial dot products
+        //      (three threads per column), sync, rank-1 update + the partial norms of the next column, sync, rescale of
+        //      the finished column + the next reflector's scalars, sync ----------------------------------------------------
+        auto reflector = [&](double c0, double t, double *out, int kcol) {  // Eigen makeHouseholderInPlace
+            if (t <= 2.2250738585072014e-308) {
+                out[0] = 0.0;  // tau
+                out[1] = 0.0;  // 1 / (c0 - beta)
+                out[2] = c0;   // beta
+            } else {
+                double beta = sqrt(fma(c0, c0, t));
+                if (c0 >= 0.0) beta = -beta;
+                out[0] = (beta - c0) / beta;
+                out[1] = 1.0 / (c0 - beta);
+                out[2] = beta;
+            }
+            tau[kcol] = out[0];
+        };
+        if (warp == 0) {
+            double t = 0.0;
+            for (int i = 1 + lane; i < mk; i += 32) {
+                const double v = RQ[i * ME_HS];
+                t = fma(v, v, t);
+            }
+            t = warp_sum(t);
+            if (lane == 0) reflector(RQ[0], t, scal, 0);
+        }
         __syncthreads();
-        // ---- reduceDimension (:794-816): Householder QR of RQ (mk x N) in place; Q^T is applied to nu on the way ------
         for (int kk = 0; kk < N; ++kk) {
-            if (warp == 0) {
+            const double *sk = scal + 4 * (kk & 1);
+            const double tk = sk[0], sc = sk[1], beta = sk[2];
+            const int part = tid / 80, jj = tid - part * 80, j = kk + 1 + jj;  // columns kk+1 .. N (N = innovation)
+            const bool act = part < 3 && j <= N;
+            const int i0 = kk + 1 + part;                                    // rows i0, i0 + 3, ...
+            if (tk != 0.0 && act) {
+                // essential part v = tail / (c0 - beta) is formed on the fly: column kk itself is rewritten last
+                const double *pv = RQ + i0 * ME_HS + kk, *pc = RQ + i0 * ME_HS + j;
+                double t0 = 0.0, t1 = 0.0;
+                int i = i0;
+                for (; i + 3 < mk; i += 6, pv += 6 * ME_HS, pc += 6 * ME_HS) {
+                    t0 = fma(pv[0], pc[0], t0);
+                    t1 = fma(pv[3 * ME_HS], pc[3 * ME_HS], t1);
+                }
+                if (i < mk) t0 = fma(pv[0], pc[0], t0);
+                T3[part * 80 + jj] = t0 + t1;
+                if (part == 0) T3[240 + jj] = RQ[kk * ME_HS + j];  // row kk is rewritten by part 0 below
+            }
+            __syncthreads();
+            if (tk != 0.0 && act) {
+                const double tt = tk * fma(sc, (T3[jj] + T3[80 + jj]) + T3[160 + jj], T3[240 + jj]);
+                const double ts = tt * sc;
+                const double *pv = RQ + i0 * ME_HS + kk;
+                double *pc = RQ + i0 * ME_HS + j;
+                for (int i = i0; i < mk; i += 3, pv += 3 * ME_HS, pc += 3 * ME_HS) pc[0] = fma(-ts, pv[0], pc[0]);
+                if (part == 0) RQ[kk * ME_HS + j] -= tt;
+            }
+            // partial norms of the next column's tail (rows > kk+1), by the three threads that have just updated it
+            if (jj == 0 && part < 3 && kk + 1 < N) {
                 double t = 0.0;
-                for (int i = kk + 1 + lane; i < mk; i += 32) {
-                    const double v = RQ[i * ME_HS + kk];
+                for (int i = i0 + (part == 0 ? 3 : 0); i < mk; i += 3) {
+                    const double v = RQ[i * ME_HS + kk + 1];
                     t = fma(v, v, t);
                 }
-                t = warp_sum(t);
-                if (lane == 0) {
-                    const double c0 = RQ[kk * ME_HS + kk];
-                    if (t <= 2.2250738585072014e-308) {
-                        scal[0] = 0.0;  // tau
-                        scal[1] = 0.0;  // 1 / (c0 - beta)
-                        scal[2] = c0;   // beta
-                    } else {
-                        double beta = sqrt(fma(c0, c0, t));
-                        if (c0 >= 0.0) beta = -beta;
-                        scal[0] = (beta - c0) / beta;
-                        scal[1] = 1.0 / (c0 - beta);
-                        scal[2] = beta;
-                    }
-                    tau[kk] = scal[0];
-                }
+                T3[300 + part] = t;
             }
             __syncthreads();
-            const double tk = scal[0], sc = scal[1];
             if (tk != 0.0) {
-                // essential part v = tail / (c0 - beta) is formed on the fly: column kk itself is rewritten last.
-                // Columns kk+1 .. N-1 and the innovation (as column N); three threads share a column (rows i = kk+1+part
-                // mod 3), partial dot products meet in T3.
-                const int part = tid / 80, jj = tid - part * 80, j = kk + 1 + jj;
-                const bool act = part < 3 && j <= N;
-                double *col = j < N ? RQ + j : nu;
-                const int cs = j < N ? ME_HS : 1;
-                if (act) {
-                    double t0 = 0.0, t1 = 0.0;
-                    int i = kk + 1 + part;
-                    for (; i + 3 < mk; i += 6) {
-                        t0 = fma(RQ[i * ME_HS + kk], col[i * cs], t0);
-                        t1 = fma(RQ[(i + 3) * ME_HS + kk], col[(i + 3) * cs], t1);
-                    }
-                    if (i < mk) t0 = fma(RQ[i * ME_HS + kk], col[i * cs], t0);
-                    T3[part * 80 + jj] = t0 + t1;
-                    if (part == 0) T3[240 + jj] = col[kk * cs];  // row kk is rewritten by part 0 below
-                }
-                __syncthreads();
-                if (act) {
-                    const double tt = tk * fma(sc, (T3[jj] + T3[80 + jj]) + T3[160 + jj], T3[240 + jj]);
-                    const double ts = tt * sc;
-                    for (int i = kk + 1 + part; i < mk; i += 3) col[i * cs] = fma(-ts, RQ[i * ME_HS + kk], col[i * cs]);
-                    if (part == 0) col[kk * cs] -= tt;
-                }
-                __syncthreads();
                 for (int i = kk + 1 + tid; i < mk; i += MS_T) RQ[i * ME_HS + kk] *= sc;
             } else {
-                __syncthreads();
                 for (int i = kk + 1 + tid; i < mk; i += MS_T) RQ[i * ME_HS + kk] = 0.0;
             }
-            if (tid == 0) RQ[kk * ME_HS + kk] = scal[2];
+            if (tid == 0) RQ[kk * ME_HS + kk] = beta;
+            if (tid == 32 && kk + 1 < N)
+                reflector(RQ[(kk + 1) * ME_HS + kk + 1], (T3[300] + T3[301]) + T3[302], scal + 4 * ((kk + 1) & 1), kk + 1);
             __syncthreads();
         }
+        if (tid < N) nu[tid] = RQ[tid * ME_HS + N];   // Q^T nu, first N entries (:811)
         // ---- thin Q = householderQ() * Identity(mk, N) into RH (:802-803): reflectors last to first; column j < kk of
         //      the partial product is still e_j, which reflector kk leaves alone ------------------------------------------
         for (int e = tid; e < mk * ME_HS; e += MS_T) {
@@ -836,21 +850,25 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             if (tk != 0.0) {   // uniform
                 const int part = tid / 80, jj = tid - part * 80, j = kk + jj;
                 const bool act = part < 3 && j < N;
+                const int i0 = kk + 1 + part;
                 if (act) {
+                    const double *pv = RQ + i0 * ME_HS + kk, *pc = RH + i0 * ME_HS + j;
                     double t0 = 0.0, t1 = 0.0;
-                    int i = kk + 1 + part;
-                    for (; i + 3 < mk; i += 6) {
-                        t0 = fma(RQ[i * ME_HS + kk], RH[i * ME_HS + j], t0);
-                        t1 = fma(RQ[(i + 3) * ME_HS + kk], RH[(i + 3) * ME_HS + j], t1);
+                    int i = i0;
+                    for (; i + 3 < mk; i += 6, pv += 6 * ME_HS, pc += 6 * ME_HS) {
+                        t0 = fma(pv[0], pc[0], t0);
+                        t1 = fma(pv[3 * ME_HS], pc[3 * ME_HS], t1);
                     }
-                    if (i < mk) t0 = fma(RQ[i * ME_HS + kk], RH[i * ME_HS + j], t0);
+                    if (i < mk) t0 = fma(pv[0], pc[0], t0);
                     T3[part * 80 + jj] = t0 + t1;
                     if (part == 0) T3[240 + jj] = RH[kk * ME_HS + j];
                 }
                 __syncthreads();
                 if (act) {
                     const double tt = tk * ((T3[jj] + T3[80 + jj]) + T3[160 + jj] + T3[240 + jj]);
-                    for (int i = kk + 1 + part; i < mk; i += 3) RH[i * ME_HS + j] = fma(-tt, RQ[i * ME_HS + kk], RH[i * ME_HS + j]);
+                    const double *pv = RQ + i0 * ME_HS + kk;
+                    double *pc = RH + i0 * ME_HS + j;
+                    for (int i = i0; i < mk; i += 3, pv += 3 * ME_HS, pc += 3 * ME_HS) pc[0] = fma(-tt, pv[0], pc[0]);
                     if (part == 0) RH[kk * ME_HS + j] -= tt;
                 }
                 __syncthreads();
