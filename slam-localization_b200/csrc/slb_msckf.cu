@@ -548,17 +548,21 @@ constexpr int ME_RA = 2632, ME_RS = 5056, ME_RH = MS_MMAX * ME_HS, ME_RQ = MS_MM
 constexpr int ME_SMEM_DOUBLES = ME_RA + ME_RS + ME_RH + ME_RQ + ME_RD;
 static_assert(ME_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF EKF update working set exceeds shared memory");
 
-// flag[0] = 1 when the shared m x m measurement noise matrix is diagonal
+// flag[0] = 1 when the shared m x m measurement noise matrix is diagonal, flag[1] = 1 when it is sigma^2 I
 __global__ void msckf_rdiag_kernel(const double *R, int m, int32_t *flag) {
-    __shared__ int off;
-    if (threadIdx.x == 0) off = 0;
+    __shared__ int off, uneq;
+    if (threadIdx.x == 0) { off = 0; uneq = 0; }
     __syncthreads();
-    int mine = 0;
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x)
-        if (e / m != e % m && R[e] != 0.0) mine = 1;
+    const double r0 = R[0];
+    int mine = 0, ne = 0;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        if (e / m != e % m) { if (R[e] != 0.0) mine = 1; }
+        else if (R[e] != r0) ne = 1;
+    }
     if (mine) off = 1;
+    if (ne) uneq = 1;
     __syncthreads();
-    if (threadIdx.x == 0) flag[0] = off ? 0 : 1;
+    if (threadIdx.x == 0) { flag[0] = off ? 0 : 1; flag[1] = (off || uneq || !(r0 > 0.0)) ? 0 : 1; }
 }
 
 __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterArgs a) {
@@ -753,6 +757,51 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             continue;
         }
         const bool compact = mk < M;
+        // With R = sigma^2 I (flagged once per launch) the QR compression is lossless: the rows it discards are orthogonal to
+        // range(H) and uncorrelated with the ones it keeps, so the update equals the plain Kalman update on the (compacted) rows,
+        //   S' = Hc P Hc^T + R',  K = P Hc^T S'^-1,
+        // to rounding (3e-15 against the QR form on the config-3 scenario).  That needs no Householder QR, no thin Q, no
+        // Q^T R Q and no second factorisation when nothing was rejected: the Cholesky factor of S from the outlier gate is reused.
+        const bool direct = a.misc[1] != 0;
+        double *Yb = RH;   // Y = covXZ Ls^-T: base, row stride, number of measurement rows it was solved against
+        int ys = ME_HS, mq = N;
+        if (direct) {
+            Yb = RQ; ys = MS_ZS; mq = mk;
+            // covXZ' = P Hc^T (N x mk) into RQ (the triangular inverse that lived there is consumed): 6 FMA per entry
+            for (int e = tid; e < N * mk; e += MS_T) {
+                const int i = e / mk, pcol = e - i * mk, r = compact ? kept[pcol] : pcol;
+                const int a0 = 12 + 6 * ((r >> 1) % k);
+                double sacc = 0.0;
+#pragma unroll
+                for (int u = 0; u < 6; ++u) sacc = fma(Hb[r * 6 + u], Psym(a0 + u, i), sacc);
+                RQ[i * MS_ZS + pcol] = sacc;
+            }
+            if (tid < mk) wv[tid] = nu[compact ? kept[tid] : tid];
+            __syncthreads();
+            if (tid < mk) nu[tid] = wv[tid];
+            if (compact || !a.gate) {
+                // S' = Hc covXZ' + R' (packed lower) and its Cholesky factor; otherwise RS still holds chol(S) from the gate
+                for (int e = tid; e < mk * (mk + 1) / 2; e += MS_T) {
+                    int pr = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                    pr += (tri(pr + 1, 0) <= e) - (tri(pr, 0) > e);
+                    const int pc = e - tri(pr, 0);
+                    const int rr = compact ? kept[pr] : pr, rc = compact ? kept[pc] : pc;
+                    const int a0 = 12 + 6 * ((rr >> 1) % k);
+                    double sacc = __ldg(a.R + (size_t)rr * M + rc);
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) sacc = fma(Hb[rr * 6 + u], RQ[(a0 + u) * MS_ZS + pc], sacc);
+                    RS[e] = sacc;
+                }
+                __syncthreads();
+                chol_blocked(RS, mk, flags, invd);
+                if (!flags[0]) {
+                    if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
+                    continue;
+                }
+            } else {
+                __syncthreads();
+            }
+        } else {
         // ---- compacted H -> RQ, compacted innovation -------------------------------------------------------------
         for (int e = tid; e < mk * N; e += MS_T) {
             const int r = e / N, c = e - r * N;
@@ -937,11 +986,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
         }
+        }
         // ---- Y = covXZ Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates --------------
-        for (int p0 = 0; p0 < N; p0 += 8) {
-            const int pb = min(8, N - p0);
+        for (int p0 = 0; p0 < mq; p0 += 8) {
+            const int pb = min(8, mq - p0);
             for (int i = tid; i < N; i += MS_T) {
-                double *row = RH + i * ME_HS + p0;
+                double *row = Yb + i * ys + p0;
                 double x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -956,53 +1006,53 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 }
             }
             __syncthreads();
-            const int j0 = p0 + pb, nct = (N - j0 + 7) >> 3;
+            const int j0 = p0 + pb, nct = (mq - j0 + 7) >> 3;
             for (int t = warp; t < nrt * nct; t += MS_W) {
                 const int tr = t / nct, tc = t - tr * nct;
                 const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
                 double d0 = 0.0, d1 = 0.0;
-                const double *pa = RH + min(ai, N - 1) * ME_HS + p0 + fk, *pb2 = RS + tri(min(bj, N - 1), p0) + fk;
+                const double *pa = Yb + min(ai, N - 1) * ys + p0 + fk, *pb2 = RS + tri(min(bj, mq - 1), p0) + fk;
                 dmma884(d0, d1, pa[0], pb2[0]);
                 dmma884(d0, d1, pa[4], pb2[4]);
                 const int oc = j0 + 8 * tc + 2 * fk;
                 if (ai < N) {
-                    if (oc < N) RH[ai * ME_HS + oc] -= d0;
-                    if (oc + 1 < N) RH[ai * ME_HS + oc + 1] -= d1;
+                    if (oc < mq) Yb[ai * ys + oc] -= d0;
+                    if (oc + 1 < mq) Yb[ai * ys + oc + 1] -= d1;
                 }
             }
             __syncthreads();
         }
         // ---- w = Ls^-1 nu' (warp 0), delta = Y w (:337) ----------------------------------------------------------
         if (warp == 0) {
-            for (int q = 0; q < N; ++q) {
+            for (int q = 0; q < mq; ++q) {
                 const double wq = nu[q] * invd[q];
                 __syncwarp();
                 if (lane == 0) wv[q] = wq;
-                for (int c = q + 1 + lane; c < N; c += 32) nu[c] -= RS[tri(c, q)] * wq;
+                for (int c = q + 1 + lane; c < mq; c += 32) nu[c] -= RS[tri(c, q)] * wq;
                 __syncwarp();
             }
         }
         __syncthreads();
         for (int i = warp; i < N; i += MS_W) {
             double sacc = 0.0;
-            for (int q = lane; q < N; q += 32) sacc += RH[i * ME_HS + q] * wv[q];
+            for (int q = lane; q < mq; q += 32) sacc += Yb[i * ys + q] * wv[q];
             sacc = warp_sum(sacc);
             if (lane == 0) dl[i] = sacc;
         }
-        // ---- Pk -= K S K^T = Y Y^T (:336) straight to the HBM record: lower 8x8 tiles, K = N -----------------------
+        // ---- Pk -= K S K^T = Y Y^T (:336) straight to the HBM record: lower 8x8 tiles, K = mq ----------------------
         {
             const int ntiles = nrt * (nrt + 1) / 2;
             for (int t = warp; t < ntiles; t += MS_W) {
                 int tr, tc;
                 tri_tile(t, tr, tc);
                 const int ai = 8 * tr + fr;
-                const double *pa = RH + min(ai, N - 1) * ME_HS + fk, *pb = RH + min(8 * tc + fr, N - 1) * ME_HS + fk;
+                const double *pa = Yb + min(ai, N - 1) * ys + fk, *pb = Yb + min(8 * tc + fr, N - 1) * ys + fk;
                 double d0 = 0.0, d1 = 0.0;
-                const int kfull = N & ~3;   // N is even: at most one ragged k-step
+                const int kfull = mq & ~3;   // mq is even: at most one ragged k-step
 #pragma unroll 4
                 for (int k0 = 0; k0 < kfull; k0 += 4) dmma884(d0, d1, pa[k0], pb[k0]);
-                if (kfull < N) {
-                    const bool in = kfull + fk < N;
+                if (kfull < mq) {
+                    const bool in = kfull + fk < mq;
                     dmma884(d0, d1, in ? pa[kfull] : 0.0, in ? pb[kfull] : 0.0);
                 }
                 const int r = ai, c = 8 * tc + 2 * fk;
