@@ -49,3 +49,26 @@ def test_no_cpu_fallback_without_gpu():
     h = C.c_void_p()
     rc = engine.lib().slb_create(C.byref(cfg), C.byref(h))
     assert rc == -2 and b"no CPU fallback" in engine.lib().slb_last_error()
+
+
+def test_next_row_entry_points_validate_arguments_without_a_gpu():
+    """Argument validation of the handle-less entry points happens before any device work: bad arguments are
+    SLB_ERR_INVALID, an empty batch is a no-op, and real work without a GPU is SLB_ERR_NO_DEVICE (never a CPU fallback)."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    L = engine.lib()
+    buf = np.zeros(45 * 45 + 64)
+    p = buf.ctypes.data_as(C.c_void_p)
+    acc = (C.c_int32 * 4)()
+    assert L.slb_ekf_update(0, 3, p, p, p, p, p, 0, p, acc, None) == 0                    # empty batch
+    assert L.slb_ekf_update(1, 4, p, p, p, p, p, 0, p, acc, None) == -1                   # m != 3 is not built
+    assert b"m = 3" in L.slb_last_error()
+    assert L.slb_ekf_predict(1, None, p, p, p, None) == -1                                 # null pointer
+    assert L.slb_datamodel_safe_fuse(0, p, p, p, p, p, p, None) == 0
+    assert L.slb_transform_compose(-1, p, p, p, p, p, p, None) == -1
+    if not torch.cuda.is_available():
+        assert L.slb_ekf_predict(1, p, p, p, p, None) == -2
+        assert L.slb_datamodel_safe_fuse(1, p, p, p, p, p, p, None) == -2
+        assert L.slb_deadreckon_update_pose(1, C.c_double(0.01), p, p, p, p, p, p, p, p, p, None) == -2
+        assert b"no CPU fallback" in L.slb_last_error()
