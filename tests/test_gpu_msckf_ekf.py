@@ -95,3 +95,17 @@ def test_predict_then_ekf_update_replay(slo):
                                                gate=False)
     assert not f.status().any()
     assert_parity(slo, BLOCKS, f.mu(), symmetrize_lower(f.P()), mu_r, symmetrize_lower(P_r), tol=1e-7)
+
+
+def test_ekf_update_diagonal_nonconstant_R(slo):
+    """A diagonal but non-constant R takes the QR path with the row-scaling form of Q^T R Q."""
+    B = 8
+    sc = synth.msckf_scenario(B, seed=11, k=10, nfeat=50)
+    rng = np.random.default_rng(1)
+    sc = dict(sc, R=np.diag(np.diag(sc["R"]) * rng.uniform(0.5, 2.0, size=100)))
+    f, mu_r, P_r, out_r, st_r = _run(slo, sc, B, gate=True)
+    np.testing.assert_array_equal(f.outliers(), out_r)
+    np.testing.assert_array_equal(f.status(), st_r)
+    ok = st_r == 0
+    assert ok.any()
+    assert_parity(slo, BLOCKS, f.mu(), symmetrize_lower(f.P()), mu_r, symmetrize_lower(P_r), mask=ok)
