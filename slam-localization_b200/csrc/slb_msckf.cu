@@ -24,7 +24,7 @@
 
 namespace slbd {
 
-constexpr int MS_T = 256;          // threads per CTA
+constexpr int MS_T = 512;          // threads per CTA (16 warps: 126 registers, no spills; 256 -> 512 gave +10..13 %, 768 spills)
 constexpr int MS_W = MS_T / 32;
 constexpr int MS_NMAX = 72, MS_MMAX = 100, MS_NSMAX = 145;
 constexpr int MS_NSPAD = 148;                    // sigma-point count padded to the DMMA k-step
