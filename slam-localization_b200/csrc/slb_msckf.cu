@@ -159,11 +159,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         }
         // ---- sigma points through h (:229-232), thread per sigma point ---------------------------------
         // h = SLB_MM_MSCKF_REPROJ: feature f is landmark f seen from clone f % k (statek is not observed)
-        if (tid < NS) {
-            const int s = tid, j = s >= 1 ? (s - 1) >> 1 : 0;
+        // work item = (sigma point, clone): NS * k items over the whole CTA
+        for (int w = tid; w < NS * k; w += MS_T) {
+            const int s = w / k, c = w - s * k, j = s >= 1 ? (s - 1) >> 1 : 0;
             const double sgn = (s & 1) ? 1.0 : -1.0;
             double *Zr = RB + s * MS_ZS;
-            for (int c = 0; c < k; ++c) {
+            {
                 const int r0 = 12 + 6 * c;
                 double d[6];
 #pragma unroll
@@ -399,11 +400,11 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
         }
-        if (tid < NS) {
-            const int s = tid, j = s >= 1 ? (s - 1) >> 1 : 0;
+        for (int w = tid; w < NS * NB; w += MS_T) {   // work item = (sigma point, block)
+            const int s = w / NB, b = w - s * NB, j = s >= 1 ? (s - 1) >> 1 : 0;
             const double sgn = (s & 1) ? 1.0 : -1.0;
             double *X = RB + s * MS_QS;
-            for (int b = 0; b < NB; ++b) {
+            {
                 double d[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) d[r] = dl[3 * b + r] + ((s >= 1 && 3 * b + r >= j) ? sgn * RA[tri(3 * b + r, j)] : 0.0);
