@@ -544,6 +544,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
 // gain algebra is Pk -= Y Y^T, delta = Y (Ls^-1 nu).  The measurement model is SLB_MM_MSCKF_REPROJ with its analytic
 // Jacobian (d pc = -R^T dp + [pc]x dtheta); H has one 2 x 6 block per feature, which the H P H^T products exploit.
 // =====================================================================================================
+constexpr int ME_QP = MS_T / 80;  // threads sharing a column in the Householder phases (rows i = first + part mod QP)
 constexpr int ME_HS = 76;  // row stride of H / Q / covXZ (= 12 mod 16: conflict-free DMMA fragment loads)
 constexpr int ME_RA = 2632, ME_RS = 5056, ME_RH = MS_MMAX * ME_HS, ME_RQ = MS_MMAX * ME_HS, ME_RD = 2304;
 constexpr int ME_SMEM_DOUBLES = ME_RA + ME_RS + ME_RH + ME_RQ + ME_RD;
@@ -579,6 +580,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
     const int NP = N * (N + 1) / 2;
     const int nrt = (N + 7) >> 3;
     auto Psym = [&](int i, int j) { return i >= j ? RA[tri(i, j)] : RA[tri(j, i)]; };
+    constexpr int QP = ME_QP;
 
     for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         double *Pg = a.P + (size_t)inst * a.pstride;
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         if (tid < mk) RQ[tid * ME_HS + N] = nu[compact ? kept[tid] : tid];
         __syncthreads();
         // ---- reduceDimension (:794-816): Householder QR of RQ (mk x N) in place.  Per column: partial dot products
-        //      (three threads per column), sync, rank-1 update + the partial norms of the next column, sync, rescale of
+        //      (QP threads per column), sync, rank-1 update + the partial norms of the next column, sync, rescale of
         //      the finished column + the next reflector's scalars, sync ----------------------------------------------------
         auto reflector = [&](double c0, double t, double *out, int kcol) {  // Eigen makeHouseholderInPlace
             if (t <= 2.2250738585072014e-308) {
@@ -843,38 +845,41 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             const double *sk = scal + 4 * (kk & 1);
             const double tk = sk[0], sc = sk[1], beta = sk[2];
             const int part = tid / 80, jj = tid - part * 80, j = kk + 1 + jj;  // columns kk+1 .. N (N = innovation)
-            const bool act = part < 3 && j <= N;
+            const bool act = part < QP && j <= N;
             const int i0 = kk + 1 + part;                                    // rows i0, i0 + 3, ...
             if (tk != 0.0 && act) {
                 // essential part v = tail / (c0 - beta) is formed on the fly: column kk itself is rewritten last
                 const double *pv = RQ + i0 * ME_HS + kk, *pc = RQ + i0 * ME_HS + j;
                 double t0 = 0.0, t1 = 0.0;
                 int i = i0;
-                for (; i + 3 < mk; i += 6, pv += 6 * ME_HS, pc += 6 * ME_HS) {
+                for (; i + QP < mk; i += 2 * QP, pv += 2 * QP * ME_HS, pc += 2 * QP * ME_HS) {
                     t0 = fma(pv[0], pc[0], t0);
-                    t1 = fma(pv[3 * ME_HS], pc[3 * ME_HS], t1);
+                    t1 = fma(pv[QP * ME_HS], pc[QP * ME_HS], t1);
                 }
                 if (i < mk) t0 = fma(pv[0], pc[0], t0);
                 T3[part * 80 + jj] = t0 + t1;
-                if (part == 0) T3[240 + jj] = RQ[kk * ME_HS + j];  // row kk is rewritten by part 0 below
+                if (part == 0) T3[QP * 80 + jj] = RQ[kk * ME_HS + j];  // row kk is rewritten by part 0 below
             }
             __syncthreads();
             if (tk != 0.0 && act) {
-                const double tt = tk * fma(sc, (T3[jj] + T3[80 + jj]) + T3[160 + jj], T3[240 + jj]);
+                double dsum = 0.0;
+#pragma unroll
+                for (int q = 0; q < QP; ++q) dsum += T3[q * 80 + jj];
+                const double tt = tk * fma(sc, dsum, T3[QP * 80 + jj]);
                 const double ts = tt * sc;
                 const double *pv = RQ + i0 * ME_HS + kk;
                 double *pc = RQ + i0 * ME_HS + j;
-                for (int i = i0; i < mk; i += 3, pv += 3 * ME_HS, pc += 3 * ME_HS) pc[0] = fma(-ts, pv[0], pc[0]);
+                for (int i = i0; i < mk; i += QP, pv += QP * ME_HS, pc += QP * ME_HS) pc[0] = fma(-ts, pv[0], pc[0]);
                 if (part == 0) RQ[kk * ME_HS + j] -= tt;
             }
             // partial norms of the next column's tail (rows > kk+1), by the three threads that have just updated it
-            if (jj == 0 && part < 3 && kk + 1 < N) {
+            if (jj == 0 && part < QP && kk + 1 < N) {
                 double t = 0.0;
-                for (int i = i0 + (part == 0 ? 3 : 0); i < mk; i += 3) {
+                for (int i = i0 + (part == 0 ? QP : 0); i < mk; i += QP) {
                     const double v = RQ[i * ME_HS + kk + 1];
                     t = fma(v, v, t);
                 }
-                T3[300 + part] = t;
+                T3[(QP + 1) * 80 + part] = t;
             }
             __syncthreads();
             if (tk != 0.0) {
@@ -884,7 +889,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             }
             if (tid == 0) RQ[kk * ME_HS + kk] = beta;
             if (tid == 32 && kk + 1 < N)
-                reflector(RQ[(kk + 1) * ME_HS + kk + 1], (T3[300] + T3[301]) + T3[302], scal + 4 * ((kk + 1) & 1), kk + 1);
+                {
+                double nsum = 0.0;
+#pragma unroll
+                for (int q = 0; q < QP; ++q) nsum += T3[(QP + 1) * 80 + q];
+                reflector(RQ[(kk + 1) * ME_HS + kk + 1], nsum, scal + 4 * ((kk + 1) & 1), kk + 1);
+            }
             __syncthreads();
         }
         if (tid < N) nu[tid] = RQ[tid * ME_HS + N];   // Q^T nu, first N entries (:811)
@@ -899,26 +909,29 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             const double tk = tau[kk];
             if (tk != 0.0) {   // uniform
                 const int part = tid / 80, jj = tid - part * 80, j = kk + jj;
-                const bool act = part < 3 && j < N;
+                const bool act = part < QP && j < N;
                 const int i0 = kk + 1 + part;
                 if (act) {
                     const double *pv = RQ + i0 * ME_HS + kk, *pc = RH + i0 * ME_HS + j;
                     double t0 = 0.0, t1 = 0.0;
                     int i = i0;
-                    for (; i + 3 < mk; i += 6, pv += 6 * ME_HS, pc += 6 * ME_HS) {
+                    for (; i + QP < mk; i += 2 * QP, pv += 2 * QP * ME_HS, pc += 2 * QP * ME_HS) {
                         t0 = fma(pv[0], pc[0], t0);
-                        t1 = fma(pv[3 * ME_HS], pc[3 * ME_HS], t1);
+                        t1 = fma(pv[QP * ME_HS], pc[QP * ME_HS], t1);
                     }
                     if (i < mk) t0 = fma(pv[0], pc[0], t0);
                     T3[part * 80 + jj] = t0 + t1;
-                    if (part == 0) T3[240 + jj] = RH[kk * ME_HS + j];
+                    if (part == 0) T3[QP * 80 + jj] = RH[kk * ME_HS + j];
                 }
                 __syncthreads();
                 if (act) {
-                    const double tt = tk * ((T3[jj] + T3[80 + jj]) + T3[160 + jj] + T3[240 + jj]);
+                    double dsum = 0.0;
+#pragma unroll
+                    for (int q = 0; q < QP; ++q) dsum += T3[q * 80 + jj];
+                    const double tt = tk * (dsum + T3[QP * 80 + jj]);
                     const double *pv = RQ + i0 * ME_HS + kk;
                     double *pc = RH + i0 * ME_HS + j;
-                    for (int i = i0; i < mk; i += 3, pv += 3 * ME_HS, pc += 3 * ME_HS) pc[0] = fma(-tt, pv[0], pc[0]);
+                    for (int i = i0; i < mk; i += QP, pv += QP * ME_HS, pc += QP * ME_HS) pc[0] = fma(-tt, pv[0], pc[0]);
                     if (part == 0) RH[kk * ME_HS + j] -= tt;
                 }
                 __syncthreads();
