@@ -317,10 +317,15 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             continue;
         }
         // ---- Y = covXZ' Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates -----
+        // The innovation rides along as row N of the solve (kept in wv: region C has exactly N rows):
+        // [covXZ; nu^T] Ls^-T has w^T = (Ls^-1 nu)^T as its last row.
+        if (tid < mk) wv[tid] = nu[tid];
+        __syncthreads();
+        const int nrt2 = (N + 8) >> 3;
         for (int p0 = 0; p0 < mk; p0 += 8) {
             const int pb = min(8, mk - p0);
-            for (int i = tid; i < N; i += MS_T) {
-                double *row = Xz + i * MS_ZS + p0;
+            for (int i = tid; i <= N; i += MS_T) {
+                double *row = (i < N ? Xz + i * MS_ZS : wv) + p0;
                 double x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -336,33 +341,24 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
             __syncthreads();
             const int j0 = p0 + pb, nct = (mk - j0 + 7) >> 3;
-            for (int t = warp; t < nrt * nct; t += MS_W) {
+            for (int t = warp; t < nrt2 * nct; t += MS_W) {
                 const int tr = t / nct, tc = t - tr * nct;
                 const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
                 double d0 = 0.0, d1 = 0.0;
                 // tiles exist only after a full panel (pb == 8); rows / columns out of range are clamped (their outputs are dropped)
-                const double *pa = Xz + min(ai, N - 1) * MS_ZS + p0 + fk, *pb2 = Sp + tri(min(bj, mk - 1), p0) + fk;
+                double *yrow = ai < N ? Xz + ai * MS_ZS : wv;
+                const double *pa = yrow + p0 + fk, *pb2 = Sp + tri(min(bj, mk - 1), p0) + fk;
                 dmma884(d0, d1, pa[0], pb2[0]);
                 dmma884(d0, d1, pa[4], pb2[4]);
                 const int oc = j0 + 8 * tc + 2 * fk;
-                if (ai < N) {
-                    if (oc < mk) Xz[ai * MS_ZS + oc] -= d0;
-                    if (oc + 1 < mk) Xz[ai * MS_ZS + oc + 1] -= d1;
+                if (ai <= N) {
+                    if (oc < mk) yrow[oc] -= d0;
+                    if (oc + 1 < mk) yrow[oc + 1] -= d1;
                 }
             }
             __syncthreads();
         }
-        // ---- w = Ls^-1 nu (warp 0), delta = Y w ------------------------------------------------------
-        if (warp == 0) {
-            for (int q = 0; q < mk; ++q) {
-                const double wq = nu[q] * invd[q];
-                __syncwarp();
-                if (lane == 0) wv[q] = wq;
-                for (int c = q + 1 + lane; c < mk; c += 32) nu[c] -= Sp[tri(c, q)] * wq;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
+        // ---- delta = Y w, w = the extra row of the solve ---------------------------------------------------------
         for (int i = warp; i < N; i += MS_W) {
             double s = 0.0;
             for (int q = lane; q < mk; q += 32) s += Xz[i * MS_ZS + q] * wv[q];
@@ -1001,10 +997,15 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             continue;
         }
         }
-        // ---- Y = covXZ Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates --------------
+        // ---- Y = covXZ Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates.  The innovation
+        //      rides along as row N: [covXZ; nu^T] Ls^-T has w^T = (Ls^-1 nu)^T as its last row, so the forward substitution
+        //      for w costs nothing extra (it used to be 100 sequential steps on one warp with the CTA waiting) ---------------
+        if (tid < mq) Yb[N * ys + tid] = nu[tid];
+        __syncthreads();
+        const int nrt2 = (N + 8) >> 3;   // row tiles including row N
         for (int p0 = 0; p0 < mq; p0 += 8) {
             const int pb = min(8, mq - p0);
-            for (int i = tid; i < N; i += MS_T) {
+            for (int i = tid; i <= N; i += MS_T) {
                 double *row = Yb + i * ys + p0;
                 double x[8];
 #pragma unroll
@@ -1021,35 +1022,26 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             }
             __syncthreads();
             const int j0 = p0 + pb, nct = (mq - j0 + 7) >> 3;
-            for (int t = warp; t < nrt * nct; t += MS_W) {
+            for (int t = warp; t < nrt2 * nct; t += MS_W) {
                 const int tr = t / nct, tc = t - tr * nct;
                 const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
                 double d0 = 0.0, d1 = 0.0;
-                const double *pa = Yb + min(ai, N - 1) * ys + p0 + fk, *pb2 = RS + tri(min(bj, mq - 1), p0) + fk;
+                const double *pa = Yb + min(ai, N) * ys + p0 + fk, *pb2 = RS + tri(min(bj, mq - 1), p0) + fk;
                 dmma884(d0, d1, pa[0], pb2[0]);
                 dmma884(d0, d1, pa[4], pb2[4]);
                 const int oc = j0 + 8 * tc + 2 * fk;
-                if (ai < N) {
+                if (ai <= N) {
                     if (oc < mq) Yb[ai * ys + oc] -= d0;
                     if (oc + 1 < mq) Yb[ai * ys + oc + 1] -= d1;
                 }
             }
             __syncthreads();
         }
-        // ---- w = Ls^-1 nu' (warp 0), delta = Y w (:337) ----------------------------------------------------------
-        if (warp == 0) {
-            for (int q = 0; q < mq; ++q) {
-                const double wq = nu[q] * invd[q];
-                __syncwarp();
-                if (lane == 0) wv[q] = wq;
-                for (int c = q + 1 + lane; c < mq; c += 32) nu[c] -= RS[tri(c, q)] * wq;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
+        // ---- delta = Y w (:337), w = row N of the solve ---------------------------------------------------------------
         for (int i = warp; i < N; i += MS_W) {
             double sacc = 0.0;
-            for (int q = lane; q < mq; q += 32) sacc += Yb[i * ys + q] * wv[q];
+            const double *wrow = Yb + N * ys;
+            for (int q = lane; q < mq; q += 32) sacc += Yb[i * ys + q] * wrow[q];
             sacc = warp_sum(sacc);
             if (lane == 0) dl[i] = sacc;
         }
