@@ -1,4 +1,4 @@
-set -x
+set +x
 timeout 900 python -m pytest tests/test_gpu_msckf.py tests/test_gpu_msckf_ekf.py -m gpu -x -q 2>&1 | tail -3
 for w in msckf msckf_ekf; do
 timeout 600 python bench.py --workload $w --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/tmp_bench.json 2>/dev/null

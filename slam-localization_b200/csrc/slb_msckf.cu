@@ -55,36 +55,44 @@ SLB_DEV void tri_tile(int t, int &tr, int &tc) {
 SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
+    auto factor_diag = [&](int p0) {
+        const int pb = min(8, n - p0);
+        // square-root-free and right-looking: u_ic -= (u_ik / d_k) u_ck keeps one shuffle + one reciprocal per
+        // column on the dependent chain (the other shuffles overlap the reciprocal); the 1/sqrt(d_k) scaling that
+        // turns U into L is applied to all columns at once afterwards
+        double u[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) u[c] = (lane < pb && c <= lane) ? A[tri(p0 + lane, p0 + c)] : 0.0;
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const double d = bcast(u[k], k);
+            if (k < pb) {
+                ok = ok && (d > 0.0);
+                const double v = u[k] * rcp_fast(d);
+#pragma unroll
+                for (int c = k + 1; c < 8; ++c) u[c] = fma(-v, bcast(u[k], c), u[c]);
+            }
+        }
+        double dg = 1.0, sx, inv;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (lane == c && c < pb) dg = u[c];
+        ok = ok && (dg > 0.0);
+        sqrt_rsqrt(dg, sx, inv);
+        if (lane < pb) invd[p0 + lane] = inv;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double ic = bcast(inv, c);
+            if (lane < pb && c <= lane) A[tri(p0 + lane, p0 + c)] = (c == lane) ? sx : u[c] * ic;
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok && lane == 0) *ok_flag = 0;
+    };
+    if (warp == 0) factor_diag(0);
+    __syncthreads();
     for (int p0 = 0; p0 < n; p0 += 8) {
         const int pb = min(8, n - p0);
-        if (warp == 0) {
-            double row[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) row[c] = (lane < pb && c <= lane) ? A[tri(p0 + lane, p0 + c)] : 0.0;
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                double sk = row[k];
-#pragma unroll
-                for (int p = 0; p < 8; ++p)
-                    if (p < k) sk = fma(-row[p], bcast(row[p], k), sk);
-                const double x = bcast(sk, k);
-                if (k < pb) {
-                    ok = ok && (x > 0.0);
-                    double sx, inv;
-                    sqrt_rsqrt(x, sx, inv);
-                    row[k] = (lane == k) ? sx : sk * inv;
-                    if (lane == 0) invd[p0 + k] = inv;
-                }
-            }
-            if (lane < pb) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c <= lane) A[tri(p0 + lane, p0 + c)] = row[c];
-            }
-            if (!ok && lane == 0) *ok_flag = 0;
-        }
-        __syncthreads();
         const int r0 = p0 + pb;
         for (int i = r0 + tid; i < n; i += MS_T) {
             double x[8];
@@ -118,6 +126,10 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
                 if (j <= i) A[tri(i, j)] -= d0;
                 if (j + 1 <= i) A[tri(i, j + 1)] -= d1;
             }
+            if (t == 0) {  // look-ahead: warp 0 owns the next diagonal block and factors it while the others update
+                __syncwarp();
+                factor_diag(r0);
+            }
         }
         __syncthreads();
     }
@@ -125,6 +137,29 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
 
 // Multi-state q-vector: statek (pos quat velo angvelo) then k sensor poses (pos quat).
 // Block b of the tangent space: 0..3 = statek blocks, 4+2c / 5+2c = pos / orient of clone c.
+// removeRow(2i); removeRow(2i+1) of the reference's gate loop applied to the index list kept[0..len) by one warp;
+// the second index is NOT re-based (quirk Q6).  Returns the new length.
+SLB_DEV int gate_remove_pair(int *kept, int len, int i, int lane) {
+    for (int pass = 0; pass < 2; ++pass) {
+        const int pos = 2 * i + pass, num = len - 1;
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = pos + lane + 32 * q;
+            v[q] = e < num ? kept[e + 1] : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = pos + lane + 32 * q;
+            if (e < num) kept[e] = v[q];
+        }
+        __syncwarp();
+        len = num;
+    }
+    return len;
+}
+
 SLB_DEV int ms_qoff(int b) { return b < 4 ? (b == 0 ? 0 : b == 1 ? 3 : b == 2 ? 7 : 10) : 13 + 7 * ((b - 4) >> 1) + (((b - 4) & 1) ? 3 : 0); }
 SLB_DEV bool ms_so3(int b) { return b < 4 ? b == 1 : ((b - 4) & 1); }
 
@@ -262,30 +297,33 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 const double m2 = (v0 * (s11 * v0 - s10 * v1) + v1 * (s00 * v1 - s10 * v0)) / det;
                 rej = !(m2 < 5.99);
             }
-            if (__syncthreads_or(rej) && tid == 0) {
+            if (__syncthreads_or(rej) && warp == 0) {
+                // the reference's sequential scan, 32 positions at a time: every lane tests one position against the
+                // current index list, the first rejection (if any) is applied, and the scan resumes from there
                 int len = M, out = 0, i = 0;
-                for (int e = 0; e < M; ++e) kept[e] = e;
+                for (int e = lane; e < M; e += 32) kept[e] = e;
+                __syncwarp();
                 while (i < len / 2) {
-                    const int ia = kept[2 * i], ib = kept[2 * i + 1];
-                    const double s00 = RA[tri(ia, ia)], s11 = RA[tri(ib, ib)], s10 = ib > ia ? RA[tri(ib, ia)] : RA[tri(ia, ib)];
-                    const double det = s00 * s11 - s10 * s10;
-                    const double v0 = nu[ia], v1 = nu[ib];
-                    const double m2 = (v0 * (s11 * v0 - s10 * v1) + v1 * (s00 * v1 - s10 * v0)) / det;
-                    if (!(m2 < 5.99)) {
-                        // removeRow(2i); removeRow(2i+1) -- the second index is NOT re-based (Q6)
-                        for (int pass = 0; pass < 2; ++pass) {
-                            const int pos = 2 * i + pass, num = len - 1;
-                            if (pos < num)
-                                for (int e = pos; e < num; ++e) kept[e] = kept[e + 1];
-                            len = num;
-                        }
-                        ++out;
-                    } else {
-                        ++i;
+                    const int ii = i + lane;
+                    bool rj = false;
+                    if (ii < len / 2) {
+                        const int ia = kept[2 * ii], ib = kept[2 * ii + 1];
+                        const double s00 = RA[tri(ia, ia)], s11 = RA[tri(ib, ib)], s10 = ib > ia ? RA[tri(ib, ia)] : RA[tri(ia, ib)];
+                        const double det = s00 * s11 - s10 * s10;
+                        const double v0 = nu[ia], v1 = nu[ib];
+                        const double m2 = (v0 * (s11 * v0 - s10 * v1) + v1 * (s00 * v1 - s10 * v0)) / det;
+                        rj = !(m2 < 5.99);
                     }
+                    const unsigned bal = __ballot_sync(0xffffffffu, rj);
+                    if (!bal) {
+                        i += 32;
+                        continue;
+                    }
+                    i += __ffs(bal) - 1;
+                    len = gate_remove_pair(kept, len, i, lane);
+                    ++out;
                 }
-                flags[1] = len;
-                flags[2] = out;
+                if (lane == 0) { flags[1] = len; flags[2] = out; }
             }
         }
         __syncthreads();
@@ -468,10 +506,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 }
             }
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 double n2 = 0.0;
-                for (int e = 0; e < N; ++e) n2 += dl[e] * dl[e];
-                flags[3] = (sqrt(n2) > 1e-6 && ++flags[4] < 10000) ? 1 : 0;
+                for (int e = lane; e < N; e += 32) n2 = fma(dl[e], dl[e], n2);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+                if (lane == 0) flags[3] = (sqrt(n2) > 1e-6 && ++flags[4] < 10000) ? 1 : 0;
             }
             __syncthreads();
             if (!flags[3]) break;
@@ -724,27 +764,29 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 rej = !(m2 < 5.99);
             }
             // while nothing is rejected the sequential scan keeps the identity indexing: "all accepted" needs no scan
-            if (__syncthreads_or(rej) && tid == 0) {
+            if (__syncthreads_or(rej) && warp == 0) {
                 int len = M, out = 0, i = 0;
-                for (int e = 0; e < M; ++e) kept[e] = e;
-                while (i < len / 2) {
-                    const double v0 = nu[kept[2 * i]], v1 = nu[kept[2 * i + 1]];
-                    const double i00 = info[3 * i], i10 = info[3 * i + 1], i11 = info[3 * i + 2];  // position, not feature (:773)
-                    const double m2 = v0 * (i00 * v0 + i10 * v1) + v1 * (i10 * v0 + i11 * v1);
-                    if (!(m2 < 5.99)) {
-                        for (int pass = 0; pass < 2; ++pass) {  // removeRow(2i); removeRow(2i+1): not re-based (Q6)
-                            const int pos = 2 * i + pass, num = len - 1;
-                            if (pos < num)
-                                for (int e = pos; e < num; ++e) kept[e] = kept[e + 1];
-                            len = num;
-                        }
-                        ++out;
-                    } else {
-                        ++i;
+                for (int e = lane; e < M; e += 32) kept[e] = e;
+                __syncwarp();
+                while (i < len / 2) {  // 32 scan positions per round, the first rejection is applied (see the UKF flavour)
+                    const int ii = i + lane;
+                    bool rj = false;
+                    if (ii < len / 2) {
+                        const double v0 = nu[kept[2 * ii]], v1 = nu[kept[2 * ii + 1]];
+                        const double i00 = info[3 * ii], i10 = info[3 * ii + 1], i11 = info[3 * ii + 2];  // position, not feature (:773)
+                        const double m2 = v0 * (i00 * v0 + i10 * v1) + v1 * (i10 * v0 + i11 * v1);
+                        rj = !(m2 < 5.99);
                     }
+                    const unsigned bal = __ballot_sync(0xffffffffu, rj);
+                    if (!bal) {
+                        i += 32;
+                        continue;
+                    }
+                    i += __ffs(bal) - 1;
+                    len = gate_remove_pair(kept, len, i, lane);  // removeRow(2i); removeRow(2i+1): not re-based (Q6)
+                    ++out;
                 }
-                flags[1] = len;
-                flags[2] = out;
+                if (lane == 0) { flags[1] = len; flags[2] = out; }
             }
             __syncthreads();
             mk = flags[1];
