@@ -39,12 +39,24 @@ static_assert(MS_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF update working set excee
 static_assert(MS_NSPAD * MS_QS <= MS_B, "sigma points do not fit region B");
 static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_B, "compacted S does not fit region B");
 
-// linear index of a lower-triangular tile -> (tr, tc), tc <= tr
+// linear index of a lower-triangular tile -> (tr, tc), tc <= tr: a constant-memory table (the index is warp-uniform,
+// so the lookup is one broadcast load instead of a sqrtf + fix-up per tile)
+struct TileTab {
+    unsigned char tr[128], tc[128];   // 13 tile rows (m = 100) need 91 entries
+    constexpr TileTab() : tr(), tc() {
+        int r = 0, c = 0;
+        for (int t = 0; t < 128; ++t) {
+            tr[t] = (unsigned char)r;
+            tc[t] = (unsigned char)c;
+            if (++c > r) { c = 0; ++r; }
+        }
+    }
+};
+__constant__ TileTab tile_tab = TileTab();
+static_assert((MS_MMAX + 7) / 8 * ((MS_MMAX + 7) / 8 + 1) / 2 <= 128, "tile table too small");
 SLB_DEV void tri_tile(int t, int &tr, int &tc) {
-    int r = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-    r += (tri(r + 1, 0) <= t) - (tri(r, 0) > t);
-    tr = r;
-    tc = t - tri(r, 0);
+    tr = tile_tab.tr[t];
+    tc = tile_tab.tc[t];
 }
 
 // In-place Cholesky of a packed lower matrix in shared memory, all threads of the CTA.  Blocked right-looking
@@ -176,14 +188,20 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
     const int NP = N * (N + 1) / 2;
     const int nrt = (N + 7) >> 3;                     // 8-row tiles of the state
 
+    bool fetched = false;   // CTA-uniform: region A already holds (or is receiving) this instance's record
     for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         double *Pg = a.P + (size_t)inst * a.pstride;
         double *mug = a.mu + (size_t)inst * a.qstride;
         const double *zg = a.z + (size_t)inst * M;
         __syncthreads();
-        for (int e = tid; e < NP; e += MS_T) RA[e] = Pg[e];
+        // the record was fetched into region A during the tail of the previous instance (see below) unless that one
+        // left early; cp.async keeps every load of the record in flight at once
+        if (!fetched)
+            for (int e = tid; e < NP; e += MS_T) pred_cp_async8(RA + e, Pg + e);
+        fetched = false;
         for (int e = tid; e < QD; e += MS_T) mu[e] = mug[e];
         if (tid == 0) { flags[0] = 1; flags[1] = M; flags[2] = 0; }
+        pred_cp_async_wait_all();
         __syncthreads();
         // ---- L = chol(Pk) (:229 -> :412) -------------------------------------------------------------
         chol_blocked(RA, N, flags, invd);
@@ -413,6 +431,9 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 const int ai = 8 * tr + fr;
                 const double *pa = Xz + min(ai, N - 1) * MS_ZS + fk, *pb = Xz + min(8 * tc + fr, N - 1) * MS_ZS + fk;
                 double d0 = 0.0, d1 = 0.0;
+                const int r = ai, c = 8 * tc + 2 * fk;
+                // the record's entries are requested before the k-loop so that their L2 latency hides behind it
+                const double g0 = (r < N && c <= r) ? Pg[tri(r, c)] : 0.0, g1 = (r < N && c + 1 <= r) ? Pg[tri(r, c + 1)] : 0.0;
                 const int kfull = mk & ~3;   // mk is even: at most one ragged k-step
 #pragma unroll 4
                 for (int k0 = 0; k0 < kfull; k0 += 4) dmma884(d0, d1, pa[k0], pb[k0]);
@@ -420,10 +441,9 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                     const bool in = kfull + fk < mk;
                     dmma884(d0, d1, in ? pa[kfull] : 0.0, in ? pb[kfull] : 0.0);
                 }
-                const int r = ai, c = 8 * tc + 2 * fk;
                 if (r < N) {
-                    if (c <= r) RA[tri(r, c)] = Pg[tri(r, c)] - d0;
-                    if (c + 1 <= r) RA[tri(r, c + 1)] = Pg[tri(r, c + 1)] - d1;
+                    if (c <= r) RA[tri(r, c)] = g0 - d0;
+                    if (c + 1 <= r) RA[tri(r, c + 1)] = g1 - d1;
                 }
             }
         }
@@ -454,6 +474,13 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
+        // L2 is dead from here on: fetch the next instance's covariance record into region A behind the mean,
+        // deviation and covariance phases of this one
+        if (inst + (int)gridDim.x < a.B) {
+            const double *Pn = a.P + (size_t)(inst + gridDim.x) * a.pstride;
+            for (int e = tid; e < NP; e += MS_T) pred_cp_async8(RA + e, Pn + e);
+            fetched = true;
+        }
         // manifold mean (:499-525): ref = X0; do { d = mean(Xi [-] ref); ref [+]= d } while (|d| > 1e-6 ...)
         for (int e = tid; e < QD; e += MS_T) ref[e] = RB[e];
         if (tid == 0) flags[4] = 0;
