@@ -61,12 +61,18 @@ SLB_DEV void tri_tile(int t, int &tr, int &tc) {
 
 // In-place Cholesky of a packed lower matrix in shared memory, all threads of the CTA.  Blocked right-looking
 // with 8-wide panels: warp 0 factors the 8x8 diagonal block (lane per row, shuffle broadcasts), one thread per
-// row solves the panel below it, then every warp rank-8-updates its share of the trailing 8x8 tiles with two
-// DMMAs each.  invd[i] = 1 / L_ii is left for the triangular solves.  ok_flag (shared int) is cleared on a
-// non-positive pivot (Eigen::LLT's info(), which the reference ignores: quirk Q8).
-SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
+// row solves the panel below it, then the other warps rank-8-update the trailing 8x8 tiles with two DMMAs each
+// while warp 0 already factors the next diagonal block (look-ahead).  invd[i] = 1 / L_ii is left for later
+// triangular solves.  ok_flag (shared int) is cleared on a non-positive pivot (Eigen::LLT's info(), which the
+// reference ignores: quirk Q8).
+// Optional right-hand sides: nx rows X (row stride xs) plus one more row xe are carried through the same panel
+// solves and trailing updates, i.e. on return [X; xe] holds [X; xe] L^-T -- the triangular solve a Cholesky is
+// usually followed by, without its own serial panel chain and barriers.
+SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *X = nullptr, int nx = 0, int xs = 0,
+                          double *xe = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
+    const int nxr = X ? nx + 1 : 0, nxt = (nxr + 7) >> 3;
     auto factor_diag = [&](int p0) {
         const int pb = min(8, n - p0);
         // square-root-free and right-looking: u_ic -= (u_ik / d_k) u_ck keeps one shuffle + one reciprocal per
@@ -105,10 +111,10 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
     __syncthreads();
     for (int p0 = 0; p0 < n; p0 += 8) {
         const int pb = min(8, n - p0);
-        const int r0 = p0 + pb;
-        for (int i = r0 + tid; i < n; i += MS_T) {
+        const int r0 = p0 + pb, na = n - r0;
+        for (int w = tid; w < na + nxr; w += MS_T) {
             double x[8];
-            double *Ai = A + tri(i, p0);
+            double *Ai = w < na ? A + tri(r0 + w, p0) : (w - na < nx ? X + (w - na) * xs : xe) + p0;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 if (c < pb) {
@@ -122,14 +128,14 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
             }
         }
         __syncthreads();
-        const int nt = (n - r0 + 7) >> 3, ntiles = nt * (nt + 1) / 2;
-        for (int t = warp; t < ntiles; t += MS_W) {
+        // rows / columns beyond the matrix only feed accumulator entries that are never stored: their addresses are clamped,
+        // not masked; a trailing update only exists after a full 8-wide panel (pb == 8), so the k-loop needs no bound either
+        const int nt = (na + 7) >> 3, ntiles = nt * (nt + 1) / 2;
+        auto a_tile = [&](int t) {
             int tr, tc;
             tri_tile(t, tr, tc);
             const int i0 = r0 + 8 * tr, j0 = r0 + 8 * tc;
             double d0 = 0.0, d1 = 0.0;
-            // rows beyond n only feed accumulator entries that are never stored: their addresses are clamped, not masked;
-            // a trailing update only exists after a full 8-wide panel (pb == 8), so the k-loop needs no bound either
             const double *pa = A + tri(min(i0 + fr, n - 1), p0) + fk, *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
             dmma884(d0, d1, pa[0], pb2[0]);
             dmma884(d0, d1, pa[4], pb2[4]);
@@ -138,17 +144,38 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd) {
                 if (j <= i) A[tri(i, j)] -= d0;
                 if (j + 1 <= i) A[tri(i, j + 1)] -= d1;
             }
-            if (t == 0) {  // look-ahead: warp 0 owns the next diagonal block and factors it while the others update
+        };
+        if (warp == 0) {
+            if (ntiles > 0) {  // look-ahead: warp 0 owns the next diagonal block and factors it while the others update
+                a_tile(0);
                 __syncwarp();
                 factor_diag(r0);
+            }
+        } else {
+            for (int t = warp; t < ntiles + nxt * nt; t += MS_W - 1) {
+                if (t < ntiles) {
+                    a_tile(t);
+                } else {
+                    const int u = t - ntiles, tr = u / nt, tc = u - tr * nt;
+                    const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;
+                    const int ac = min(ai, nxr - 1);
+                    double *xrow = ac < nx ? X + ac * xs : xe;
+                    double d0 = 0.0, d1 = 0.0;
+                    const double *pa = xrow + p0 + fk, *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
+                    dmma884(d0, d1, pa[0], pb2[0]);
+                    dmma884(d0, d1, pa[4], pb2[4]);
+                    const int oc = j0 + 2 * fk;
+                    if (ai < nxr) {
+                        if (oc < n) xrow[oc] -= d0;
+                        if (oc + 1 < n) xrow[oc + 1] -= d1;
+                    }
+                }
             }
         }
         __syncthreads();
     }
 }
 
-// Multi-state q-vector: statek (pos quat velo angvelo) then k sensor poses (pos quat).
-// Block b of the tangent space: 0..3 = statek blocks, 4+2c / 5+2c = pos / orient of clone c.
 // removeRow(2i); removeRow(2i+1) of the reference's gate loop applied to the index list kept[0..len) by one warp;
 // the second index is NOT re-based (quirk Q6).  Returns the new length.
 SLB_DEV int gate_remove_pair(int *kept, int len, int i, int lane) {
@@ -366,53 +393,15 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             Sp = RB;
             __syncthreads();
         }
-        // ---- Ls = chol(S') -------------------------------------------------------------------------------
-        chol_blocked(Sp, mk, flags, invd);
+        // ---- Ls = chol(S') and Y = covXZ' Ls^-T in one sweep: the rows of covXZ' are carried through the panel solves and
+        //      trailing updates of the factorisation.  The innovation rides along as one more row (kept in wv: region C has
+        //      exactly N rows): [covXZ; nu^T] Ls^-T has w^T = (Ls^-1 nu)^T as its last row.
+        if (tid < mk) wv[tid] = nu[tid];
+        __syncthreads();
+        chol_blocked(Sp, mk, flags, invd, Xz, N, MS_ZS, wv);
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
-        }
-        // ---- Y = covXZ' Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates -----
-        // The innovation rides along as row N of the solve (kept in wv: region C has exactly N rows):
-        // [covXZ; nu^T] Ls^-T has w^T = (Ls^-1 nu)^T as its last row.
-        if (tid < mk) wv[tid] = nu[tid];
-        __syncthreads();
-        const int nrt2 = (N + 8) >> 3;
-        for (int p0 = 0; p0 < mk; p0 += 8) {
-            const int pb = min(8, mk - p0);
-            for (int i = tid; i <= N; i += MS_T) {
-                double *row = (i < N ? Xz + i * MS_ZS : wv) + p0;
-                double x[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c < pb) {
-                        double sv = row[c];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q < c) sv = fma(-x[q], Sp[tri(p0 + c, p0 + q)], sv);
-                        x[c] = sv * invd[p0 + c];
-                        row[c] = x[c];
-                    }
-                }
-            }
-            __syncthreads();
-            const int j0 = p0 + pb, nct = (mk - j0 + 7) >> 3;
-            for (int t = warp; t < nrt2 * nct; t += MS_W) {
-                const int tr = t / nct, tc = t - tr * nct;
-                const int ai = 8 * tr + fr, bj = j0 + 8 * tc + fr;
-                double d0 = 0.0, d1 = 0.0;
-                // tiles exist only after a full panel (pb == 8); rows / columns out of range are clamped (their outputs are dropped)
-                double *yrow = ai < N ? Xz + ai * MS_ZS : wv;
-                const double *pa = yrow + p0 + fk, *pb2 = Sp + tri(min(bj, mk - 1), p0) + fk;
-                dmma884(d0, d1, pa[0], pb2[0]);
-                dmma884(d0, d1, pa[4], pb2[4]);
-                const int oc = j0 + 8 * tc + 2 * fk;
-                if (ai <= N) {
-                    if (oc < mk) yrow[oc] -= d0;
-                    if (oc + 1 < mk) yrow[oc + 1] -= d1;
-                }
-            }
-            __syncthreads();
         }
         // ---- delta = Y w, w = the extra row of the solve ---------------------------------------------------------
         for (int i = warp; i < N; i += MS_W) {
@@ -833,6 +822,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         const bool direct = a.misc[1] != 0;
         double *Yb = RH;   // Y = covXZ Ls^-T: base, row stride, number of measurement rows it was solved against
         int ys = ME_HS, mq = N;
+        bool solved = false;   // the triangular solve was folded into the factorisation (chol_blocked with right-hand sides)
         if (direct) {
             Yb = RQ; ys = MS_ZS; mq = mk;
             // covXZ' = P Hc^T (N x mk) into RQ (the triangular inverse that lived there is consumed): 6 FMA per entry
@@ -846,7 +836,10 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             }
             if (tid < mk) wv[tid] = nu[compact ? kept[tid] : tid];
             __syncthreads();
-            if (tid < mk) nu[tid] = wv[tid];
+            if (tid < mk) {
+                nu[tid] = wv[tid];
+                Yb[N * ys + tid] = wv[tid];   // the innovation rides along as row N of the solve (see below)
+            }
             if (compact || !a.gate) {
                 // S' = Hc covXZ' + R' (packed lower) and its Cholesky factor; otherwise RS still holds chol(S) from the gate
                 for (int e = tid; e < mk * (mk + 1) / 2; e += MS_T) {
@@ -861,7 +854,8 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                     RS[e] = sacc;
                 }
                 __syncthreads();
-                chol_blocked(RS, mk, flags, invd);
+                chol_blocked(RS, mk, flags, invd, Yb, N, ys, Yb + N * ys);
+                solved = true;
                 if (!flags[0]) {
                     if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
                     continue;
@@ -1060,7 +1054,9 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             RS[e] = sacc;
         }
         __syncthreads();
-        chol_blocked(RS, N, flags, invd);
+        if (tid < mq) Yb[N * ys + tid] = nu[tid];
+        chol_blocked(RS, N, flags, invd, Yb, N, ys, Yb + N * ys);
+        solved = true;
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
@@ -1069,10 +1065,10 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         // ---- Y = covXZ Ls^-T: blocked right-looking TRSM, 8-column panels (thread per row), DMMA updates.  The innovation
         //      rides along as row N: [covXZ; nu^T] Ls^-T has w^T = (Ls^-1 nu)^T as its last row, so the forward substitution
         //      for w costs nothing extra (it used to be 100 sequential steps on one warp with the CTA waiting) ---------------
-        if (tid < mq) Yb[N * ys + tid] = nu[tid];
-        __syncthreads();
+        //      When S had to be factored anew, chol_blocked has already carried these rows along; what follows is the
+        //      stand-alone solve against the factor that the outlier gate left behind.
         const int nrt2 = (N + 8) >> 3;   // row tiles including row N
-        for (int p0 = 0; p0 < mq; p0 += 8) {
+        for (int p0 = 0; p0 < (solved ? 0 : mq); p0 += 8) {
             const int pb = min(8, mq - p0);
             for (int i = tid; i <= N; i += MS_T) {
                 double *row = Yb + i * ys + p0;
