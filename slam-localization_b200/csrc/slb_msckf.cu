@@ -68,8 +68,11 @@ SLB_DEV void tri_tile(int t, int &tr, int &tc) {
 // Optional right-hand sides: nx rows X (row stride xs) plus one more row xe are carried through the same panel
 // solves and trailing updates, i.e. on return [X; xe] holds [X; xe] L^-T -- the triangular solve a Cholesky is
 // usually followed by, without its own serial panel chain and barriers.
+// Optional inverse factor: Wp (packed lower, preset to the identity by the caller) is treated as the right-hand side
+// I stored transposed -- row i of the right-hand side is column i of Wp -- so that it ends up as I L^-T transposed,
+// i.e. Wp = L^-1.  Only the tiles that can be non-zero (row tile <= current panel) are touched.
 SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *X = nullptr, int nx = 0, int xs = 0,
-                          double *xe = nullptr) {
+                          double *xe = nullptr, double *Wp = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     const int nxr = X ? nx + 1 : 0, nxt = (nxr + 7) >> 3;
@@ -112,18 +115,35 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
     for (int p0 = 0; p0 < n; p0 += 8) {
         const int pb = min(8, n - p0);
         const int r0 = p0 + pb, na = n - r0;
-        for (int w = tid; w < na + nxr; w += MS_T) {
+        const int nwr = Wp ? r0 : 0;   // rows of the identity right-hand side that can be non-zero in this panel
+        for (int w = tid; w < na + nxr + nwr; w += MS_T) {
             double x[8];
-            double *Ai = w < na ? A + tri(r0 + w, p0) : (w - na < nx ? X + (w - na) * xs : xe) + p0;
+            if (w < na + nxr) {
+                double *Ai = w < na ? A + tri(r0 + w, p0) : (w - na < nx ? X + (w - na) * xs : xe) + p0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c < pb) {
-                    double sv = Ai[c];
+                for (int c = 0; c < 8; ++c) {
+                    if (c < pb) {
+                        double sv = Ai[c];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (q < c) sv = fma(-x[q], A[tri(p0 + c, p0 + q)], sv);
-                    x[c] = sv * invd[p0 + c];
-                    Ai[c] = x[c];
+                        for (int q = 0; q < 8; ++q)
+                            if (q < c) sv = fma(-x[q], A[tri(p0 + c, p0 + q)], sv);
+                        x[c] = sv * invd[p0 + c];
+                        Ai[c] = x[c];
+                    }
+                }
+            } else {
+                const int i = w - na - nxr;   // entries (i, col) with col < i are structural zeros and are not stored
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < pb) {
+                        const int col = p0 + c;
+                        double sv = col >= i ? Wp[tri(col, i)] : 0.0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q < c) sv = fma(-x[q], A[tri(p0 + c, p0 + q)], sv);
+                        x[c] = sv * invd[col];
+                        if (col >= i) Wp[tri(col, i)] = x[c];
+                    }
                 }
             }
         }
@@ -152,9 +172,21 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                 factor_diag(r0);
             }
         } else {
-            for (int t = warp; t < ntiles + nxt * nt; t += MS_W - 1) {
+            const int nwt = Wp ? (p0 >> 3) + 1 : 0;   // row tiles of the identity right-hand side reached so far
+            for (int t = warp; t < ntiles + (nxt + nwt) * nt; t += MS_W - 1) {
                 if (t < ntiles) {
                     a_tile(t);
+                } else if (t >= ntiles + nxt * nt) {
+                    const int u = t - ntiles - nxt * nt, tr = u / nt, tc = u - tr * nt;
+                    const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;   // ai <= p0 + 7 < n
+                    double d0 = 0.0, d1 = 0.0;
+                    const double *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
+                    const int k0 = p0 + fk, k1 = k0 + 4;
+                    dmma884(d0, d1, k0 >= ai ? Wp[tri(k0, ai)] : 0.0, pb2[0]);
+                    dmma884(d0, d1, k1 >= ai ? Wp[tri(k1, ai)] : 0.0, pb2[4]);
+                    const int oc = j0 + 2 * fk;   // > ai: always inside the stored triangle
+                    if (oc < n) Wp[tri(oc, ai)] -= d0;
+                    if (oc + 1 < n) Wp[tri(oc + 1, ai)] -= d1;
                 } else {
                     const int u = t - ntiles, tr = u / nt, tc = u - tr * nt;
                     const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;
@@ -472,45 +504,44 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         }
         // manifold mean (:499-525): ref = X0; do { d = mean(Xi [-] ref); ref [+]= d } while (|d| > 1e-6 ...)
         for (int e = tid; e < QD; e += MS_T) ref[e] = RB[e];
-        if (tid == 0) flags[4] = 0;
         __syncthreads();
-        // per-warp partial sums go to region C (Y is dead) and are added in warp order: the result of an
-        // instance must not depend on scheduling (bitwise reproducible across batch sizes and GPUs)
+        // Work item = (block b, group g): group g sums X_s [-] ref over the sigma points s = g, g + G, ... in that order and
+        // parks its partial in region C (Y is dead); the partials are then added in group order, so the result of an
+        // instance does not depend on scheduling (bitwise reproducible across batch sizes and GPUs).
         double *part = RC;
-        const int nwa = (NS + 31) / 32;
+        const int G = min(MS_T / NB, 32);
+        const int mb = tid / G, mg = tid - mb * G;
+        int iters = 0;
         while (true) {
-            for (int b = 0; b < NB; ++b) {
-                double d[3] = {0.0, 0.0, 0.0};
-                if (tid < NS) {
-                    const double *X = RB + tid * MS_QS;
-                    const int qo = ms_qoff(b);
-                    if (ms_so3(b)) {
-                        double r[4];
-                        quat_cmul(ref + qo, X + qo, r);
+            if (mb < NB) {
+                const int qo = ms_qoff(mb);
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                if (ms_so3(mb)) {
+                    for (int sp = mg; sp < NS; sp += G) {
+                        double r[4], d[3];
+                        quat_cmul(ref + qo, RB + sp * MS_QS + qo, r);
                         so3_log(r, d);
-                    } else {
-                        d[0] = X[qo] - ref[qo]; d[1] = X[qo + 1] - ref[qo + 1]; d[2] = X[qo + 2] - ref[qo + 2];
+                        s0 += d[0]; s1 += d[1]; s2 += d[2];
+                    }
+                } else {
+                    for (int sp = mg; sp < NS; sp += G) {
+                        const double *X = RB + sp * MS_QS + qo;
+                        s0 += X[0] - ref[qo]; s1 += X[1] - ref[qo + 1]; s2 += X[2] - ref[qo + 2];
                     }
                 }
-                if (warp < nwa) {
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const double s = warp_sum(d[r]);
-                        if (lane == 0) part[warp * MS_NMAX + 3 * b + r] = s;
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid < N) {
-                double s = 0.0;
-                for (int w2 = 0; w2 < nwa; ++w2) s += part[w2 * MS_NMAX + tid];
-                acc[tid] = s;
+                double *pp = part + mg * MS_NMAX + 3 * mb;
+                pp[0] = s0; pp[1] = s1; pp[2] = s2;
             }
             __syncthreads();
             if (tid < NB) {
                 const int b = tid, qo = ms_qoff(b);
                 const double wn = 1.0 / (double)NS;
-                const double d[3] = {acc[3 * b] * wn, acc[3 * b + 1] * wn, acc[3 * b + 2] * wn};
+                double d[3] = {0.0, 0.0, 0.0};
+                for (int g = 0; g < G; ++g) {
+                    const double *pp = part + g * MS_NMAX + 3 * b;
+                    d[0] += pp[0]; d[1] += pp[1]; d[2] += pp[2];
+                }
+                d[0] *= wn; d[1] *= wn; d[2] *= wn;
                 dl[3 * b] = d[0]; dl[3 * b + 1] = d[1]; dl[3 * b + 2] = d[2];
                 if (ms_so3(b)) {
                     double e[4], q[4];
@@ -522,17 +553,14 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 }
             }
             __syncthreads();
-            if (warp == 0) {
-                double n2 = 0.0;
-                for (int e = lane; e < N; e += 32) n2 = fma(dl[e], dl[e], n2);
+            // |d|: every warp computes it for itself (same operations, same result), so the loop needs no third barrier
+            double n2 = 0.0;
+            for (int e = lane; e < N; e += 32) n2 = fma(dl[e], dl[e], n2);
 #pragma unroll
-                for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-                if (lane == 0) flags[3] = (sqrt(n2) > 1e-6 && ++flags[4] < 10000) ? 1 : 0;
-            }
-            __syncthreads();
-            if (!flags[3]) break;
+            for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            if (!(sqrt(n2) > 1e-6 && ++iters < 10000)) break;
         }
-        if (flags[4] >= 10000) st |= SLB_ST_MEAN_NOCONV;
+        if (iters >= 10000) st |= SLB_ST_MEAN_NOCONV;
         // deviations d_s = X_s [-] mean, in place (72 <= 83 slots per sigma point); the pad rows NS..NSPAD-1 are zeroed
         if (tid >= NS && tid < MS_NSPAD)
             for (int e = 0; e < N; ++e) RB[tid * MS_QS + e] = 0.0;
@@ -704,80 +732,43 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 RS[e] = sacc;
             }
             __syncthreads();
-            chol_blocked(RS, M, flags, invd);
+            // W = L^-1 (packed lower in RQ; T is consumed) comes out of the same sweep: the identity is carried through the
+            // factorisation as a right-hand side (chol_blocked), so the inverse costs no serial chain of its own
+            for (int e = tid; e < M * (M + 1) / 2; e += MS_T) RQ[e] = 0.0;
+            __syncthreads();
+            if (tid < M) RQ[tri(tid, tid)] = 1.0;
+            chol_blocked(RS, M, flags, invd, nullptr, 0, 0, nullptr, RQ);
             if (!flags[0]) {
                 if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
                 continue;
             }
-            // W = L^-1, packed lower in RQ, by 8-row blocks: W(I,:) = L_II^-1 (E(I,:) - sum_{K<I} L(I,K) W(K,:)).  The sum is
-            // 8x8x4 DMMA tiles over all warps; the 8x8 forward substitution with L_II is one thread per column.
-            {
-                const int nbr = (M + 7) >> 3;
-                for (int I = 0; I < nbr; ++I) {
-                    // tiles (I, J), J < I:  T = sum_{K=J}^{I-1} L(I,K) W(K,J), stored negated in place of W(I,J)
-                    for (int J = warp; J < I; J += MS_W) {
-                        double d0 = 0.0, d1 = 0.0;
-                        const int ar = min(8 * I + fr, M - 1);   // rows >= M only feed accumulator rows that are dropped
-                        const int bc = 8 * J + fr;
-                        for (int K = J; K < I; ++K) {
-#pragma unroll
-                            for (int k0 = 0; k0 < 8; k0 += 4) {
-                                const int kk = 8 * K + k0 + fk;   // < 8 I <= M
-                                const double av = RS[tri(ar, kk)];
-                                const double bv = kk >= bc ? RQ[tri(kk, bc)] : 0.0;   // W is lower triangular
-                                dmma884(d0, d1, av, bv);
-                            }
-                        }
-                        const int r = 8 * I + fr, c = 8 * J + 2 * fk;
-                        if (r < M) {
-                            RQ[tri(r, c)] = -d0;
-                            RQ[tri(r, c + 1)] = -d1;
-                        }
-                    }
-                    __syncthreads();
-                    // columns 0 .. 8I+7 of block row I: x = L_II^-1 r  (r = the negated sums above, e_c on the diagonal tile)
-                    {
-                        const int c = tid, i0 = 8 * I;
-                        if (c < min(i0 + 8, M)) {
-                            double x[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const int i = i0 + q;
-                                if (i < M && i >= c) {
-                                    double sv = c >= i0 ? (i == c ? 1.0 : 0.0) : RQ[tri(i, c)];
-#pragma unroll
-                                    for (int p = 0; p < 8; ++p)
-                                        if (p < q && i0 + p >= c) sv = fma(-RS[tri(i, i0 + p)], x[p], sv);
-                                    x[q] = sv * invd[i];
-                                    RQ[tri(i, c)] = x[q];
-                                } else {
-                                    x[q] = 0.0;
-                                }
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
             // 2x2 diagonal blocks of the information matrix: info_f = W[:, 2f:2f+2]^T W[:, 2f:2f+2]
             bool rej = false;
-            if (tid < NF) {
-                const int ia = 2 * tid, ib = ia + 1;
+            if (tid < ((8 * NF + 31) & ~31)) {   // 8 threads per feature split the rows; whole warps take the branch
+                const int f = tid >> 3, part = tid & 7, ia = 2 * f, ib = ia + 1;
                 double i00 = 0.0, i10 = 0.0, i11 = 0.0;
-                {
+                if (part == 0 && f < NF) {
                     const double wa = RQ[tri(ia, ia)];
                     i00 = wa * wa;
                 }
-                for (int r = ib; r < M; ++r) {
+                for (int r = ib + part; r < (f < NF ? M : 0); r += 8) {
                     const double wa = RQ[tri(r, ia)], wb = RQ[tri(r, ib)];
                     i00 = fma(wa, wa, i00);
                     i10 = fma(wa, wb, i10);
                     i11 = fma(wb, wb, i11);
                 }
-                info[3 * tid] = i00; info[3 * tid + 1] = i10; info[3 * tid + 2] = i11;
-                const double v0 = nu[ia], v1 = nu[ib];
-                const double m2 = v0 * (i00 * v0 + i10 * v1) + v1 * (i10 * v0 + i11 * v1);
-                rej = !(m2 < 5.99);
+#pragma unroll
+                for (int o = 4; o; o >>= 1) {
+                    i00 += __shfl_xor_sync(0xffffffffu, i00, o);
+                    i10 += __shfl_xor_sync(0xffffffffu, i10, o);
+                    i11 += __shfl_xor_sync(0xffffffffu, i11, o);
+                }
+                if (part == 0 && f < NF) {
+                    info[3 * f] = i00; info[3 * f + 1] = i10; info[3 * f + 2] = i11;
+                    const double v0 = nu[ia], v1 = nu[ib];
+                    const double m2 = v0 * (i00 * v0 + i10 * v1) + v1 * (i10 * v0 + i11 * v1);
+                    rej = !(m2 < 5.99);
+                }
             }
             // while nothing is rejected the sequential scan keeps the identity indexing: "all accepted" needs no scan
             if (__syncthreads_or(rej) && warp == 0) {
