@@ -6,5 +6,3 @@ python -c "
 import json
 d=json.loads(open('gpurun_out/tmp_bench.json').read().strip().splitlines()[-1]); print('$w', 'value %.4g'%d['value'], 'ms %.3f'%d['ms_per_step'])"
 done
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:msckf_update_kernel -c 1 -o gpurun_out/src_msckf -f python profiles/run_kernels.py msckf > gpurun_out/ncu_src_msckf.log 2>&1
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:msckf_ekf_update_kernel -c 1 -o gpurun_out/src_msckf_ekf -f python profiles/run_kernels.py msckf_ekf > gpurun_out/ncu_src_msckf_ekf.log 2>&1

@@ -157,13 +157,14 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
             const int i0 = r0 + 8 * tr, j0 = r0 + 8 * tc;
             double d0 = 0.0, d1 = 0.0;
             const double *pa = A + tri(min(i0 + fr, n - 1), p0) + fk, *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
+            const int i = i0 + fr, j = j0 + 2 * fk;
+            const bool v0 = i < n && j <= i, v1 = i < n && j + 1 <= i;
+            double *po = A + tri(min(i, n - 1), min(j, i));   // old values requested together with the operands
+            const double c0 = v0 ? po[0] : 0.0, c1 = v1 ? po[1] : 0.0;
             dmma884(d0, d1, pa[0], pb2[0]);
             dmma884(d0, d1, pa[4], pb2[4]);
-            const int i = i0 + fr, j = j0 + 2 * fk;
-            if (i < n) {
-                if (j <= i) A[tri(i, j)] -= d0;
-                if (j + 1 <= i) A[tri(i, j + 1)] -= d1;
-            }
+            if (v0) po[0] = c0 - d0;
+            if (v1) po[1] = c1 - d1;
         };
         if (warp == 0) {
             if (ntiles > 0) {  // look-ahead: warp 0 owns the next diagonal block and factors it while the others update
@@ -182,11 +183,13 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                     double d0 = 0.0, d1 = 0.0;
                     const double *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
                     const int k0 = p0 + fk, k1 = k0 + 4;
+                    const int oc = j0 + 2 * fk;   // > ai: always inside the stored triangle
+                    double *po0 = Wp + tri(min(oc, n - 1), ai), *po1 = Wp + tri(min(oc + 1, n - 1), ai);
+                    const double c0 = *po0, c1 = *po1;
                     dmma884(d0, d1, k0 >= ai ? Wp[tri(k0, ai)] : 0.0, pb2[0]);
                     dmma884(d0, d1, k1 >= ai ? Wp[tri(k1, ai)] : 0.0, pb2[4]);
-                    const int oc = j0 + 2 * fk;   // > ai: always inside the stored triangle
-                    if (oc < n) Wp[tri(oc, ai)] -= d0;
-                    if (oc + 1 < n) Wp[tri(oc + 1, ai)] -= d1;
+                    if (oc < n) *po0 = c0 - d0;
+                    if (oc + 1 < n) *po1 = c1 - d1;
                 } else {
                     const int u = t - ntiles, tr = u / nt, tc = u - tr * nt;
                     const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;
@@ -194,13 +197,14 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                     double *xrow = ac < nx ? X + ac * xs : xe;
                     double d0 = 0.0, d1 = 0.0;
                     const double *pa = xrow + p0 + fk, *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
+                    const int oc = j0 + 2 * fk;
+                    const bool v0 = ai < nxr && oc < n, v1 = ai < nxr && oc + 1 < n;
+                    double *po0 = xrow + min(oc, n - 1), *po1 = xrow + min(oc + 1, n - 1);
+                    const double c0 = *po0, c1 = *po1;
                     dmma884(d0, d1, pa[0], pb2[0]);
                     dmma884(d0, d1, pa[4], pb2[4]);
-                    const int oc = j0 + 2 * fk;
-                    if (ai < nxr) {
-                        if (oc < n) xrow[oc] -= d0;
-                        if (oc + 1 < n) xrow[oc + 1] -= d1;
-                    }
+                    if (v0) *po0 = c0 - d0;
+                    if (v1) *po1 = c1 - d1;
                 }
             }
         }
