@@ -37,7 +37,7 @@ constexpr int MS_D = 896;                        // small vectors
 constexpr int MS_SMEM_DOUBLES = MS_A + MS_B + MS_C + MS_D;
 static_assert(MS_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF update working set exceeds shared memory");
 static_assert(MS_NSPAD * MS_QS <= MS_B, "sigma points do not fit region B");
-static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_B, "compacted S does not fit region B");
+static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_A && MS_A + 1600 <= MS_B, "compacted S + panel staging do not fit region B");
 
 // linear index of a lower-triangular tile -> (tr, tc), tc <= tr: a constant-memory table (the index is warp-uniform,
 // so the lookup is one broadcast load instead of a sqrtf + fix-up per tile)
@@ -71,8 +71,13 @@ SLB_DEV void tri_tile(int t, int &tr, int &tc) {
 // Optional inverse factor: Wp (packed lower, preset to the identity by the caller) is treated as the right-hand side
 // I stored transposed -- row i of the right-hand side is column i of Wp -- so that it ends up as I L^-T transposed,
 // i.e. Wp = L^-1.  Only the tiles that can be non-zero (row tile <= current panel) are touched.
-SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *X = nullptr, int nx = 0, int xs = 0,
-                          double *xe = nullptr, double *Wp = nullptr) {
+// PS is a 1600-double scratch: every solved panel is also parked there as dense 8-wide rows, swizzled so that the
+// DMMA fragment loads of the trailing update are bank-conflict free (the packed triangle's row starts are not:
+// 2.4 wavefronts per ideal one, and the tiles are shared-memory-bandwidth bound).
+constexpr int MS_PS = 1600;
+SLB_DEV int ps_idx(int srow, int k) { return srow * 8 + ((k + 4 * ((srow >> 1) & 1)) & 7); }
+SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *PS, double *X = nullptr, int nx = 0,
+                          int xs = 0, double *xe = nullptr, double *Wp = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     const int nxr = X ? nx + 1 : 0, nxt = (nxr + 7) >> 3;
@@ -116,8 +121,10 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
         const int pb = min(8, n - p0);
         const int r0 = p0 + pb, na = n - r0;
         const int nwr = Wp ? r0 : 0;   // rows of the identity right-hand side that can be non-zero in this panel
+        const int nap = (na + 7) & ~7, nxp = (nxr + 7) & ~7;   // staging: trailing rows | right-hand sides | identity rows
         for (int w = tid; w < na + nxr + nwr; w += MS_T) {
             double x[8];
+            const int srow = w < na ? w : (w < na + nxr ? nap + (w - na) : nap + nxp + (w - na - nxr));
             if (w < na + nxr) {
                 double *Ai = w < na ? A + tri(r0 + w, p0) : (w - na < nx ? X + (w - na) * xs : xe) + p0;
 #pragma unroll
@@ -146,23 +153,29 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                     }
                 }
             }
+            if (na > 0) {   // a trailing update follows (then pb == 8 and all of x is defined)
+#pragma unroll
+                for (int c = 0; c < 8; c += 2)
+                    *reinterpret_cast<double2 *>(PS + ps_idx(srow, c)) = make_double2(x[c], x[c + 1]);
+            }
         }
         __syncthreads();
         // rows / columns beyond the matrix only feed accumulator entries that are never stored: their addresses are clamped,
         // not masked; a trailing update only exists after a full 8-wide panel (pb == 8), so the k-loop needs no bound either
         const int nt = (na + 7) >> 3, ntiles = nt * (nt + 1) / 2;
+        // operands come from the staged panel; rows beyond the matrix are clamped (their accumulator rows are dropped)
         auto a_tile = [&](int t) {
             int tr, tc;
             tri_tile(t, tr, tc);
             const int i0 = r0 + 8 * tr, j0 = r0 + 8 * tc;
             double d0 = 0.0, d1 = 0.0;
-            const double *pa = A + tri(min(i0 + fr, n - 1), p0) + fk, *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
+            const int ra = min(8 * tr + fr, na - 1), rb = min(8 * tc + fr, na - 1);
             const int i = i0 + fr, j = j0 + 2 * fk;
             const bool v0 = i < n && j <= i, v1 = i < n && j + 1 <= i;
             double *po = A + tri(min(i, n - 1), min(j, i));   // old values requested together with the operands
             const double c0 = v0 ? po[0] : 0.0, c1 = v1 ? po[1] : 0.0;
-            dmma884(d0, d1, pa[0], pb2[0]);
-            dmma884(d0, d1, pa[4], pb2[4]);
+            dmma884(d0, d1, PS[ps_idx(ra, fk)], PS[ps_idx(rb, fk)]);
+            dmma884(d0, d1, PS[ps_idx(ra, fk + 4)], PS[ps_idx(rb, fk + 4)]);
             if (v0) po[0] = c0 - d0;
             if (v1) po[1] = c1 - d1;
         };
@@ -174,35 +187,37 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
             }
         } else {
             const int nwt = Wp ? (p0 >> 3) + 1 : 0;   // row tiles of the identity right-hand side reached so far
+            // u / nt below by multiplication (u < 2^10, nt <= 13): an integer division is a ~100-cycle dependent chain in
+            // front of every tile's address arithmetic, and a warp has only one tile in flight
+            const unsigned ntm = nt > 0 ? (65536u + nt - 1) / nt : 0u;
             for (int t = warp; t < ntiles + (nxt + nwt) * nt; t += MS_W - 1) {
                 if (t < ntiles) {
                     a_tile(t);
                 } else if (t >= ntiles + nxt * nt) {
-                    const int u = t - ntiles - nxt * nt, tr = u / nt, tc = u - tr * nt;
+                    const int u = t - ntiles - nxt * nt, tr = (int)((u * ntm) >> 16), tc = u - tr * nt;
                     const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;   // ai <= p0 + 7 < n
                     double d0 = 0.0, d1 = 0.0;
-                    const double *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
-                    const int k0 = p0 + fk, k1 = k0 + 4;
+                    const int ra = nap + nxp + ai, rb = min(8 * tc + fr, na - 1);   // structural zeros are staged as zeros
                     const int oc = j0 + 2 * fk;   // > ai: always inside the stored triangle
                     double *po0 = Wp + tri(min(oc, n - 1), ai), *po1 = Wp + tri(min(oc + 1, n - 1), ai);
                     const double c0 = *po0, c1 = *po1;
-                    dmma884(d0, d1, k0 >= ai ? Wp[tri(k0, ai)] : 0.0, pb2[0]);
-                    dmma884(d0, d1, k1 >= ai ? Wp[tri(k1, ai)] : 0.0, pb2[4]);
+                    dmma884(d0, d1, PS[ps_idx(ra, fk)], PS[ps_idx(rb, fk)]);
+                    dmma884(d0, d1, PS[ps_idx(ra, fk + 4)], PS[ps_idx(rb, fk + 4)]);
                     if (oc < n) *po0 = c0 - d0;
                     if (oc + 1 < n) *po1 = c1 - d1;
                 } else {
-                    const int u = t - ntiles, tr = u / nt, tc = u - tr * nt;
+                    const int u = t - ntiles, tr = (int)((u * ntm) >> 16), tc = u - tr * nt;
                     const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;
                     const int ac = min(ai, nxr - 1);
                     double *xrow = ac < nx ? X + ac * xs : xe;
                     double d0 = 0.0, d1 = 0.0;
-                    const double *pa = xrow + p0 + fk, *pb2 = A + tri(min(j0 + fr, n - 1), p0) + fk;
+                    const int ra = nap + ac, rb = min(8 * tc + fr, na - 1);
                     const int oc = j0 + 2 * fk;
                     const bool v0 = ai < nxr && oc < n, v1 = ai < nxr && oc + 1 < n;
                     double *po0 = xrow + min(oc, n - 1), *po1 = xrow + min(oc + 1, n - 1);
                     const double c0 = *po0, c1 = *po1;
-                    dmma884(d0, d1, pa[0], pb2[0]);
-                    dmma884(d0, d1, pa[4], pb2[4]);
+                    dmma884(d0, d1, PS[ps_idx(ra, fk)], PS[ps_idx(rb, fk)]);
+                    dmma884(d0, d1, PS[ps_idx(ra, fk + 4)], PS[ps_idx(rb, fk + 4)]);
                     if (v0) *po0 = c0 - d0;
                     if (v1) *po1 = c1 - d1;
                 }
@@ -241,6 +256,7 @@ SLB_DEV bool ms_so3(int b) { return b < 4 ? b == 1 : ((b - 4) & 1); }
 __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a) {
     extern __shared__ __align__(16) double sm[];
     double *RA = sm, *RB = RA + MS_A, *RC = RB + MS_B, *RD = RC + MS_C;
+    double *PS = RB + MS_A;   // panel staging of chol_blocked: region B is idle (or holds the compacted S' in its first MS_A slots) during every factorisation
     double *mu = RD, *zbar = mu + 84, *nu = zbar + 100, *wv = nu + 100, *dl = wv + 100, *acc = dl + 72, *ref = acc + 72,
            *invd = ref + 84;  // 104
     int *kept = reinterpret_cast<int *>(invd + 104);  // 100 ints
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         pred_cp_async_wait_all();
         __syncthreads();
         // ---- L = chol(Pk) (:229 -> :412) -------------------------------------------------------------
-        chol_blocked(RA, N, flags, invd);
+        chol_blocked(RA, N, flags, invd, PS);
         int st = 0;
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         //      exactly N rows): [covXZ; nu^T] Ls^-T has w^T = (Ls^-1 nu)^T as its last row.
         if (tid < mk) wv[tid] = nu[tid];
         __syncthreads();
-        chol_blocked(Sp, mk, flags, invd, Xz, N, MS_ZS, wv);
+        chol_blocked(Sp, mk, flags, invd, PS, Xz, N, MS_ZS, wv);
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
@@ -474,7 +490,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         }
         __syncthreads();
         // ---- applyDelta(K nu) (:263 -> :659-666): L2 = chol(P_new), X = mu [+] (delta +- L2 e_j) ----------
-        chol_blocked(RA, N, flags, invd);
+        chol_blocked(RA, N, flags, invd, PS);
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
@@ -631,7 +647,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
 constexpr int ME_QP = MS_T / 80;  // threads sharing a column in the Householder phases (rows i = first + part mod QP)
 constexpr int ME_HS = 76;  // row stride of H / Q / covXZ (= 12 mod 16: conflict-free DMMA fragment loads)
 constexpr int ME_RA = 2632, ME_RS = 5056, ME_RH = MS_MMAX * ME_HS, ME_RQ = MS_MMAX * ME_HS, ME_RD = 2304;
-constexpr int ME_SMEM_DOUBLES = ME_RA + ME_RS + ME_RH + ME_RQ + ME_RD;
+constexpr int ME_SMEM_DOUBLES = ME_RA + ME_RS + ME_RH + ME_RQ + ME_RD + MS_PS;
 static_assert(ME_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF EKF update working set exceeds shared memory");
 
 // flag[0] = 1 when the shared m x m measurement noise matrix is diagonal, flag[1] = 1 when it is sigma^2 I
@@ -653,7 +669,7 @@ __global__ void msckf_rdiag_kernel(const double *R, int m, int32_t *flag) {
 
 __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterArgs a) {
     extern __shared__ __align__(16) double sm[];
-    double *RA = sm, *RS = RA + ME_RA, *RH = RS + ME_RS, *RQ = RH + ME_RH, *RD = RQ + ME_RQ;
+    double *RA = sm, *RS = RA + ME_RA, *RH = RS + ME_RS, *RQ = RH + ME_RH, *RD = RQ + ME_RQ, *PS = RD + ME_RD;
     double *mu = RD, *nu = mu + 84, *wv = nu + 100, *dl = wv + 100, *invd = dl + 72, *tau = invd + 104, *Hb = tau + 72,
            *info = Hb + 600, *T3 = info + 152, *scal = T3 + 800;  // scal: 8
     int *kept = reinterpret_cast<int *>(scal + 8);  // 100 ints
@@ -741,7 +757,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             for (int e = tid; e < M * (M + 1) / 2; e += MS_T) RQ[e] = 0.0;
             __syncthreads();
             if (tid < M) RQ[tri(tid, tid)] = 1.0;
-            chol_blocked(RS, M, flags, invd, nullptr, 0, 0, nullptr, RQ);
+            chol_blocked(RS, M, flags, invd, PS, nullptr, 0, 0, nullptr, RQ);
             if (!flags[0]) {
                 if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
                 continue;
@@ -849,7 +865,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                     RS[e] = sacc;
                 }
                 __syncthreads();
-                chol_blocked(RS, mk, flags, invd, Yb, N, ys, Yb + N * ys);
+                chol_blocked(RS, mk, flags, invd, PS, Yb, N, ys, Yb + N * ys);
                 solved = true;
                 if (!flags[0]) {
                     if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
@@ -1050,7 +1066,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         }
         __syncthreads();
         if (tid < mq) Yb[N * ys + tid] = nu[tid];
-        chol_blocked(RS, N, flags, invd, Yb, N, ys, Yb + N * ys);
+        chol_blocked(RS, N, flags, invd, PS, Yb, N, ys, Yb + N * ys);
         solved = true;
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
