@@ -187,39 +187,48 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
             }
         } else {
             const int nwt = Wp ? (p0 >> 3) + 1 : 0;   // row tiles of the identity right-hand side reached so far
-            // u / nt below by multiplication (u < 2^10, nt <= 13): an integer division is a ~100-cycle dependent chain in
-            // front of every tile's address arithmetic, and a warp has only one tile in flight
-            const unsigned ntm = nt > 0 ? (65536u + nt - 1) / nt : 0u;
-            for (int t = warp; t < ntiles + (nxt + nwt) * nt; t += MS_W - 1) {
+            // Right-hand-side tiles are taken two column tiles at a time (16 output columns): the row operand is loaded
+            // once and the two accumulator chains overlap.  u / ntp by multiplication (u < 2^10): an integer division
+            // is a ~100-cycle dependent chain in front of the address arithmetic, and a warp has one task in flight.
+            const int ntp = (nt + 1) >> 1;
+            const unsigned ntm = ntp > 0 ? (65536u + ntp - 1) / ntp : 0u;
+            for (int t = warp; t < ntiles + (nxt + nwt) * ntp; t += MS_W - 1) {
                 if (t < ntiles) {
                     a_tile(t);
-                } else if (t >= ntiles + nxt * nt) {
-                    const int u = t - ntiles - nxt * nt, tr = (int)((u * ntm) >> 16), tc = u - tr * nt;
-                    const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;   // ai <= p0 + 7 < n
-                    double d0 = 0.0, d1 = 0.0;
-                    const int ra = nap + nxp + ai, rb = min(8 * tc + fr, na - 1);   // structural zeros are staged as zeros
-                    const int oc = j0 + 2 * fk;   // > ai: always inside the stored triangle
-                    double *po0 = Wp + tri(min(oc, n - 1), ai), *po1 = Wp + tri(min(oc + 1, n - 1), ai);
-                    const double c0 = *po0, c1 = *po1;
-                    dmma884(d0, d1, PS[ps_idx(ra, fk)], PS[ps_idx(rb, fk)]);
-                    dmma884(d0, d1, PS[ps_idx(ra, fk + 4)], PS[ps_idx(rb, fk + 4)]);
-                    if (oc < n) *po0 = c0 - d0;
-                    if (oc + 1 < n) *po1 = c1 - d1;
+                    continue;
+                }
+                const bool wk = t >= ntiles + nxt * ntp;   // identity right-hand side (else: X rows)
+                const int u = t - ntiles - (wk ? nxt * ntp : 0), tr = (int)((u * ntm) >> 16), tc = 2 * (u - tr * ntp);
+                const int ai = 8 * tr + fr, ja = r0 + 8 * tc + 2 * fk, jb = ja + 8;
+                const int rb0 = min(8 * tc + fr, na - 1), rb1 = min(8 * tc + 8 + fr, na - 1);
+                int ra;
+                double *pa0, *pa1, *pb0, *pb1;
+                bool rowok;
+                if (wk) {   // ai <= p0 + 7 < n; output columns > ai: always inside the stored triangle
+                    ra = nap + nxp + ai;   // structural zeros are staged as zeros
+                    rowok = true;
+                    pa0 = Wp + tri(min(ja, n - 1), ai); pa1 = Wp + tri(min(ja + 1, n - 1), ai);
+                    pb0 = Wp + tri(min(jb, n - 1), ai); pb1 = Wp + tri(min(jb + 1, n - 1), ai);
                 } else {
-                    const int u = t - ntiles, tr = (int)((u * ntm) >> 16), tc = u - tr * nt;
-                    const int ai = 8 * tr + fr, j0 = r0 + 8 * tc;
                     const int ac = min(ai, nxr - 1);
                     double *xrow = ac < nx ? X + ac * xs : xe;
-                    double d0 = 0.0, d1 = 0.0;
-                    const int ra = nap + ac, rb = min(8 * tc + fr, na - 1);
-                    const int oc = j0 + 2 * fk;
-                    const bool v0 = ai < nxr && oc < n, v1 = ai < nxr && oc + 1 < n;
-                    double *po0 = xrow + min(oc, n - 1), *po1 = xrow + min(oc + 1, n - 1);
-                    const double c0 = *po0, c1 = *po1;
-                    dmma884(d0, d1, PS[ps_idx(ra, fk)], PS[ps_idx(rb, fk)]);
-                    dmma884(d0, d1, PS[ps_idx(ra, fk + 4)], PS[ps_idx(rb, fk + 4)]);
-                    if (v0) *po0 = c0 - d0;
-                    if (v1) *po1 = c1 - d1;
+                    ra = nap + ac;
+                    rowok = ai < nxr;
+                    pa0 = xrow + min(ja, n - 1); pa1 = xrow + min(ja + 1, n - 1);
+                    pb0 = xrow + min(jb, n - 1); pb1 = xrow + min(jb + 1, n - 1);
+                }
+                const double a0 = PS[ps_idx(ra, fk)], a1 = PS[ps_idx(ra, fk + 4)];
+                const double ca0 = *pa0, ca1 = *pa1, cb0 = *pb0, cb1 = *pb1;
+                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+                dmma884(d0, d1, a0, PS[ps_idx(rb0, fk)]);
+                dmma884(e0, e1, a0, PS[ps_idx(rb1, fk)]);
+                dmma884(d0, d1, a1, PS[ps_idx(rb0, fk + 4)]);
+                dmma884(e0, e1, a1, PS[ps_idx(rb1, fk + 4)]);
+                if (rowok) {
+                    if (ja < n) *pa0 = ca0 - d0;
+                    if (ja + 1 < n) *pa1 = ca1 - d1;
+                    if (jb < n) *pb0 = cb0 - e0;
+                    if (jb + 1 < n) *pb1 = cb1 - e1;
                 }
             }
         }
