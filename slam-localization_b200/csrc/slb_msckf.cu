@@ -74,6 +74,14 @@ SLB_DEV void tri_tile(int t, int &tr, int &tc) {
 // PS is a 1600-double scratch: every solved panel is also parked there as dense 8-wide rows, swizzled so that the
 // DMMA fragment loads of the trailing update are bank-conflict free (the packed triangle's row starts are not:
 // 2.4 wavefronts per ideal one, and the tiles are shared-memory-bandwidth bound).
+// -DSLB_CHOL_TIMING=<call index>: per-panel clock64() stamps of one chol_blocked call of CTA 0 (profiles/chol_timing.py)
+#ifdef SLB_CHOL_TIMING
+__device__ long long chol_dbg[16 * 16 * 8];   // [panel][warp][slot]
+__device__ int chol_dbg_call;
+#define CHOL_T(panel, slot) do { if (blockIdx.x == 0 && chol_dbg_call == SLB_CHOL_TIMING && (threadIdx.x & 31) == 0 && (panel) < 16) chol_dbg[((panel) * 16 + (threadIdx.x >> 5)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define CHOL_T(panel, slot) do { } while (0)
+#endif
 constexpr int MS_PS = 1600;
 SLB_DEV int ps_idx(int srow, int k) { return srow * 8 + ((k + 4 * ((srow >> 1) & 1)) & 7); }
 SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *PS, double *X = nullptr, int nx = 0,
@@ -81,37 +89,55 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     const int nxr = X ? nx + 1 : 0, nxt = (nxr + 7) >> 3;
+    double *dinv = PS + MS_PS - 64;   // inverse of the current diagonal block, row-major 8 x 8 (staging uses < 192 of its 200 rows)
+    // 8x8 diagonal block on one warp, two entries per lane in the DMMA accumulator layout (row fr, columns 2 fk and
+    // 2 fk + 1).  Right-looking and square-root-free: step k broadcasts d_k = a_kk, a_ik and a_jk by shuffles, then
+    // a_ij -= (a_ik / d_k) a_jk is ONE FMA per entry -- the dependent chain per column is shuffle + reciprocal + multiply +
+    // FMA and there is hardly any other instruction to issue (lane-per-row needed up to 7 shuffle + FMA pairs per step).
+    // The same Gauss transforms are accumulated on the identity (M = prod (I - v_k e_k^T)): diag(1 / L_ii) M is the inverse
+    // of the block, which turns the panel solve below it from an 8-step forward substitution per row into 36 independent
+    // FMAs per row.  All square roots are taken after the loop.
     auto factor_diag = [&](int p0) {
         const int pb = min(8, n - p0);
-        // square-root-free and right-looking: u_ic -= (u_ik / d_k) u_ck keeps one shuffle + one reciprocal per
-        // column on the dependent chain (the other shuffles overlap the reciprocal); the 1/sqrt(d_k) scaling that
-        // turns U into L is applied to all columns at once afterwards
-        double u[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) u[c] = (lane < pb && c <= lane) ? A[tri(p0 + lane, p0 + c)] : 0.0;
+        const int i = fr, j0 = 2 * fk, j1 = j0 + 1;
+        double a0 = (i < pb && j0 <= i) ? A[tri(p0 + i, p0 + j0)] : 0.0;
+        double a1 = (i < pb && j1 <= i) ? A[tri(p0 + i, p0 + j1)] : 0.0;
+        double m0 = (i == j0) ? 1.0 : 0.0, m1 = (i == j1) ? 1.0 : 0.0;
+        double di = 1.0, dj0 = 1.0, dj1 = 1.0;   // pivots of this lane's row and of its two columns
         bool ok = true;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const double d = bcast(u[k], k);
+        for (int k = 0; k < 8; ++k) {
             if (k < pb) {
+                const int kh = k >> 1;
+                const double ak = (k & 1) ? a1 : a0;                       // this lane's entry in column pair kh
+                const double d = bcast(ak, 4 * k + kh);                    // a_kk
+                const double aik = __shfl_sync(0xffffffffu, ak, 4 * i + kh);
                 ok = ok && (d > 0.0);
-                const double v = u[k] * rcp_fast(d);
-#pragma unroll
-                for (int c = k + 1; c < 8; ++c) u[c] = fma(-v, bcast(u[k], c), u[c]);
+                if (i == k) di = d;
+                if (j0 == k) dj0 = d;
+                if (j1 == k) dj1 = d;
+                if (k < 7) {
+                    const double ajk0 = __shfl_sync(0xffffffffu, ak, 4 * j0 + kh), ajk1 = __shfl_sync(0xffffffffu, ak, 4 * j1 + kh);
+                    const double mk0 = bcast(m0, 4 * k + fk), mk1 = bcast(m1, 4 * k + fk);
+                    const double v = aik * rcp_fast(d);
+                    if (j0 > k) a0 = fma(-v, ajk0, a0);
+                    if (j1 > k) a1 = fma(-v, ajk1, a1);
+                    const double vm = i > k ? v : 0.0;
+                    m0 = fma(-vm, mk0, m0);
+                    m1 = fma(-vm, mk1, m1);
+                }
             }
         }
-        double dg = 1.0, sx, inv;
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (lane == c && c < pb) dg = u[c];
-        ok = ok && (dg > 0.0);
-        sqrt_rsqrt(dg, sx, inv);
-        if (lane < pb) invd[p0 + lane] = inv;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const double ic = bcast(inv, c);
-            if (lane < pb && c <= lane) A[tri(p0 + lane, p0 + c)] = (c == lane) ? sx : u[c] * ic;
+        double si, ri, s0, r0c, s1, r1c;
+        sqrt_rsqrt(di, si, ri);
+        sqrt_rsqrt(dj0, s0, r0c);
+        sqrt_rsqrt(dj1, s1, r1c);
+        if (i < pb) {
+            if (fk == 0) invd[p0 + i] = ri;
+            if (j0 <= i) A[tri(p0 + i, p0 + j0)] = (j0 == i) ? s0 : a0 * r0c;
+            if (j1 <= i) A[tri(p0 + i, p0 + j1)] = (j1 == i) ? s1 : a1 * r1c;
         }
+        *reinterpret_cast<double2 *>(dinv + i * 8 + j0) = make_double2(j0 <= i ? ri * m0 : 0.0, j1 <= i ? ri * m1 : 0.0);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok && lane == 0) *ok_flag = 0;
     };
@@ -122,36 +148,42 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
         const int r0 = p0 + pb, na = n - r0;
         const int nwr = Wp ? r0 : 0;   // rows of the identity right-hand side that can be non-zero in this panel
         const int nap = (na + 7) & ~7, nxp = (nxr + 7) & ~7;   // staging: trailing rows | right-hand sides | identity rows
+        CHOL_T(p0 >> 3, 0);
         for (int w = tid; w < na + nxr + nwr; w += MS_T) {
             double x[8];
             const int srow = w < na ? w : (w < na + nxr ? nap + (w - na) : nap + nxp + (w - na - nxr));
+            // row * inv(L_pp)^T: x_c = sum_{q <= c} a_q Dinv[c][q] -- no dependent chain, and all loads precede the stores
+            double av[8];
             if (w < na + nxr) {
                 double *Ai = w < na ? A + tri(r0 + w, p0) : (w - na < nx ? X + (w - na) * xs : xe) + p0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c < pb) {
-                        double sv = Ai[c];
+                for (int c = 0; c < 8; ++c) av[c] = c < pb ? Ai[c] : 0.0;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q < c) sv = fma(-x[q], A[tri(p0 + c, p0 + q)], sv);
-                        x[c] = sv * invd[p0 + c];
-                        Ai[c] = x[c];
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    double sv = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q <= c) sv = fma(av[q], dinv[c * 8 + q], sv);
+                    x[c] = sv;
                 }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < pb) Ai[c] = x[c];
             } else {
                 const int i = w - na - nxr;   // entries (i, col) with col < i are structural zeros and are not stored
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (c < pb) {
-                        const int col = p0 + c;
-                        double sv = col >= i ? Wp[tri(col, i)] : 0.0;
+                for (int c = 0; c < 8; ++c) av[c] = (c < pb && p0 + c >= i) ? Wp[tri(p0 + c, i)] : 0.0;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q < c) sv = fma(-x[q], A[tri(p0 + c, p0 + q)], sv);
-                        x[c] = sv * invd[col];
-                        if (col >= i) Wp[tri(col, i)] = x[c];
-                    }
+                for (int c = 0; c < 8; ++c) {
+                    double sv = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q <= c) sv = fma(av[q], dinv[c * 8 + q], sv);
+                    x[c] = sv;
                 }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < pb && p0 + c >= i) Wp[tri(p0 + c, i)] = x[c];
             }
             if (na > 0) {   // a trailing update follows (then pb == 8 and all of x is defined)
 #pragma unroll
@@ -159,7 +191,9 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                     *reinterpret_cast<double2 *>(PS + ps_idx(srow, c)) = make_double2(x[c], x[c + 1]);
             }
         }
+        CHOL_T(p0 >> 3, 1);
         __syncthreads();
+        CHOL_T(p0 >> 3, 2);
         // rows / columns beyond the matrix only feed accumulator entries that are never stored: their addresses are clamped,
         // not masked; a trailing update only exists after a full 8-wide panel (pb == 8), so the k-loop needs no bound either
         const int nt = (na + 7) >> 3, ntiles = nt * (nt + 1) / 2;
@@ -183,6 +217,7 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
             if (ntiles > 0) {  // look-ahead: warp 0 owns the next diagonal block and factors it while the others update
                 a_tile(0);
                 __syncwarp();
+                CHOL_T(p0 >> 3, 3);
                 factor_diag(r0);
             }
         } else {
@@ -232,8 +267,13 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                 }
             }
         }
+        CHOL_T(p0 >> 3, 4);
         __syncthreads();
+        CHOL_T(p0 >> 3, 5);
     }
+#ifdef SLB_CHOL_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) ++chol_dbg_call;
+#endif
 }
 
 // removeRow(2i); removeRow(2i+1) of the reference's gate loop applied to the index list kept[0..len) by one warp;
@@ -1234,3 +1274,9 @@ int launch_msckf_update_ekf(int mm, const FilterArgs &a, cudaStream_t s) {
 }
 
 }  // namespace slb
+
+#ifdef SLB_CHOL_TIMING
+extern "C" int slb_debug_chol(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, slbd::chol_dbg, sizeof(long long) * 16 * 16 * 8);
+}
+#endif
