@@ -97,11 +97,9 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
     // The same Gauss transforms are accumulated on the identity (M = prod (I - v_k e_k^T)): diag(1 / L_ii) M is the inverse
     // of the block, which turns the panel solve below it from an 8-step forward substitution per row into 36 independent
     // FMAs per row.  All square roots are taken after the loop.
-    auto factor_diag = [&](int p0) {
+    auto factor_diag = [&](int p0, double a0, double a1) {   // a0, a1: this lane's two entries (0 outside the lower triangle)
         const int pb = min(8, n - p0);
         const int i = fr, j0 = 2 * fk, j1 = j0 + 1;
-        double a0 = (i < pb && j0 <= i) ? A[tri(p0 + i, p0 + j0)] : 0.0;
-        double a1 = (i < pb && j1 <= i) ? A[tri(p0 + i, p0 + j1)] : 0.0;
         double m0 = (i == j0) ? 1.0 : 0.0, m1 = (i == j1) ? 1.0 : 0.0;
         double di = 1.0, dj0 = 1.0, dj1 = 1.0;   // pivots of this lane's row and of its two columns
         bool ok = true;
@@ -141,7 +139,10 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
         ok = __all_sync(0xffffffffu, ok);
         if (!ok && lane == 0) *ok_flag = 0;
     };
-    if (warp == 0) factor_diag(0);
+    if (warp == 0) {
+        const int pb = min(8, n);
+        factor_diag(0, (fr < pb && 2 * fk <= fr) ? A[tri(fr, 2 * fk)] : 0.0, (fr < pb && 2 * fk + 1 <= fr) ? A[tri(fr, 2 * fk + 1)] : 0.0);
+    }
     __syncthreads();
     for (int p0 = 0; p0 < n; p0 += 8) {
         const int pb = min(8, n - p0);
@@ -214,11 +215,20 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
             if (v1) po[1] = c1 - d1;
         };
         if (warp == 0) {
-            if (ntiles > 0) {  // look-ahead: warp 0 owns the next diagonal block and factors it while the others update
-                a_tile(0);
-                __syncwarp();
+            if (ntiles > 0) {
+                // look-ahead: warp 0 owns the next diagonal block.  Its trailing update (both operands are the staged rows
+                // 0..7) leaves the block in the accumulator layout, which is the layout factor_diag works in: no round trip
+                // through shared memory; the factorisation runs while the other warps update their tiles.
+                const int rr = min(fr, na - 1), pbn = min(8, na);
+                const int i = r0 + fr, j = r0 + 2 * fk;
+                const bool v0 = fr < pbn && 2 * fk <= fr, v1 = fr < pbn && 2 * fk + 1 <= fr;
+                const double x0 = PS[ps_idx(rr, fk)], x1 = PS[ps_idx(rr, fk + 4)];
+                const double c0 = v0 ? A[tri(i, j)] : 0.0, c1 = v1 ? A[tri(i, j + 1)] : 0.0;
+                double d0 = 0.0, d1 = 0.0;
+                dmma884(d0, d1, x0, x0);
+                dmma884(d0, d1, x1, x1);
                 CHOL_T(p0 >> 3, 3);
-                factor_diag(r0);
+                factor_diag(r0, v0 ? c0 - d0 : 0.0, v1 ? c1 - d1 : 0.0);
             }
         } else {
             const int nwt = Wp ? (p0 >> 3) + 1 : 0;   // row tiles of the identity right-hand side reached so far
