@@ -89,7 +89,9 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     const int nxr = X ? nx + 1 : 0, nxt = (nxr + 7) >> 3;
-    double *dinv = PS + MS_PS - 64;   // inverse of the current diagonal block, row-major 8 x 8 (staging uses < 192 of its 200 rows)
+    // inverse of a diagonal block, row-major 8 x 8, double-buffered by panel parity: the look-ahead writes the next panel's
+    // while the right-hand-side tasks still read the current one (staging uses < 184 of the 200 rows of PS)
+    auto dinv_of = [&](int p0) { return PS + MS_PS - 128 + 64 * ((p0 >> 3) & 1); };
     // 8x8 diagonal block on one warp, two entries per lane in the DMMA accumulator layout (row fr, columns 2 fk and
     // 2 fk + 1).  Right-looking and square-root-free: step k broadcasts d_k = a_kk, a_ik and a_jk by shuffles, then
     // a_ij -= (a_ik / d_k) a_jk is ONE FMA per entry -- the dependent chain per column is shuffle + reciprocal + multiply +
@@ -100,6 +102,7 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
     auto factor_diag = [&](int p0, double a0, double a1) {   // a0, a1: this lane's two entries (0 outside the lower triangle)
         const int pb = min(8, n - p0);
         const int i = fr, j0 = 2 * fk, j1 = j0 + 1;
+        double *dinv = dinv_of(p0);
         double m0 = (i == j0) ? 1.0 : 0.0, m1 = (i == j1) ? 1.0 : 0.0;
         double di = 1.0, dj0 = 1.0, dj1 = 1.0;   // pivots of this lane's row and of its two columns
         bool ok = true;
@@ -148,15 +151,16 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
         const int pb = min(8, n - p0);
         const int r0 = p0 + pb, na = n - r0;
         const int nwr = Wp ? r0 : 0;   // rows of the identity right-hand side that can be non-zero in this panel
-        const int nap = (na + 7) & ~7, nxp = (nxr + 7) & ~7;   // staging: trailing rows | right-hand sides | identity rows
+        const int nap = (na + 7) & ~7;   // staging: trailing rows | identity right-hand-side rows
+        const double *dinv = dinv_of(p0);
         CHOL_T(p0 >> 3, 0);
-        for (int w = tid; w < na + nxr + nwr; w += MS_T) {
+        for (int w = tid; w < na + nwr; w += MS_T) {
             double x[8];
-            const int srow = w < na ? w : (w < na + nxr ? nap + (w - na) : nap + nxp + (w - na - nxr));
+            const int srow = w < na ? w : nap + (w - na);
             // row * inv(L_pp)^T: x_c = sum_{q <= c} a_q Dinv[c][q] -- no dependent chain, and all loads precede the stores
             double av[8];
-            if (w < na + nxr) {
-                double *Ai = w < na ? A + tri(r0 + w, p0) : (w - na < nx ? X + (w - na) * xs : xe) + p0;
+            if (w < na) {
+                double *Ai = A + tri(r0 + w, p0);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) av[c] = c < pb ? Ai[c] : 0.0;
 #pragma unroll
@@ -171,7 +175,7 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                 for (int c = 0; c < 8; ++c)
                     if (c < pb) Ai[c] = x[c];
             } else {
-                const int i = w - na - nxr;   // entries (i, col) with col < i are structural zeros and are not stored
+                const int i = w - na;   // entries (i, col) with col < i are structural zeros and are not stored
 #pragma unroll
                 for (int c = 0; c < 8; ++c) av[c] = (c < pb && p0 + c >= i) ? Wp[tri(p0 + c, i)] : 0.0;
 #pragma unroll
@@ -231,37 +235,63 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                 factor_diag(r0, v0 ? c0 - d0 : 0.0, v1 ? c1 - d1 : 0.0);
             }
         } else {
+            // Work list of the 15 other warps, longest tasks first:
+            //   [0, nxq)        right-hand-side rows X, LEFT-looking: columns p0..p0+7 of 16 rows are finished here,
+            //                   X(:, p) = (X(:, p) - sum_{q < p} X(:, q) L(p, q)^T) inv(L_pp)^T -- a register-accumulated k-loop
+            //                   (one shared L fragment for two row tiles) instead of a read-modify-write of every trailing
+            //                   tile at every panel; this work grows with p while the trailing tiles shrink
+            //   then            trailing tiles 1.. of the matrix (right-looking, tile 0 is warp 0's)
+            //   then            identity right-hand side (Wp), right-looking, two column tiles per task
             const int nwt = Wp ? (p0 >> 3) + 1 : 0;   // row tiles of the identity right-hand side reached so far
-            // Right-hand-side tiles are taken two column tiles at a time (16 output columns): the row operand is loaded
-            // once and the two accumulator chains overlap.  u / ntp by multiplication (u < 2^10): an integer division
-            // is a ~100-cycle dependent chain in front of the address arithmetic, and a warp has one task in flight.
+            const int nxq = (nxt + 1) >> 1, nat = max(ntiles - 1, 0);
             const int ntp = (nt + 1) >> 1;
-            const unsigned ntm = ntp > 0 ? (65536u + ntp - 1) / ntp : 0u;
-            for (int t = warp; t < ntiles + (nxt + nwt) * ntp; t += MS_W - 1) {
-                if (t < ntiles) {
-                    a_tile(t);
+            const unsigned ntm = ntp > 0 ? (65536u + ntp - 1) / ntp : 0u;   // u / ntp by multiplication (u < 2^10)
+            for (int t = warp - 1; t < nxq + nat + nwt * ntp; t += MS_W - 1) {
+                if (t < nxq) {
+                    const int ia = 16 * t + fr, ib = ia + 8, ca = min(ia, nxr - 1), cb = min(ib, nxr - 1);
+                    double *xa = ca < nx ? X + ca * xs : xe, *xb = cb < nx ? X + cb * xs : xe;
+                    const double *lrow = A + tri(min(p0 + fr, n - 1), 0) + fk;   // L(p0 + fr, q + fk): B fragment
+                    double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+                    for (int q = 0; q < p0; q += 4) {
+                        const double bl = lrow[q];
+                        dmma884(d0, d1, xa[q + fk], bl);
+                        dmma884(e0, e1, xb[q + fk], bl);
+                    }
+                    const int c0 = p0 + 2 * fk, k0 = p0 + fk, k1 = k0 + 4;
+                    const bool v0 = c0 < n, v1 = c0 + 1 < n, oka = ia < nxr, okb = ib < nxr;
+                    // (X - sum) goes back in place so that it can be re-read as an A fragment for the product with inv(L_pp)^T
+                    const double ta0 = (v0 ? xa[c0] : 0.0) - d0, ta1 = (v1 ? xa[c0 + 1] : 0.0) - d1;
+                    const double tb0 = (v0 ? xb[c0] : 0.0) - e0, tb1 = (v1 ? xb[c0 + 1] : 0.0) - e1;
+                    if (oka && v0) xa[c0] = ta0;
+                    if (oka && v1) xa[c0 + 1] = ta1;
+                    if (okb && v0) xb[c0] = tb0;
+                    if (okb && v1) xb[c0 + 1] = tb1;
+                    __syncwarp();
+                    const double aa0 = k0 < n ? xa[k0] : 0.0, aa1 = k1 < n ? xa[k1] : 0.0;
+                    const double ab0 = k0 < n ? xb[k0] : 0.0, ab1 = k1 < n ? xb[k1] : 0.0;
+                    const double bd0 = dinv[fr * 8 + fk], bd1 = dinv[fr * 8 + fk + 4];   // B[k][c] = Dinv[c][k]
+                    double f0 = 0.0, f1 = 0.0, g0 = 0.0, g1 = 0.0;
+                    dmma884(f0, f1, aa0, bd0);
+                    dmma884(g0, g1, ab0, bd0);
+                    dmma884(f0, f1, aa1, bd1);
+                    dmma884(g0, g1, ab1, bd1);
+                    __syncwarp();
+                    if (oka && v0) xa[c0] = f0;
+                    if (oka && v1) xa[c0 + 1] = f1;
+                    if (okb && v0) xb[c0] = g0;
+                    if (okb && v1) xb[c0 + 1] = g1;
                     continue;
                 }
-                const bool wk = t >= ntiles + nxt * ntp;   // identity right-hand side (else: X rows)
-                const int u = t - ntiles - (wk ? nxt * ntp : 0), tr = (int)((u * ntm) >> 16), tc = 2 * (u - tr * ntp);
-                const int ai = 8 * tr + fr, ja = r0 + 8 * tc + 2 * fk, jb = ja + 8;
-                const int rb0 = min(8 * tc + fr, na - 1), rb1 = min(8 * tc + 8 + fr, na - 1);
-                int ra;
-                double *pa0, *pa1, *pb0, *pb1;
-                bool rowok;
-                if (wk) {   // ai <= p0 + 7 < n; output columns > ai: always inside the stored triangle
-                    ra = nap + nxp + ai;   // structural zeros are staged as zeros
-                    rowok = true;
-                    pa0 = Wp + tri(min(ja, n - 1), ai); pa1 = Wp + tri(min(ja + 1, n - 1), ai);
-                    pb0 = Wp + tri(min(jb, n - 1), ai); pb1 = Wp + tri(min(jb + 1, n - 1), ai);
-                } else {
-                    const int ac = min(ai, nxr - 1);
-                    double *xrow = ac < nx ? X + ac * xs : xe;
-                    ra = nap + ac;
-                    rowok = ai < nxr;
-                    pa0 = xrow + min(ja, n - 1); pa1 = xrow + min(ja + 1, n - 1);
-                    pb0 = xrow + min(jb, n - 1); pb1 = xrow + min(jb + 1, n - 1);
+                if (t < nxq + nat) {
+                    a_tile(t - nxq + 1);
+                    continue;
                 }
+                const int u = t - nxq - nat, tr = (int)((u * ntm) >> 16), tc = 2 * (u - tr * ntp);
+                const int ai = 8 * tr + fr, ja = r0 + 8 * tc + 2 * fk, jb = ja + 8;   // ai <= p0 + 7 < n; columns > ai: stored triangle
+                const int rb0 = min(8 * tc + fr, na - 1), rb1 = min(8 * tc + 8 + fr, na - 1);
+                const int ra = nap + ai;   // structural zeros are staged as zeros
+                double *pa0 = Wp + tri(min(ja, n - 1), ai), *pa1 = Wp + tri(min(ja + 1, n - 1), ai);
+                double *pb0 = Wp + tri(min(jb, n - 1), ai), *pb1 = Wp + tri(min(jb + 1, n - 1), ai);
                 const double a0 = PS[ps_idx(ra, fk)], a1 = PS[ps_idx(ra, fk + 4)];
                 const double ca0 = *pa0, ca1 = *pa1, cb0 = *pb0, cb1 = *pb1;
                 double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
@@ -269,12 +299,10 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                 dmma884(e0, e1, a0, PS[ps_idx(rb1, fk)]);
                 dmma884(d0, d1, a1, PS[ps_idx(rb0, fk + 4)]);
                 dmma884(e0, e1, a1, PS[ps_idx(rb1, fk + 4)]);
-                if (rowok) {
-                    if (ja < n) *pa0 = ca0 - d0;
-                    if (ja + 1 < n) *pa1 = ca1 - d1;
-                    if (jb < n) *pb0 = cb0 - e0;
-                    if (jb + 1 < n) *pb1 = cb1 - e1;
-                }
+                if (ja < n) *pa0 = ca0 - d0;
+                if (ja + 1 < n) *pa1 = ca1 - d1;
+                if (jb < n) *pb0 = cb0 - e0;
+                if (jb + 1 < n) *pb1 = cb1 - e1;
             }
         }
         CHOL_T(p0 >> 3, 4);
