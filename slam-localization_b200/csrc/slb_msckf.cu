@@ -246,16 +246,27 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
             const int nxq = (nxt + 1) >> 1, nat = max(ntiles - 1, 0);
             const int ntp = (nt + 1) >> 1;
             const unsigned ntm = ntp > 0 ? (65536u + ntp - 1) / ntp : 0u;   // u / ntp by multiplication (u < 2^10)
-            for (int t = warp - 1; t < nxq + nat + nwt * ntp; t += MS_W - 1) {
+            // warps 4, 8, 12 share warp 0's scheduler (and its FP64 pipe): they come last in the task order, so the long
+            // right-hand-side tasks never land next to the diagonal factorisation
+            const int rank = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : 11 + (warp >> 2);
+            for (int t = rank; t < nxq + nat + nwt * ntp; t += MS_W - 1) {
                 if (t < nxq) {
                     const int ia = 16 * t + fr, ib = ia + 8, ca = min(ia, nxr - 1), cb = min(ib, nxr - 1);
                     double *xa = ca < nx ? X + ca * xs : xe, *xb = cb < nx ? X + cb * xs : xe;
                     const double *lrow = A + tri(min(p0 + fr, n - 1), 0) + fk;   // L(p0 + fr, q + fk): B fragment
                     double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
-                    for (int q = 0; q < p0; q += 4) {
-                        const double bl = lrow[q];
-                        dmma884(d0, d1, xa[q + fk], bl);
-                        dmma884(e0, e1, xb[q + fk], bl);
+                    {   // p0 is a multiple of 8: two k-steps per trip on separate accumulators (four DMMA chains in flight)
+                        double d2 = 0.0, d3 = 0.0, e2 = 0.0, e3 = 0.0;
+#pragma unroll 2
+                        for (int q = 0; q < p0; q += 8) {
+                            const double bl0 = lrow[q], bl1 = lrow[q + 4];
+                            const double xa0 = xa[q + fk], xa1 = xa[q + fk + 4], xb0 = xb[q + fk], xb1 = xb[q + fk + 4];
+                            dmma884(d0, d1, xa0, bl0);
+                            dmma884(e0, e1, xb0, bl0);
+                            dmma884(d2, d3, xa1, bl1);
+                            dmma884(e2, e3, xb1, bl1);
+                        }
+                        d0 += d2; d1 += d3; e0 += e2; e1 += e3;
                     }
                     const int c0 = p0 + 2 * fk, k0 = p0 + fk, k1 = k0 + 4;
                     const bool v0 = c0 < n, v1 = c0 + 1 < n, oka = ia < nxr, okb = ib < nxr;
