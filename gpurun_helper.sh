@@ -7,8 +7,8 @@ import json
 d=json.loads(open('gpurun_out/tmp_bench.json').read().strip().splitlines()[-1]); print('$w', 'value %.4g'%d['value'], 'ms %.3f'%d['ms_per_step'])"
 done
 cp slam-localization_b200/csrc/libslb.so /tmp/libslb_orig.so
-for v in t1; do
+for v in t0; do
 cp tmp_exp/libslb_$v.so slam-localization_b200/csrc/libslb.so
-for w in ukf; do echo "== $v $w"; timeout 120 python profiles/chol_timing.py $w slam-localization_b200/csrc/libslb.so 2>&1 | tail -16; done
+for w in ekf; do echo "== $v $w"; timeout 120 python profiles/chol_timing.py $w slam-localization_b200/csrc/libslb.so 2>&1 | tail -16; done
 done
 cp /tmp/libslb_orig.so slam-localization_b200/csrc/libslb.so

@@ -68,9 +68,9 @@ SLB_DEV void tri_tile(int t, int &tr, int &tc) {
 // Optional right-hand sides: nx rows X (row stride xs) plus one more row xe are carried through the same panel
 // solves and trailing updates, i.e. on return [X; xe] holds [X; xe] L^-T -- the triangular solve a Cholesky is
 // usually followed by, without its own serial panel chain and barriers.
-// Optional inverse factor: Wp (packed lower, preset to the identity by the caller) is treated as the right-hand side
-// I stored transposed -- row i of the right-hand side is column i of Wp -- so that it ends up as I L^-T transposed,
-// i.e. Wp = L^-1.  Only the tiles that can be non-zero (row tile <= current panel) are touched.
+// Optional inverse factor: Wp (packed lower) receives L^-1.  It is the right-hand side I carried through the factorisation,
+// stored transposed -- row i of the right-hand side is column i of Wp -- so that I L^-T lands as its transpose.  Only the
+// tiles that can be non-zero (row tile <= current panel) exist; nothing has to be preset.
 // PS is a 1600-double scratch: every solved panel is also parked there as dense 8-wide rows, swizzled so that the
 // DMMA fragment loads of the trailing update are bank-conflict free (the packed triangle's row starts are not:
 // 2.4 wavefronts per ideal one, and the tiles are shared-memory-bandwidth bound).
@@ -150,51 +150,29 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
     for (int p0 = 0; p0 < n; p0 += 8) {
         const int pb = min(8, n - p0);
         const int r0 = p0 + pb, na = n - r0;
-        const int nwr = Wp ? r0 : 0;   // rows of the identity right-hand side that can be non-zero in this panel
-        const int nap = (na + 7) & ~7;   // staging: trailing rows | identity right-hand-side rows
         const double *dinv = dinv_of(p0);
         CHOL_T(p0 >> 3, 0);
-        for (int w = tid; w < na + nwr; w += MS_T) {
-            double x[8];
-            const int srow = w < na ? w : nap + (w - na);
+        for (int w = tid; w < na; w += MS_T) {
             // row * inv(L_pp)^T: x_c = sum_{q <= c} a_q Dinv[c][q] -- no dependent chain, and all loads precede the stores
-            double av[8];
-            if (w < na) {
-                double *Ai = A + tri(r0 + w, p0);
+            double x[8], av[8];
+            double *Ai = A + tri(r0 + w, p0);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) av[c] = c < pb ? Ai[c] : 0.0;
+            for (int c = 0; c < 8; ++c) av[c] = c < pb ? Ai[c] : 0.0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    double sv = 0.0;
+            for (int c = 0; c < 8; ++c) {
+                double sv = 0.0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (q <= c) sv = fma(av[q], dinv[c * 8 + q], sv);
-                    x[c] = sv;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c < pb) Ai[c] = x[c];
-            } else {
-                const int i = w - na;   // entries (i, col) with col < i are structural zeros and are not stored
-#pragma unroll
-                for (int c = 0; c < 8; ++c) av[c] = (c < pb && p0 + c >= i) ? Wp[tri(p0 + c, i)] : 0.0;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    double sv = 0.0;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (q <= c) sv = fma(av[q], dinv[c * 8 + q], sv);
-                    x[c] = sv;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c < pb && p0 + c >= i) Wp[tri(p0 + c, i)] = x[c];
+                for (int q = 0; q < 8; ++q)
+                    if (q <= c) sv = fma(av[q], dinv[c * 8 + q], sv);
+                x[c] = sv;
             }
-            if (na > 0) {   // a trailing update follows (then pb == 8 and all of x is defined)
 #pragma unroll
-                for (int c = 0; c < 8; c += 2)
-                    *reinterpret_cast<double2 *>(PS + ps_idx(srow, c)) = make_double2(x[c], x[c + 1]);
-            }
+            for (int c = 0; c < 8; ++c)
+                if (c < pb) Ai[c] = x[c];
+            // a trailing update follows (na > 0: then pb == 8 and all of x is defined): park the row for the fragment loads
+#pragma unroll
+            for (int c = 0; c < 8; c += 2)
+                *reinterpret_cast<double2 *>(PS + ps_idx(w, c)) = make_double2(x[c], x[c + 1]);
         }
         CHOL_T(p0 >> 3, 1);
         __syncthreads();
@@ -240,16 +218,15 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
             //                   X(:, p) = (X(:, p) - sum_{q < p} X(:, q) L(p, q)^T) inv(L_pp)^T -- a register-accumulated k-loop
             //                   (one shared L fragment for two row tiles) instead of a read-modify-write of every trailing
             //                   tile at every panel; this work grows with p while the trailing tiles shrink
+            //   [nxq, nxq+nwt)  identity right-hand side (Wp), left-looking in the same way; row tile r <= p starts its k-loop at
+            //                   column 8r, and the diagonal tile r = p is inv(L_pp)^T itself
             //   then            trailing tiles 1.. of the matrix (right-looking, tile 0 is warp 0's)
-            //   then            identity right-hand side (Wp), right-looking, two column tiles per task
             const int nwt = Wp ? (p0 >> 3) + 1 : 0;   // row tiles of the identity right-hand side reached so far
             const int nxq = (nxt + 1) >> 1, nat = max(ntiles - 1, 0);
-            const int ntp = (nt + 1) >> 1;
-            const unsigned ntm = ntp > 0 ? (65536u + ntp - 1) / ntp : 0u;   // u / ntp by multiplication (u < 2^10)
             // warps 4, 8, 12 share warp 0's scheduler (and its FP64 pipe): they come last in the task order, so the long
             // right-hand-side tasks never land next to the diagonal factorisation
             const int rank = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : 11 + (warp >> 2);
-            for (int t = rank; t < nxq + nat + nwt * ntp; t += MS_W - 1) {
+            for (int t = rank; t < nxq + nwt + nat; t += MS_W - 1) {
                 if (t < nxq) {
                     const int ia = 16 * t + fr, ib = ia + 8, ca = min(ia, nxr - 1), cb = min(ib, nxr - 1);
                     double *xa = ca < nx ? X + ca * xs : xe, *xb = cb < nx ? X + cb * xs : xe;
@@ -293,27 +270,41 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
                     if (okb && v1) xb[c0 + 1] = g1;
                     continue;
                 }
-                if (t < nxq + nat) {
-                    a_tile(t - nxq + 1);
+                if (t < nxq + nwt) {
+                    const int r = t - nxq, wi = 8 * r + fr;   // row of the right-hand side = column wi of Wp
+                    const int c0 = p0 + 2 * fk;
+                    if (8 * r == p0) {   // diagonal tile: I inv(L_pp)^T
+                        if (wi < n) {
+                            if (2 * fk >= fr && c0 < n) Wp[tri(c0, wi)] = dinv[(2 * fk) * 8 + fr];
+                            if (2 * fk + 1 >= fr && c0 + 1 < n) Wp[tri(c0 + 1, wi)] = dinv[(2 * fk + 1) * 8 + fr];
+                        }
+                        continue;
+                    }
+                    const double *lrow = A + tri(min(p0 + fr, n - 1), 0) + fk;   // L(p0 + fr, q + fk): B fragment
+                    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll 2
+                    for (int q = 8 * r; q < p0; q += 8) {   // entries left of the diagonal of Wp's transpose are structural zeros
+                        const int ka = q + fk, kb = ka + 4;
+                        const double xa0 = ka >= wi ? Wp[tri(ka, wi)] : 0.0, xa1 = kb >= wi ? Wp[tri(kb, wi)] : 0.0;
+                        dmma884(d0, d1, xa0, lrow[q]);
+                        dmma884(d2, d3, xa1, lrow[q + 4]);
+                    }
+                    const bool v0 = c0 < n, v1 = c0 + 1 < n;
+                    const int k0 = p0 + fk, k1 = k0 + 4;
+                    if (v0) Wp[tri(c0, wi)] = -(d0 + d2);   // in place, to be re-read as an A fragment
+                    if (v1) Wp[tri(c0 + 1, wi)] = -(d1 + d3);
+                    __syncwarp();
+                    const double aa0 = k0 < n ? Wp[tri(k0, wi)] : 0.0, aa1 = k1 < n ? Wp[tri(k1, wi)] : 0.0;
+                    const double bd0 = dinv[fr * 8 + fk], bd1 = dinv[fr * 8 + fk + 4];   // B[k][c] = Dinv[c][k]
+                    double f0 = 0.0, f1 = 0.0;
+                    dmma884(f0, f1, aa0, bd0);
+                    dmma884(f0, f1, aa1, bd1);
+                    __syncwarp();
+                    if (v0) Wp[tri(c0, wi)] = f0;
+                    if (v1) Wp[tri(c0 + 1, wi)] = f1;
                     continue;
                 }
-                const int u = t - nxq - nat, tr = (int)((u * ntm) >> 16), tc = 2 * (u - tr * ntp);
-                const int ai = 8 * tr + fr, ja = r0 + 8 * tc + 2 * fk, jb = ja + 8;   // ai <= p0 + 7 < n; columns > ai: stored triangle
-                const int rb0 = min(8 * tc + fr, na - 1), rb1 = min(8 * tc + 8 + fr, na - 1);
-                const int ra = nap + ai;   // structural zeros are staged as zeros
-                double *pa0 = Wp + tri(min(ja, n - 1), ai), *pa1 = Wp + tri(min(ja + 1, n - 1), ai);
-                double *pb0 = Wp + tri(min(jb, n - 1), ai), *pb1 = Wp + tri(min(jb + 1, n - 1), ai);
-                const double a0 = PS[ps_idx(ra, fk)], a1 = PS[ps_idx(ra, fk + 4)];
-                const double ca0 = *pa0, ca1 = *pa1, cb0 = *pb0, cb1 = *pb1;
-                double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
-                dmma884(d0, d1, a0, PS[ps_idx(rb0, fk)]);
-                dmma884(e0, e1, a0, PS[ps_idx(rb1, fk)]);
-                dmma884(d0, d1, a1, PS[ps_idx(rb0, fk + 4)]);
-                dmma884(e0, e1, a1, PS[ps_idx(rb1, fk + 4)]);
-                if (ja < n) *pa0 = ca0 - d0;
-                if (ja + 1 < n) *pa1 = ca1 - d1;
-                if (jb < n) *pb0 = cb0 - e0;
-                if (jb + 1 < n) *pb1 = cb1 - e1;
+                a_tile(t - nxq - nwt + 1);
             }
         }
         CHOL_T(p0 >> 3, 4);
@@ -852,9 +843,6 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             __syncthreads();
             // W = L^-1 (packed lower in RQ; T is consumed) comes out of the same sweep: the identity is carried through the
             // factorisation as a right-hand side (chol_blocked), so the inverse costs no serial chain of its own
-            for (int e = tid; e < M * (M + 1) / 2; e += MS_T) RQ[e] = 0.0;
-            __syncthreads();
-            if (tid < M) RQ[tri(tid, tid)] = 1.0;
             chol_blocked(RS, M, flags, invd, PS, nullptr, 0, 0, nullptr, RQ);
             if (!flags[0]) {
                 if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
