@@ -152,27 +152,22 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
         const int r0 = p0 + pb, na = n - r0;
         const double *dinv = dinv_of(p0);
         CHOL_T(p0 >> 3, 0);
-        for (int w = tid; w < na; w += MS_T) {
-            // row * inv(L_pp)^T: x_c = sum_{q <= c} a_q Dinv[c][q] -- no dependent chain, and all loads precede the stores
-            double x[8], av[8];
-            double *Ai = A + tri(r0 + w, p0);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) av[c] = c < pb ? Ai[c] : 0.0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                double sv = 0.0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (q <= c) sv = fma(av[q], dinv[c * 8 + q], sv);
-                x[c] = sv;
+        // panel below the diagonal block: rows * inv(L_pp)^T, one 8-row tile per warp as two DMMAs (B[k][c] = Dinv[c][k]); the
+        // result goes back in place and, as dense swizzled 8-wide rows, into the staging area for the fragment loads of the
+        // trailing update.  na > 0 implies a full panel (pb == 8).
+        for (int rt = warp; 8 * rt < na; rt += MS_W) {
+            const int w = 8 * rt + fr, wc = min(w, na - 1);
+            const double *Ai = A + tri(r0 + wc, p0);
+            double x0 = 0.0, x1 = 0.0;
+            dmma884(x0, x1, Ai[fk], dinv[fr * 8 + fk]);
+            dmma884(x0, x1, Ai[fk + 4], dinv[fr * 8 + fk + 4]);
+            __syncwarp();   // every lane has read its fragment of the rows before they are overwritten
+            if (w < na) {
+                double *Ao = A + tri(r0 + w, p0) + 2 * fk;
+                Ao[0] = x0;
+                Ao[1] = x1;
+                *reinterpret_cast<double2 *>(PS + ps_idx(w, 2 * fk)) = make_double2(x0, x1);
             }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < pb) Ai[c] = x[c];
-            // a trailing update follows (na > 0: then pb == 8 and all of x is defined): park the row for the fragment loads
-#pragma unroll
-            for (int c = 0; c < 8; c += 2)
-                *reinterpret_cast<double2 *>(PS + ps_idx(w, c)) = make_double2(x[c], x[c + 1]);
         }
         CHOL_T(p0 >> 3, 1);
         __syncthreads();
