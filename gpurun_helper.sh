@@ -1,6 +1,9 @@
 set +x
-cp slam-localization_b200/csrc/libslb.so /tmp/libslb_orig.so
-make -C slam-localization_b200/csrc timing CALL=1 EXTRA=-DSLB_EXP_NOK > /dev/null 2>&1
-cp slam-localization_b200/csrc/libslb_timing.so slam-localization_b200/csrc/libslb.so
-timeout 120 python profiles/chol_timing.py ukf slam-localization_b200/csrc/libslb.so 2>&1 | tail -15
-cp /tmp/libslb_orig.so slam-localization_b200/csrc/libslb.so
+mkdir -p gpurun_out/scale2
+for w in ukfom usckf msckf; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload $w > gpurun_out/scale2/bench_$w.json 2> gpurun_out/scale2/bench_$w.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/scale2/bench_$w.json').read().strip().splitlines()[-1]); print('$w', 'n_gpus', d['n_gpus'], 'value %.4g'%d['value'], 'ms %.4f'%d['ms_per_step'], 'e2e %.4g'%d['e2e']['value'], d['clocks'])"
+done
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 2 --warmup 1 > gpurun_out/scale2/bench_reference.json 2> gpurun_out/scale2/bench_reference.err; cut -c1-200 gpurun_out/scale2/bench_reference.json
