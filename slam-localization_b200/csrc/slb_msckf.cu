@@ -515,14 +515,27 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         if (mk < M) {
             // compact S -> region B (Z is dead), covXZ in place (kept[] is increasing, kept[p] >= p)
             for (int e = tid; e < mk * (mk + 1) / 2; e += MS_T) {
-                int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-                while (tri(r, 0) > e) --r;
-                while (tri(r + 1, 0) <= e) ++r;
+                int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+                r += (tri(r + 1, 0) <= e) - (tri(r, 0) > e);
                 const int c = e - tri(r, 0);
                 RB[e] = RA[tri(kept[r], kept[c])];
             }
-            for (int i = tid; i < N; i += MS_T)
-                for (int p = 0; p < mk; ++p) RC[i * MS_ZS + p] = RC[i * MS_ZS + kept[p]];
+            // a warp per row of covXZ: the row is gathered into registers before it is overwritten (m <= 128 = 4 per lane)
+            for (int i = warp; i < N; i += MS_W) {
+                double *row = RC + i * MS_ZS;
+                double v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int pp = lane + 32 * q;
+                    v[q] = pp < mk ? row[kept[pp]] : 0.0;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int pp = lane + 32 * q;
+                    if (pp < mk) row[pp] = v[q];
+                }
+            }
             if (tid < mk) wv[tid] = nu[kept[tid]];
             __syncthreads();
             if (tid < mk) nu[tid] = wv[tid];
