@@ -46,19 +46,20 @@ def test_ekf_update_gate_and_outliers(slo, frac):
     assert np.linalg.eigvalsh(symmetrize_lower(f.P())[ok]).min() > 0
 
 
-def test_ekf_update_fewer_clones(slo):
-    """k = 9 clones (N = 66) with 50 features: different tile remainders everywhere."""
+@pytest.mark.parametrize("k,nfeat", [(9, 50), (4, 21), (7, 43), (10, 37)])
+def test_ekf_update_fewer_clones(slo, k, nfeat):
+    """Fewer clones / features (k = 9: N = 66): different panel and tile remainders everywhere (m >= N, the QR row rule)."""
     B = 12
-    sc = synth.msckf_scenario(B, seed=5, k=9, nfeat=50)
-    f = engine.Msckf(B, nclones=9)
+    sc = synth.msckf_scenario(B, seed=5, k=k, nfeat=nfeat)
+    f = engine.Msckf(B, nclones=k)
     f.set_state(sc["mu"], sc["P"])
     f.update_ekf(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"], gate=True)
-    mu_r, P_r, out_r, st_r = slo.msckf_update_ekf(slo.MM_MSCKF_REPROJ, 9, sc["mu"], symmetrize_lower(sc["P"]), sc["landmarks"],
+    mu_r, P_r, out_r, st_r = slo.msckf_update_ekf(slo.MM_MSCKF_REPROJ, k, sc["mu"], symmetrize_lower(sc["P"]), sc["landmarks"],
                                                   sc["z"], sc["R"], gate=True)
     np.testing.assert_array_equal(f.outliers(), out_r)
     np.testing.assert_array_equal(f.status(), st_r)
     ok = st_r == 0
-    assert_parity(slo, [0, 1, 0, 0] + [0, 1] * 9, f.mu(), symmetrize_lower(f.P()), mu_r, symmetrize_lower(P_r), mask=ok)
+    assert_parity(slo, [0, 1, 0, 0] + [0, 1] * k, f.mu(), symmetrize_lower(f.P()), mu_r, symmetrize_lower(P_r), mask=ok)
 
 
 def test_ekf_update_general_R(slo):
