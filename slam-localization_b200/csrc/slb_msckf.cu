@@ -7,7 +7,7 @@
 // shared memory (~224 KB: one CTA per SM, persistent over the batch):
 //   A  5056 doubles : P -> L (Cholesky in place) ... later S -> Ls ... later P_new -> L2
 //   B 14800 doubles : Z (148 x 100) ... later compacted S' (outliers) ... later X / D (148 x 84)
-//   C  7200 doubles : W -> covXZ (in-place TRMM) -> Y = covXZ Ls^-T (in-place TRSM)
+//   C  7200 doubles : W -> covXZ (in-place TRMM) -> Y = covXZ Ls^-T (in place, inside chol_blocked)
 // Algebra: with S = Ls Ls^T and Y = covXZ Ls^-T the reference's  K = covXZ S^-1, Pk -= K S K^T,
 // delta = K nu  become  Pk -= Y Y^T,  delta = Y (Ls^-1 nu)  -- same maths as :257-263 without forming
 // the explicit inverse (quirk Q9).  covXZ = L W with W_j = 0.5 (Z+_j - Z-_j), as in the other kernels.
