@@ -37,7 +37,8 @@ constexpr int MS_D = 896;                        // small vectors
 constexpr int MS_SMEM_DOUBLES = MS_A + MS_B + MS_C + MS_D;
 static_assert(MS_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF update working set exceeds shared memory");
 static_assert(MS_NSPAD * MS_QS <= MS_B, "sigma points do not fit region B");
-static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_A && MS_A + 1600 <= MS_B, "compacted S + panel staging do not fit region B");
+static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_A && MS_A + 2 * 1600 <= MS_B, "compacted S + two panel stagings do not fit region B");
+static_assert(2400 >= 32 * MS_NMAX && 2400 + MS_NMAX * (MS_NMAX + 1) / 2 <= MS_C, "parked factor does not fit region C");
 
 // linear index of a lower-triangular tile -> (tr, tc), tc <= tr: a constant-memory table (the index is warp-uniform,
 // so the lookup is one broadcast load instead of a sqrtf + fix-up per tile)
@@ -83,6 +84,7 @@ __device__ int chol_dbg_call;
 #define CHOL_T(panel, slot) do { } while (0)
 #endif
 constexpr int MS_PS = 1600;
+constexpr int MS_NXL = 2400;   // offset in region C of the next instance's factor (above the <= 32 x 72 partial sums of the mean)
 SLB_DEV int ps_idx(int srow, int k) { return srow * 8 + ((k + 4 * ((srow >> 1) & 1)) & 7); }
 SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *PS, double *X = nullptr, int nx = 0,
                           int xs = 0, double *xe = nullptr, double *Wp = nullptr) {
@@ -311,6 +313,126 @@ SLB_DEV void chol_blocked(double *A, int n, int *ok_flag, double *invd, double *
 #endif
 }
 
+// ---- two factorisations in lockstep -----------------------------------------------------------------------------------
+// A Cholesky without right-hand sides keeps one warp busy (the diagonal-block chain) and 15 waiting.  chol(P_new) of the
+// current instance and chol(P) of the NEXT instance (its record is already in shared memory) are independent, so they are
+// factored panel by panel in the same phases: warp 0 owns the diagonal blocks of A1, warp 1 (another scheduler) those of
+// A2, the panel solves and trailing tiles of both are spread over the other warps.  Same arithmetic per matrix as
+// chol_blocked (bitwise: the per-matrix operations and their order do not depend on which warp runs them).
+SLB_DEV void dual_factor_diag(double *A, int n, int p0, double a0, double a1, double *dinv, int *ok_flag, int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int pb = min(8, n - p0);
+    const int i = fr, j0 = 2 * fk, j1 = j0 + 1;
+    double m0 = (i == j0) ? 1.0 : 0.0, m1 = (i == j1) ? 1.0 : 0.0;
+    double di = 1.0, dj0 = 1.0, dj1 = 1.0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < pb) {
+            const int kh = k >> 1;
+            const double ak = (k & 1) ? a1 : a0;
+            const double d = bcast(ak, 4 * k + kh);
+            const double aik = __shfl_sync(0xffffffffu, ak, 4 * i + kh);
+            ok = ok && (d > 0.0);
+            if (i == k) di = d;
+            if (j0 == k) dj0 = d;
+            if (j1 == k) dj1 = d;
+            if (k < 7) {
+                const double ajk0 = __shfl_sync(0xffffffffu, ak, 4 * j0 + kh), ajk1 = __shfl_sync(0xffffffffu, ak, 4 * j1 + kh);
+                const double mk0 = bcast(m0, 4 * k + fk), mk1 = bcast(m1, 4 * k + fk);
+                const double v = aik * rcp_fast(d);
+                if (j0 > k) a0 = fma(-v, ajk0, a0);
+                if (j1 > k) a1 = fma(-v, ajk1, a1);
+                const double vm = i > k ? v : 0.0;
+                m0 = fma(-vm, mk0, m0);
+                m1 = fma(-vm, mk1, m1);
+            }
+        }
+    }
+    double si, ri, s0, r0c, s1, r1c;
+    sqrt_rsqrt(di, si, ri);
+    sqrt_rsqrt(dj0, s0, r0c);
+    sqrt_rsqrt(dj1, s1, r1c);
+    if (i < pb) {
+        if (j0 <= i) A[tri(p0 + i, p0 + j0)] = (j0 == i) ? s0 : a0 * r0c;
+        if (j1 <= i) A[tri(p0 + i, p0 + j1)] = (j1 == i) ? s1 : a1 * r1c;
+    }
+    *reinterpret_cast<double2 *>(dinv + i * 8 + j0) = make_double2(j0 <= i ? ri * m0 : 0.0, j1 <= i ? ri * m1 : 0.0);
+    ok = __all_sync(0xffffffffu, ok);
+    if (!ok && lane == 0) *ok_flag = 0;
+}
+
+SLB_DEV void chol_dual(double *A1, double *A2, int n, int *ok1, int *ok2, double *PS1, double *PS2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    auto dinv_of = [&](double *PS, int p0) { return PS + MS_PS - 128 + 64 * ((p0 >> 3) & 1); };
+    if (warp < 2) {
+        double *A = warp ? A2 : A1;
+        const int pb = min(8, n);
+        dual_factor_diag(A, n, 0, (fr < pb && 2 * fk <= fr) ? A[tri(fr, 2 * fk)] : 0.0, (fr < pb && 2 * fk + 1 <= fr) ? A[tri(fr, 2 * fk + 1)] : 0.0,
+                         dinv_of(warp ? PS2 : PS1, 0), warp ? ok2 : ok1, lane);
+    }
+    __syncthreads();
+    for (int p0 = 0; p0 < n; p0 += 8) {
+        const int pb = min(8, n - p0);
+        const int r0 = p0 + pb, na = n - r0;
+        const int ntl = (na + 7) >> 3;
+        for (int t = warp; t < 2 * ntl; t += MS_W) {   // panel solve: rows * inv(L_pp)^T, one 8-row tile per warp
+            const int m = t >= ntl, rt = t - m * ntl;
+            double *A = m ? A2 : A1, *PS = m ? PS2 : PS1;
+            const double *dinv = dinv_of(PS, p0);
+            const int w = 8 * rt + fr, wc = min(w, na - 1);
+            const double *Ai = A + tri(r0 + wc, p0);
+            double x0 = 0.0, x1 = 0.0;
+            dmma884(x0, x1, Ai[fk], dinv[fr * 8 + fk]);
+            dmma884(x0, x1, Ai[fk + 4], dinv[fr * 8 + fk + 4]);
+            __syncwarp();
+            if (w < na) {
+                double *Ao = A + tri(r0 + w, p0) + 2 * fk;
+                Ao[0] = x0;
+                Ao[1] = x1;
+                *reinterpret_cast<double2 *>(PS + ps_idx(w, 2 * fk)) = make_double2(x0, x1);
+            }
+        }
+        __syncthreads();
+        const int nt = (na + 7) >> 3, ntiles = nt * (nt + 1) / 2;
+        if (warp < 2) {
+            if (ntiles > 0) {   // look-ahead on the next diagonal block of this warp's matrix
+                double *A = warp ? A2 : A1, *PS = warp ? PS2 : PS1;
+                const int rr = min(fr, na - 1), pbn = min(8, na);
+                const int i = r0 + fr, j = r0 + 2 * fk;
+                const bool v0 = fr < pbn && 2 * fk <= fr, v1 = fr < pbn && 2 * fk + 1 <= fr;
+                const double x0 = PS[ps_idx(rr, fk)], x1 = PS[ps_idx(rr, fk + 4)];
+                const double c0 = v0 ? A[tri(i, j)] : 0.0, c1 = v1 ? A[tri(i, j + 1)] : 0.0;
+                double d0 = 0.0, d1 = 0.0;
+                dmma884(d0, d1, x0, x0);
+                dmma884(d0, d1, x1, x1);
+                dual_factor_diag(A, n, r0, v0 ? c0 - d0 : 0.0, v1 ? c1 - d1 : 0.0, dinv_of(PS, r0), warp ? ok2 : ok1, lane);
+            }
+        } else {
+            const int nat = max(ntiles - 1, 0);
+            for (int t = warp - 2; t < 2 * nat; t += MS_W - 2) {
+                const int m = t >= nat, tt = t - m * nat + 1;
+                double *A = m ? A2 : A1, *PS = m ? PS2 : PS1;
+                int tr, tc;
+                tri_tile(tt, tr, tc);
+                const int i0 = r0 + 8 * tr, j0 = r0 + 8 * tc;
+                double d0 = 0.0, d1 = 0.0;
+                const int ra = min(8 * tr + fr, na - 1), rb = min(8 * tc + fr, na - 1);
+                const int i = i0 + fr, j = j0 + 2 * fk;
+                const bool v0 = i < n && j <= i, v1 = i < n && j + 1 <= i;
+                double *po = A + tri(min(i, n - 1), min(j, i));
+                const double c0 = v0 ? po[0] : 0.0, c1 = v1 ? po[1] : 0.0;
+                dmma884(d0, d1, PS[ps_idx(ra, fk)], PS[ps_idx(rb, fk)]);
+                dmma884(d0, d1, PS[ps_idx(ra, fk + 4)], PS[ps_idx(rb, fk + 4)]);
+                if (v0) po[0] = c0 - d0;
+                if (v1) po[1] = c1 - d1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // removeRow(2i); removeRow(2i+1) of the reference's gate loop applied to the index list kept[0..len) by one warp;
 // the second index is NOT re-based (quirk Q6).  Returns the new length.
 SLB_DEV int gate_remove_pair(int *kept, int len, int i, int lane) {
@@ -351,23 +473,27 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
     const int NP = N * (N + 1) / 2;
     const int nrt = (N + 7) >> 3;                     // 8-row tiles of the state
 
-    bool fetched = false;   // CTA-uniform: region A already holds (or is receiving) this instance's record
+    // CTA-uniform: the previous iteration already factored this instance's covariance (chol_dual, in lockstep with its own
+    // chol(P_new)) and parked L at RC + MS_NXL, its pivot flag in flags[5]
+    bool have_l = false;
     for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         double *Pg = a.P + (size_t)inst * a.pstride;
         double *mug = a.mu + (size_t)inst * a.qstride;
         const double *zg = a.z + (size_t)inst * M;
         __syncthreads();
-        // the record was fetched into region A during the tail of the previous instance (see below) unless that one
-        // left early; cp.async keeps every load of the record in flight at once
-        if (!fetched)
+        // cp.async keeps every load of the record in flight at once
+        if (have_l) {
+            for (int e = tid; e < NP; e += MS_T) RA[e] = RC[MS_NXL + e];
+        } else {
             for (int e = tid; e < NP; e += MS_T) pred_cp_async8(RA + e, Pg + e);
-        fetched = false;
+        }
         for (int e = tid; e < QD; e += MS_T) mu[e] = mug[e];
-        if (tid == 0) { flags[0] = 1; flags[1] = M; flags[2] = 0; }
+        if (tid == 0) { flags[0] = have_l ? flags[5] : 1; flags[1] = M; flags[2] = 0; }
         pred_cp_async_wait_all();
         __syncthreads();
-        // ---- L = chol(Pk) (:229 -> :412) -------------------------------------------------------------
-        chol_blocked(RA, N, flags, invd, PS);
+        // ---- L = chol(Pk) (:229 -> :412), unless the previous iteration already did it ------------------
+        if (!have_l) chol_blocked(RA, N, flags, invd, PS);
+        have_l = false;
         int st = 0;
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
@@ -552,6 +678,14 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
         }
+        // region B (the compacted S' and the panel staging) is dead: the next instance's covariance record goes there now, to be
+        // factored together with this instance's P_new below
+        const bool more = inst + (int)gridDim.x < a.B;
+        if (more) {
+            const double *Pn = a.P + (size_t)(inst + gridDim.x) * a.pstride;
+            for (int e = tid; e < NP; e += MS_T) pred_cp_async8(RB + e, Pn + e);
+            if (tid == 0) flags[5] = 1;
+        }
         // ---- delta = Y w, w = the extra row of the solve ---------------------------------------------------------
         for (int i = warp; i < N; i += MS_W) {
             double s = 0.0;
@@ -585,9 +719,19 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 }
             }
         }
+        pred_cp_async_wait_all();
         __syncthreads();
-        // ---- applyDelta(K nu) (:263 -> :659-666): L2 = chol(P_new), X = mu [+] (delta +- L2 e_j) ----------
-        chol_blocked(RA, N, flags, invd, PS);
+        // ---- applyDelta(K nu) (:263 -> :659-666): L2 = chol(P_new), X = mu [+] (delta +- L2 e_j).  A factorisation without
+        //      right-hand sides keeps one warp busy and fifteen waiting, so chol(P) of the NEXT instance runs in lockstep with
+        //      it (chol_dual) and is parked in region C (Y is dead; the mean's partial sums stay below MS_NXL) ----------------
+        if (more) {
+            chol_dual(RA, RB, N, flags, flags + 5, PS, PS + MS_PS);
+            for (int e = tid; e < NP; e += MS_T) RC[MS_NXL + e] = RB[e];
+            have_l = true;
+            __syncthreads();   // region B is about to receive the sigma points
+        } else {
+            chol_blocked(RA, N, flags, invd, PS);
+        }
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
@@ -612,13 +756,6 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
-        // L2 is dead from here on: fetch the next instance's covariance record into region A behind the mean,
-        // deviation and covariance phases of this one
-        if (inst + (int)gridDim.x < a.B) {
-            const double *Pn = a.P + (size_t)(inst + gridDim.x) * a.pstride;
-            for (int e = tid; e < NP; e += MS_T) pred_cp_async8(RA + e, Pn + e);
-            fetched = true;
-        }
         // manifold mean (:499-525): ref = X0; do { d = mean(Xi [-] ref); ref [+]= d } while (|d| > 1e-6 ...)
         for (int e = tid; e < QD; e += MS_T) ref[e] = RB[e];
         __syncthreads();

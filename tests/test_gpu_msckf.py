@@ -94,6 +94,34 @@ def test_msckf_indefinite_covariance_is_flagged():
     np.testing.assert_array_equal(f.mu()[3], sc["mu"][3])
 
 
+def test_msckf_update_several_instances_per_cta(slo):
+    """More instances than SMs: every CTA walks several instances, and from the second one on the covariance factor of
+    an instance is computed one iteration early, in lockstep with the previous instance's chol(P_new) (chol_dual).
+    Parity against the oracle with the gate on and outliers present, and an indefinite covariance in the second and
+    third round of a CTA (flagged when it becomes the 'next' instance; state untouched; neighbours unaffected)."""
+    B, k, nfeat = 333, 10, 50
+    sc = synth.msckf_scenario(B, seed=57, k=k, nfeat=nfeat, outlier_frac=0.04)
+    P = sc["P"].copy()
+    bad = [160, 161, 310]
+    for i in bad:
+        P[i, 20, 20] = -1.0
+    f = engine.Msckf(B, nclones=k)
+    f.set_state(sc["mu"], P)
+    f.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"], gate=True)
+    mu, Pr, out, st, _ = slo.msckf_update(slo.MM_MSCKF_REPROJ, k, sc["mu"], P, sc["landmarks"], sc["z"], sc["R"],
+                                         gate=True, nthreads=8)
+    gs = f.status()
+    assert all(gs[i] & engine.ST_CHOL_FAIL for i in bad)
+    np.testing.assert_array_equal(f.mu()[bad], sc["mu"][bad])
+    good = np.ones(B, bool)
+    good[bad] = False
+    ok = good & (st == 0)
+    assert ok.sum() > B // 2
+    np.testing.assert_array_equal(gs[ok], 0)
+    np.testing.assert_array_equal(f.outliers()[good], out[good])
+    parity.assert_parity(slo, blocks(k), f.mu(), f.P(), mu, Pr, mask=ok)
+
+
 def test_msckf_full_size_properties():
     """16,384 instances (BASELINE config 3): batch results are independent of the batch (instance i equals
     instance i run in a small batch, bit for bit), covariances stay symmetric PSD, status clean."""
