@@ -537,13 +537,26 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             nu[tid] = zg[tid] - zb;
         }
         // ---- W_j = 0.5 (Z+_j - Z-_j) into region C ---------------------------------------------------
-        for (int j = warp; j < N; j += MS_W)
-            for (int c = lane; c < M; c += 32)
-                RC[j * MS_ZS + c] = 0.5 * (RB[(1 + 2 * j) * MS_ZS + c] - RB[(2 + 2 * j) * MS_ZS + c]);
-        __syncthreads();
-        // centre Z for the covariance; the pad rows NS..NSPAD-1 are zeroed so the k-loop of S needs no bound check
-        for (int s = warp; s < MS_NSPAD; s += MS_W)
-            for (int c = lane; c < M; c += 32) RB[s * MS_ZS + c] = s < NS ? RB[s * MS_ZS + c] - zbar[c] : 0.0;
+        //      and, in the same pass over the pair of rows, centre Z for the covariance (each element is read once; the four
+        //      column chunks of a row pair are independent chains).  The pad rows NS..NSPAD-1 are zeroed so that the k-loop
+        //      of S needs no bound check.
+        __syncthreads();   // zbar
+        for (int j = warp; j < N; j += MS_W) {
+            double *zp = RB + (1 + 2 * j) * MS_ZS, *zm = zp + MS_ZS;
+#pragma unroll
+            for (int q = 0; q < (MS_MMAX + 31) / 32; ++q) {
+                const int c = lane + 32 * q;
+                if (c < M) {
+                    const double vp = zp[c], vm = zm[c], zb = zbar[c];
+                    RC[j * MS_ZS + c] = 0.5 * (vp - vm);
+                    zp[c] = vp - zb;
+                    zm[c] = vm - zb;
+                }
+            }
+        }
+        for (int e = tid; e < M; e += MS_T) RB[e] -= zbar[e];
+        for (int e = tid; e < (MS_NSPAD - NS) * M; e += MS_T) RB[(NS + e / M) * MS_ZS + e % M] = 0.0;
+        __syncthreads();   // W complete before the TRMM reads other warps' rows
         // ---- covXZ = L W (:239 -> :635-657): in-place TRMM on region C.  A warp owns an 8-column strip and
         //      walks the row tiles bottom-up (row tile tr reads only rows <= 8 tr + 7 of its own strip) ------
         for (int tc = warp; tc < ((M + 7) >> 3); tc += MS_W) {
