@@ -929,6 +929,8 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
     auto Psym = [&](int i, int j) { return i >= j ? RA[tri(i, j)] : RA[tri(j, i)]; };
     constexpr int QP = ME_QP;
 
+    // With R = sigma^2 I (flagged once per launch by msckf_rdiag_kernel) the update takes the direct form (see below)
+    const bool direct = a.misc[1] != 0;
     for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         double *Pg = a.P + (size_t)inst * a.pstride;
         double *mug = a.mu + (size_t)inst * a.qstride;
@@ -936,7 +938,8 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         __syncthreads();
         for (int e = tid; e < NP; e += MS_T) RA[e] = Pg[e];
         for (int e = tid; e < QD; e += MS_T) mu[e] = mug[e];
-        for (int e = tid; e < M * ME_HS; e += MS_T) RH[e] = 0.0;
+        if (!direct)   // the dense H is only read by the QR path
+            for (int e = tid; e < M * ME_HS; e += MS_T) RH[e] = 0.0;
         if (tid == 0) { flags[0] = 1; flags[1] = M; flags[2] = 0; }
         __syncthreads();
         // ---- mean_z = h(mu, H), innovation (:311-313): thread per feature ---------------------------------------
@@ -971,12 +974,17 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 const double h0 = iz * (J[0][cc] - z0 * J[2][cc]), h1 = iz * (J[1][cc] - z1 * J[2][cc]);
                 Hb[(2 * f) * 6 + cc] = h0;
                 Hb[(2 * f + 1) * 6 + cc] = h1;
-                RH[(2 * f) * ME_HS + 12 + 6 * c + cc] = h0;
-                RH[(2 * f + 1) * ME_HS + 12 + 6 * c + cc] = h1;
+                if (!direct) {
+                    RH[(2 * f) * ME_HS + 12 + 6 * c + cc] = h0;
+                    RH[(2 * f + 1) * ME_HS + 12 + 6 * c + cc] = h1;
+                }
             }
         }
         __syncthreads();
         int mk = M;
+        // in the direct form the dense H in RH is not needed, so the gate's L^-1 goes there and T = H P survives in RQ to be
+        // reused as (P Hc^T)^T
+        double *Wq = direct ? RH : RQ;
         if (a.gate) {
             // ---- information = (H P H^T + R)^-1 (:765-766).  T = H P over the clone columns (6 FMA per entry) ------
             for (int e = tid; e < M * (N - 12); e += MS_T) {
@@ -1001,7 +1009,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             __syncthreads();
             // W = L^-1 (packed lower in RQ; T is consumed) comes out of the same sweep: the identity is carried through the
             // factorisation as a right-hand side (chol_blocked), so the inverse costs no serial chain of its own
-            chol_blocked(RS, M, flags, invd, PS, nullptr, 0, 0, nullptr, RQ);
+            chol_blocked(RS, M, flags, invd, PS, nullptr, 0, 0, nullptr, Wq);
             if (!flags[0]) {
                 if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
                 continue;
@@ -1012,11 +1020,11 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                 const int f = tid >> 3, part = tid & 7, ia = 2 * f, ib = ia + 1;
                 double i00 = 0.0, i10 = 0.0, i11 = 0.0;
                 if (part == 0 && f < NF) {
-                    const double wa = RQ[tri(ia, ia)];
+                    const double wa = Wq[tri(ia, ia)];
                     i00 = wa * wa;
                 }
                 for (int r = ib + part; r < (f < NF ? M : 0); r += 8) {
-                    const double wa = RQ[tri(r, ia)], wb = RQ[tri(r, ib)];
+                    const double wa = Wq[tri(r, ia)], wb = Wq[tri(r, ib)];
                     i00 = fma(wa, wa, i00);
                     i10 = fma(wa, wb, i10);
                     i11 = fma(wb, wb, i11);
@@ -1074,20 +1082,28 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         //   S' = Hc P Hc^T + R',  K = P Hc^T S'^-1,
         // to rounding (3e-15 against the QR form on the config-3 scenario).  That needs no Householder QR, no thin Q, no
         // Q^T R Q and no second factorisation when nothing was rejected: the Cholesky factor of S from the outlier gate is reused.
-        const bool direct = a.misc[1] != 0;
         double *Yb = RH;   // Y = covXZ Ls^-T: base, row stride, number of measurement rows it was solved against
         int ys = ME_HS, mq = N;
         bool solved = false;   // the triangular solve was folded into the factorisation (chol_blocked with right-hand sides)
         if (direct) {
-            Yb = RQ; ys = MS_ZS; mq = mk;
-            // covXZ' = P Hc^T (N x mk) into RQ (the triangular inverse that lived there is consumed): 6 FMA per entry
-            for (int e = tid; e < N * mk; e += MS_T) {
+            // covXZ' = P Hc^T (N x mk), 6 FMA per entry.  After the gate its clone rows are the (compacted) transpose of T, which
+            // still sits in RQ: they are copied into RH (the triangular inverse that lived there is consumed) and only the 12
+            // statek rows are computed; without the gate everything is computed, into RQ.
+            Yb = a.gate ? RH : RQ; ys = MS_ZS; mq = mk;
+            const int ncomp = a.gate ? 12 : N;   // rows computed from scratch
+            for (int e = tid; e < ncomp * mk; e += MS_T) {
                 const int i = e / mk, pcol = e - i * mk, r = compact ? kept[pcol] : pcol;
                 const int a0 = 12 + 6 * ((r >> 1) % k);
                 double sacc = 0.0;
 #pragma unroll
                 for (int u = 0; u < 6; ++u) sacc = fma(Hb[r * 6 + u], Psym(a0 + u, i), sacc);
-                RQ[i * MS_ZS + pcol] = sacc;
+                Yb[i * MS_ZS + pcol] = sacc;
+            }
+            if (a.gate) {
+                for (int e = tid; e < (N - 12) * mk; e += MS_T) {
+                    const int pcol = e / (N - 12), i = 12 + (e - pcol * (N - 12));   // consecutive threads read consecutive T entries
+                    Yb[i * MS_ZS + pcol] = RQ[(compact ? kept[pcol] : pcol) * ME_HS + i];
+                }
             }
             if (tid < mk) wv[tid] = nu[compact ? kept[tid] : tid];
             __syncthreads();
@@ -1105,7 +1121,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
                     const int a0 = 12 + 6 * ((rr >> 1) % k);
                     double sacc = __ldg(a.R + (size_t)rr * M + rc);
 #pragma unroll
-                    for (int u = 0; u < 6; ++u) sacc = fma(Hb[rr * 6 + u], RQ[(a0 + u) * MS_ZS + pc], sacc);
+                    for (int u = 0; u < 6; ++u) sacc = fma(Hb[rr * 6 + u], Yb[(a0 + u) * MS_ZS + pc], sacc);
                     RS[e] = sacc;
                 }
                 __syncthreads();
