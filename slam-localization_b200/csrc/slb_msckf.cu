@@ -987,13 +987,19 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
         double *Wq = direct ? RH : RQ;
         if (a.gate) {
             // ---- information = (H P H^T + R)^-1 (:765-766).  T = H P over the clone columns (6 FMA per entry) ------
-            for (int e = tid; e < M * (N - 12); e += MS_T) {
-                const int r = e / (N - 12), j = 12 + (e - r * (N - 12));
-                const int a0 = 12 + 6 * ((r >> 1) % k);
-                double sacc = 0.0;
+            // the two rows of a feature share their six rows of P: one item = (feature, column)
+            for (int e = tid; e < NF * (N - 12); e += MS_T) {
+                const int f = e / (N - 12), j = 12 + (e - f * (N - 12));
+                const int a0 = 12 + 6 * (f % k);
+                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int u = 0; u < 6; ++u) sacc = fma(Hb[r * 6 + u], Psym(a0 + u, j), sacc);
-                RQ[r * ME_HS + j] = sacc;
+                for (int u = 0; u < 6; ++u) {
+                    const double pv = Psym(a0 + u, j);
+                    s0 = fma(Hb[(2 * f) * 6 + u], pv, s0);
+                    s1 = fma(Hb[(2 * f + 1) * 6 + u], pv, s1);
+                }
+                RQ[(2 * f) * ME_HS + j] = s0;
+                RQ[(2 * f + 1) * ME_HS + j] = s1;
             }
             __syncthreads();
             for (int e = tid; e < M * (M + 1) / 2; e += MS_T) {
