@@ -381,7 +381,7 @@ class MsckfWorkload:
 
     phases = ("predict12_kernel", "msckf_update_kernel")
     dominant = 1
-    traffic = (92.7e6 + 35.3e6) / 4096 * 16384   # ncu dram read+write of msckf_update_kernel (4096-instance launch) scaled
+    traffic = (92.7e6 + 36.7e6) / 4096 * 16384   # ncu dram read+write of msckf_update_kernel (4096-instance launch) scaled
 
     def step_phase(self, k, p):
         e = self.engine

@@ -252,7 +252,7 @@ class MsckfEkfWorkload:
     kernel = "slbd::msckf_ekf_update_kernel (+ predict12_kernel)"
     phases = ("predict12_kernel", "msckf_ekf_update_kernel")
     dominant = 1
-    traffic = (46.4e6 + 0.53e6) / 2048 * 16384       # ncu dram read+write (2048-instance launch: the write-back stays in L2)
+    traffic = (46.4e6 + 1.06e6) / 2048 * 16384       # ncu dram read+write (2048-instance launch: the write-back stays in L2)
 
     def __init__(self, rank, seed=777):
         self.sc = synth.msckf_scenario(self.NPRIOR, seed=seed + 1000 * rank, k=self.K, nfeat=self.NFEAT)
