@@ -94,17 +94,18 @@ def test_msckf_indefinite_covariance_is_flagged():
     np.testing.assert_array_equal(f.mu()[3], sc["mu"][3])
 
 
-def test_msckf_update_several_instances_per_cta(slo):
+@pytest.mark.parametrize("k,nfeat", [(10, 50), (3, 13), (1, 4)])
+def test_msckf_update_several_instances_per_cta(slo, k, nfeat):
     """More instances than SMs: every CTA walks several instances, and from the second one on the covariance factor of
     an instance is computed one iteration early, in lockstep with the previous instance's chol(P_new) (chol_dual).
     Parity against the oracle with the gate on and outliers present, and an indefinite covariance in the second and
     third round of a CTA (flagged when it becomes the 'next' instance; state untouched; neighbours unaffected)."""
-    B, k, nfeat = 333, 10, 50
+    B = 333
     sc = synth.msckf_scenario(B, seed=57, k=k, nfeat=nfeat, outlier_frac=0.04)
     P = sc["P"].copy()
     bad = [160, 161, 310]
     for i in bad:
-        P[i, 20, 20] = -1.0
+        P[i, 14, 14] = -1.0
     f = engine.Msckf(B, nclones=k)
     f.set_state(sc["mu"], P)
     f.update(engine.MM_MSCKF_REPROJ, sc["landmarks"], sc["z"], sc["R"], gate=True)
