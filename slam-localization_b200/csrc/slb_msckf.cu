@@ -931,12 +931,20 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
 
     // With R = sigma^2 I (flagged once per launch by msckf_rdiag_kernel) the update takes the direct form (see below)
     const bool direct = a.misc[1] != 0;
+    bool fetched = false;   // CTA-uniform: RQ holds (or is receiving) this instance's covariance record, see below
     for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         double *Pg = a.P + (size_t)inst * a.pstride;
         double *mug = a.mu + (size_t)inst * a.qstride;
         const double *zg = a.z + (size_t)inst * M;
         __syncthreads();
-        for (int e = tid; e < NP; e += MS_T) RA[e] = Pg[e];
+        if (fetched) {
+            pred_cp_async_wait_all();
+            __syncthreads();
+            for (int e = tid; e < NP; e += MS_T) RA[e] = RQ[e];
+        } else {
+            for (int e = tid; e < NP; e += MS_T) RA[e] = Pg[e];
+        }
+        fetched = false;
         for (int e = tid; e < QD; e += MS_T) mu[e] = mug[e];
         if (!direct)   // the dense H is only read by the QR path
             for (int e = tid; e < M * ME_HS; e += MS_T) RH[e] = 0.0;
@@ -1116,6 +1124,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_ekf_update_kernel(slb::FilterAr
             if (tid < mk) {
                 nu[tid] = wv[tid];
                 Yb[N * ys + tid] = wv[tid];   // the innovation rides along as row N of the solve (see below)
+            }
+            if (a.gate && inst + (int)gridDim.x < a.B) {
+                // T is consumed: RQ is idle for the rest of this instance and receives the next instance's covariance record
+                const double *Pn = a.P + (size_t)(inst + gridDim.x) * a.pstride;
+                for (int e = tid; e < NP; e += MS_T) pred_cp_async8(RQ + e, Pn + e);
+                fetched = true;
             }
             if (compact || !a.gate) {
                 // S' = Hc covXZ' + R' (packed lower) and its Cholesky factor; otherwise RS still holds chol(S) from the gate

@@ -27,9 +27,10 @@ def test_ekf_update_no_gate(slo, B):
     assert_parity(slo, BLOCKS, f.mu(), symmetrize_lower(f.P()), mu_r, symmetrize_lower(P_r))
 
 
-@pytest.mark.parametrize("frac", [0.0, 0.04, 0.12])
-def test_ekf_update_gate_and_outliers(slo, frac):
-    B = 96
+# B = 333: more instances than SMs -- from its second instance on a CTA takes the covariance record that was fetched into
+# shared memory during the previous instance (also after instances that left early with a status)
+@pytest.mark.parametrize("frac,B", [(0.0, 96), (0.04, 96), (0.12, 96), (0.04, 333), (0.12, 333)])
+def test_ekf_update_gate_and_outliers(slo, frac, B):
     sc = synth.msckf_scenario(B, seed=77, k=10, nfeat=50, outlier_frac=frac)
     f, mu_r, P_r, out_r, st_r = _run(slo, sc, B, gate=True)
     np.testing.assert_array_equal(f.outliers(), out_r)              # integer outputs: exact
