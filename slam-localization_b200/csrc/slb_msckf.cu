@@ -28,6 +28,7 @@ constexpr int MS_T = 512;          // threads per CTA (16 warps: 126 registers, 
 constexpr int MS_W = MS_T / 32;
 constexpr int MS_NMAX = 72, MS_MMAX = 100, MS_NSMAX = 145;
 constexpr int MS_NSPAD = 148;                    // sigma-point count padded to the DMMA k-step
+static_assert(MS_NSMAX == 2 * MS_NMAX + 1 && MS_NSPAD >= MS_NSMAX && MS_NSPAD % 4 == 0, "sigma-point padding");
 constexpr int MS_A = 5056;                       // >= 100*101/2 and >= 72*73/2
 constexpr int MS_ZS = 100;                       // row stride of Z and of covXZ / Y   (= 4 mod 16)
 constexpr int MS_QS = 84;                        // row stride of the sigma points X / deviations D (= 4 mod 16)
