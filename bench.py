@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- filter-steps/sec of the batched sigma-point filter hot path on N B200s of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ukfom|usckf|msckf|fusion|ekf|safefusion|deadreckon]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ukfom|usckf|msckf|fusion|ekf|msckf_ekf|safefusion|deadreckon]
                   [--impl reference]
 
 A "step" is one pass of the hot path (predict + update) over one batch of synthetic inputs.  The
