@@ -5,10 +5,13 @@
                   [--impl reference]
 
 A "step" is one pass of the hot path (predict + update) over one batch of synthetic inputs.  The
-default workload is BASELINE.json configs[1]: batched UKFoM on the MTK pos/SO(3)/vel state, 65,536
-independent instances per GPU.  One process per GPU (torchrun for N > 1); instances shard by index
-with no collective on the step path ("weak" scaling: the per-GPU fleet is fixed); the only NCCL
-traffic is the end-of-run all-reduce of the ensemble statistics, reported separately.
+default workload is BASELINE.json configs[3] (the north_star's): the Monte-Carlo USCKF fleet, 4M
+instances over 8 GPUs = 524,288 per GPU (N = 48, m = 3), one fused predict+update launch per step.
+The other GPU configs -- configs[1] batched UKFoM (65,536), configs[2] batched MSCKF (16,384),
+configs[4] DataModel fusion (1M) -- are measured in the same run and nested under "also", each
+with its own value / roofline / e2e.  One process per GPU (torchrun for N > 1); instances shard by
+index with no collective on the step path ("weak" scaling: the per-GPU fleet is fixed); the only
+NCCL traffic is the end-of-run all-reduce of the ensemble statistics, reported separately.
 
 One JSON line is printed by rank 0; see the task contract for the keys.  `--impl reference` times
 the reference's CPU algorithm instead: the dependency-free oracle port (the reference itself needs
@@ -121,8 +124,6 @@ class UkfomWorkload:
     kernel = "slbd::ukf_kernel<MTK9, IMU, GPS, G=4, fused>"
     phases = ("ukf_kernel",)
     dominant = 0
-    traffic = 33.7e6 + 0.07e6       # ncu dram read+write per launch (profiles/r01_ncu_full_summary_final.txt); the 36 MB
-                                    # fleet fits L2, so the write-back of a lone profiled launch is not counted
 
     def __init__(self, rank, seed=1234):
         self.seed = seed + 1000 * rank
@@ -199,7 +200,6 @@ class FusionWorkload:
     kernel = "slbd::datamodel_kernel<6, fusion>"
     phases = ("datamodel_kernel",)
     dominant = 0
-    traffic = 704.8e6 + 322.3e6     # ncu dram read+write per launch (profiles/r01_ncu_full_summary_final.txt)
 
     def __init__(self, rank, seed=99):
         self.sc = synth.fusion_scenario(self.B, d=self.d, seed=seed + rank)
@@ -287,8 +287,6 @@ class UsckfWorkload:
 
     phases = ("predict12_kernel", "usckf_update_kernel")
     dominant = 1
-    traffic = (649.7e6 + 618.4e6) / 65536 * 524288  # ncu dram read+write of usckf_update_kernel (65 536-instance launch,
-                                                    # profiles/r01_ncu_full_summary_final.txt) scaled to this fleet
 
     def step_phase(self, k, p):
         e = self.engine
@@ -321,12 +319,14 @@ class UsckfWorkload:
         return self.f.ensemble_stats().t
 
     def cpu_step(self, slo, nsample, nthreads):
+        # instance i of the fleet starts from prior i % NPRIOR with its own u / z: walk the sample in blocks of priors
         sc = self.sc
-        n = min(nsample, self.NPRIOR)
         t0 = time.perf_counter()
-        slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, sc["mu"][:n], sc["P"][:n], self.u[:n], sc["dt"], sc["Q"],
-                       self.z[:n], sc["R"], nthreads=nthreads)
-        return (time.perf_counter() - t0) * nsample / n
+        for b0 in range(0, nsample, self.NPRIOR):
+            n = min(self.NPRIOR, nsample - b0)
+            slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, sc["mu"][:n], sc["P"][:n], self.u[b0:b0 + n], sc["dt"],
+                           sc["Q"], self.z[b0:b0 + n], sc["R"], nthreads=nthreads)
+        return time.perf_counter() - t0
 
 
 class MsckfWorkload:
@@ -381,7 +381,6 @@ class MsckfWorkload:
 
     phases = ("predict12_kernel", "msckf_update_kernel")
     dominant = 1
-    traffic = (92.7e6 + 36.7e6) / 4096 * 16384   # ncu dram read+write of msckf_update_kernel (4096-instance launch) scaled
 
     def step_phase(self, k, p):
         e = self.engine
@@ -416,12 +415,13 @@ class MsckfWorkload:
 
     def cpu_step(self, slo, nsample, nthreads):
         sc = self.sc
-        n = min(nsample, self.NPRIOR)
         t0 = time.perf_counter()
-        mu, P, _ = slo.msckf_predict(slo.PM_MSCKF_DELTAPOSE, self.K, sc["mu"][:n], sc["P"][:n], self.u[:n], 0.0, sc["Q"],
-                                     nthreads=nthreads)
-        slo.msckf_update(slo.MM_MSCKF_REPROJ, self.K, mu, P, sc["landmarks"], self.z[:n], sc["R"], nthreads=nthreads)
-        return (time.perf_counter() - t0) * nsample / n
+        for b0 in range(0, nsample, self.NPRIOR):
+            n = min(self.NPRIOR, nsample - b0)
+            mu, P, _ = slo.msckf_predict(slo.PM_MSCKF_DELTAPOSE, self.K, sc["mu"][:n], sc["P"][:n], self.u[b0:b0 + n], 0.0,
+                                         sc["Q"], nthreads=nthreads)
+            slo.msckf_update(slo.MM_MSCKF_REPROJ, self.K, mu, P, sc["landmarks"], self.z[b0:b0 + n], sc["R"], nthreads=nthreads)
+        return time.perf_counter() - t0
 
 
 WORKLOADS = {"ukfom": UkfomWorkload, "fusion": FusionWorkload, "usckf": UsckfWorkload, "msckf": MsckfWorkload}
@@ -434,33 +434,56 @@ for _cls in bench_workloads.WORKLOADS:
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_baseline(wl, steps=1, warmup=0, budget_s=12.0):
+BOUND = {"usckf": "fp64", "ukfom": "fp64", "msckf": "fp64", "msckf_ekf": "fp64", "fusion": "hbm", "ekf": "hbm",
+         "safefusion": "hbm", "deadreckon": "hbm"}   # the binding roofline per config
+ALSO = ("ukfom", "msckf", "fusion")                  # nested under "also" when the default workload runs
+
+
+def config_of(wl, world):
+    """The `config` object of the JSON line: identical in the b200 and the reference arm."""
+    return dict(wl.describe(), l2="every step's state is larger than L2 or a rotating set of fleets is (see l2_policy)",
+                parallelism="instance-index shard x%d, no step-path collective" % world)
+
+
+def measured_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's dominant kernel, from the committed
+    ncu --set full capture of the same workload shape (profiles/traffic.json names the capture); None if absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p)).get(name)
+        return (float(d["bytes_per_launch"]), d["source"]) if d else (None, None)
+    except Exception:
+        return None, None
+
+
+def cpu_baseline(wl, steps=3, warmup=1, budget_s=12.0):
     """Times the oracle (CPU restatement of the reference's algorithm) on all host threads over a
-    bounded sample of the same workload."""
+    bounded sample of the same workload, `steps` timed passes after `warmup`."""
     from oracle import slo
     slo.build()
     cores = slo.hardware_threads()
     n0 = min(wl.units_per_step(), 64 * cores)
     t = wl.cpu_step(slo, n0, cores)
     rate = n0 / t
-    nsample = int(min(wl.units_per_step(), max(n0, rate * budget_s / max(1, steps + warmup))))
+    steps = max(1, steps)
+    nsample = int(min(wl.units_per_step(), max(n0, rate * budget_s / (steps + warmup))))
     for _ in range(warmup):
         wl.cpu_step(slo, nsample, cores)
-    ts = [wl.cpu_step(slo, nsample, cores) for _ in range(max(1, steps))]
+    ts = [wl.cpu_step(slo, nsample, cores) for _ in range(steps)]
     tot = sum(ts)
     return {"value": nsample * len(ts) / tot, "unit": wl.unit, "cores": cores, "kind": "port",
-            "sample": "%d of %d units per step, %d step(s), oracle/libslo.so on %d threads" %
-                      (nsample, wl.units_per_step(), len(ts), cores)}, tot / len(ts) * 1e3
+            "sample": "%d of %d units per step, %d step(s) after %d warm-up, oracle/libslo.so on %d threads" %
+                      (nsample, wl.units_per_step(), len(ts), warmup, cores)}, tot / len(ts) * 1e3
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload](0)
-    cb, ms = cpu_baseline(wl, steps=args.steps, warmup=args.warmup, budget_s=60.0)
+    cb, ms = cpu_baseline(wl, steps=max(3, args.steps), warmup=max(1, args.warmup), budget_s=60.0)
     line = {"impl": "reference", "metric": wl.metric, "value": cb["value"], "unit": wl.unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": wl.describe(),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(wl, max(world, args.gpus)),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference's own Eigen/MTK code cannot be built in this image; timed arm is the oracle port"}
@@ -468,15 +491,161 @@ def run_reference(args, rank, world):
     return 0
 
 
+def measure(wl, args, ctx, sample_clocks):
+    """Runs one workload's device-resident arm, end-to-end arm and stats gather; returns the result dict (rank 0)
+    or None (other ranks).  ctx = (torch, dist, engine, rank, world, local)."""
+    torch, dist, engine, rank, world, local = ctx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def rank_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl.setup_gpu(engine, torch)
+    hbm_peak, peak_src = measured_peaks()
+
+    # ---- device-resident arm -----------------------------------------------------------------------
+    # the sampler starts before the warm-up so that nvidia-smi is already streaming (one line per 20 ms) when the timed
+    # region begins; only lines that arrive while the GPU is under this workload's load are summarised
+    sampler = ClockSampler(local)
+    if rank == 0 and sample_clocks:
+        sampler.start()
+    for k in range(args.warmup):
+        wl.step(k)
+    barrier()
+    n0 = engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_load0 = time.monotonic()
+    e0.record()
+    nph = len(wl.phases)
+    mids = []
+    if nph == 1:
+        for k in range(args.steps):
+            wl.step(args.warmup + k)
+    else:  # an event after every launch but the last of a step: the dominant kernel's own duration
+        for k in range(args.steps):
+            row = []
+            for p in range(nph):
+                wl.step_phase(args.warmup + k, p)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                row.append(ev)
+            mids.append(row)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if nph == 1:
+        dom_ms = ms / args.steps
+    else:
+        tot = 0.0
+        for k, row in enumerate(mids):
+            start = (mids[k - 1][-1] if k else e0) if wl.dominant == 0 else row[wl.dominant - 1]
+            tot += start.elapsed_time(row[wl.dominant])
+        dom_ms = tot / args.steps
+    launches = engine.launch_count() - n0
+    t_load1 = time.monotonic()
+    clocks = None
+    if rank == 0 and sample_clocks:
+        # a timed region shorter than a few sampling periods is followed by untimed steps of the same workload until at
+        # least 5 samples were taken under load; they are not part of any reported time
+        extended = False
+        t_end = time.monotonic() + 1.0
+        kx = args.warmup + args.steps
+        while sampler.proc and sampler.count(t_load0, t_load1) < 5 and time.monotonic() < t_end:
+            for _ in range(8):
+                wl.step(kx)
+                kx += 1
+            torch.cuda.synchronize()
+            t_load1 = time.monotonic()
+            extended = True
+        clocks = sampler.stop(t_load0, t_load1)
+        clocks["sampled_over"] = "timed region + untimed steps of the same workload" if extended else "timed region"
+    ms_max = rank_max(ms)
+    units = wl.units_per_step() * args.steps * world
+    value = units / (ms_max * 1e-3)
+    ok = wl.status_ok()
+
+    # ---- end-to-end arm: host buffers in, host result out, every step -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ke = max(3, min(args.steps, 50))
+        for k in range(3):
+            wl.step_e2e(k)
+        if hasattr(wl, "e2e_drain"):
+            wl.e2e_drain()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(ke):
+            wl.step_e2e(k)
+        if hasattr(wl, "e2e_drain"):
+            wl.e2e_drain()          # pipelined host API: wait for the steps still in flight (inside the timed region)
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e = rank_max(max(e0.elapsed_time(e1), wall))
+        h2d, d2h = wl.e2e_bytes()
+        e2e = {"value": wl.units_per_step() * ke * world / (ms_e * 1e-3), "unit": wl.unit,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
+               "pcie_gbs_per_rank": (h2d + d2h) * ke / (ms_e * 1e-3) / 1e9,
+               "api": getattr(wl, "e2e_api", None)}
+
+    # ---- end-of-run ensemble statistics (the only collective; not on the step path) -----------------
+    gather_ms = None
+    if wl.stats_tensor() is not None:
+        barrier()
+        e0.record()
+        wl.gather_stats() if hasattr(wl, "gather_stats") else fleet.merge_stats(wl.stats_tensor())
+        e1.record()
+        barrier()
+        gather_ms = e0.elapsed_time(e1)
+
+    if rank != 0:
+        return None
+    ms_per_step = ms_max / args.steps
+    launch_ms = dom_ms                # average duration of the dominant kernel's launches (CUDA events, rank 0)
+    hbm_ach = wl.bytes_per_unit * wl.units_per_step() / (launch_ms * 1e-3) / 1e9
+    fp64_peak = engine.fp64_peak_tflops()
+    fp64_ach = wl.flops_per_unit * wl.units_per_step() / (ms_per_step * 1e-3) / 1e12
+    traffic, traffic_src = measured_traffic(wl.name)
+    common = {"traffic": traffic, "traffic_source": traffic_src, "kernel": wl.kernel, "kernel_ms": launch_ms,
+              "launches_per_step": list(wl.phases)}
+    r_hbm = dict({"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                  "peak_source": peak_src, "algorithmic_bytes_per_unit": wl.bytes_per_unit}, **common)
+    r_f64 = dict({"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                  "frac": fp64_ach / fp64_peak if fp64_peak else None,
+                  "peak_source": "measured in this run (slb_bench_fp64_peak, register-resident DFMA; DMMA peak is the same)",
+                  "algorithmic_flops_per_unit": wl.flops_per_unit, "over": "whole step (all launches)"}, **common)
+    binding = BOUND.get(wl.name, "hbm")
+    return {
+        "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(wl, world),
+        "l2_policy": wl.l2_policy,
+        "roofline": r_f64 if binding == "fp64" else r_hbm,       # the binding roofline (BASELINE.md section 3)
+        "roofline_other": r_hbm if binding == "fp64" else r_f64,  # the non-binding one, for information
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "status_clean": ok,
+        "ensemble_stats_allreduce_ms": gather_ms,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="ukfom", choices=sorted(WORKLOADS))
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="usckf", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the nested runs of the other BASELINE configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -497,142 +666,39 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from slam_localization_b200 import engine
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    ctx = (torch, dist, engine, rank, world, local)
 
     wl = WORKLOADS[args.workload](rank)
-    wl.setup_gpu(engine, torch)
-    hbm_peak, peak_src = measured_peaks()
+    line = measure(wl, args, ctx, sample_clocks=True)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"], _ = cpu_baseline(wl)
+    del wl
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
-    # ---- device-resident arm -----------------------------------------------------------------------
-    # the sampler starts before the warm-up so that nvidia-smi is already streaming (one line per 20 ms) when the timed
-    # region begins; only lines that arrive while the GPU is under this workload's load are summarised
-    sampler = ClockSampler(local)
+    # the other BASELINE configs, nested: one driver run covers configs[1..4]
+    if args.workload == "usckf" and not args.no_also:
+        also = {}
+        for name in ALSO:
+            w2 = WORKLOADS[name](rank)
+            a2 = argparse.Namespace(**vars(args))
+            if name == "ukfom":      # a 0.14 ms step: more steps so that the timed region is not dominated by jitter
+                a2.steps = max(args.steps, 200)
+            r = measure(w2, a2, ctx, sample_clocks=False)
+            if rank == 0:
+                keep = {k: r[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "config", "l2_policy", "roofline",
+                                          "roofline_other", "e2e", "gpu_launches", "status_clean",
+                                          "ensemble_stats_allreduce_ms")}
+                if world == 1 and not args.no_cpu_baseline:
+                    keep["cpu_baseline"], _ = cpu_baseline(w2, budget_s=5.0)
+                also[name] = keep
+            del w2
+            gc.collect()
+            torch.cuda.empty_cache()
+        if rank == 0:
+            line["also"] = also
     if rank == 0:
-        sampler.start()
-    for k in range(args.warmup):
-        wl.step(k)
-    barrier()
-    n0 = engine.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_load0 = time.monotonic()
-    e0.record()
-    nph = len(wl.phases)
-    mids = []
-    if nph == 1:
-        for k in range(args.steps):
-            wl.step(args.warmup + k)
-    else:  # an event after every launch but the last of a step: the dominant kernel's own duration
-        for k in range(args.steps):
-            row = []
-            for p in range(nph):
-                wl.step_phase(args.warmup + k, p)
-                if p < nph - 1:
-                    ev = torch.cuda.Event(enable_timing=True)
-                    ev.record()
-                    row.append(ev)
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            row.append(ev)
-            mids.append(row)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if nph == 1:
-        dom_ms = ms / args.steps
-    else:
-        tot = 0.0
-        for k, row in enumerate(mids):
-            start = (mids[k - 1][-1] if k else e0) if wl.dominant == 0 else row[wl.dominant - 1]
-            tot += start.elapsed_time(row[wl.dominant])
-        dom_ms = tot / args.steps
-    launches = engine.launch_count() - n0
-    t_load1 = time.monotonic()
-    clocks = None
-    if rank == 0:
-        # a timed region shorter than a few sampling periods (ukfom: 200 steps = 28 ms) is followed by untimed steps of
-        # the same workload until at least 5 samples were taken under load; they are not part of any reported time
-        extended = False
-        t_end = time.monotonic() + 1.0
-        kx = args.warmup + args.steps
-        while sampler.proc and sampler.count(t_load0, t_load1) < 5 and time.monotonic() < t_end:
-            for _ in range(8):
-                wl.step(kx)
-                kx += 1
-            torch.cuda.synchronize()
-            t_load1 = time.monotonic()
-            extended = True
-        clocks = sampler.stop(t_load0, t_load1)
-        clocks["sampled_over"] = "timed region + untimed steps of the same workload" if extended else "timed region"
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    units = wl.units_per_step() * args.steps * world
-    value = units / (ms_max * 1e-3)
-    ok = wl.status_ok()
-
-    # ---- end-to-end arm: host buffers in, host result out, every step -------------------------------
-    e2e = None
-    if not args.no_e2e:
-        ke = max(3, min(args.steps, 50))
-        for k in range(3):
-            wl.step_e2e(k)
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for k in range(ke):
-            wl.step_e2e(k)
-        e1.record()
-        barrier()
-        wall = (time.perf_counter() - t0) * 1e3
-        ms_e = max(e0.elapsed_time(e1), wall)
-        t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        h2d, d2h = wl.e2e_bytes()
-        e2e = {"value": wl.units_per_step() * ke * world / (float(t.item()) * 1e-3), "unit": wl.unit,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke}
-
-    # ---- end-of-run ensemble statistics (the only collective; not on the step path) -----------------
-    gather_ms = None
-    st = wl.stats_tensor()
-    if st is not None:
-        barrier()
-        e0.record()
-        st = fleet.merge_stats(wl.stats_tensor())   # NCCL all-reduce (SUM) of 1 + N + N*N doubles; no-op at N = 1
-        e1.record()
-        barrier()
-        gather_ms = e0.elapsed_time(e1)
-
-    if rank == 0:
-        ms_per_step = ms_max / args.steps
-        launch_ms = dom_ms                # average duration of the dominant kernel's launches (CUDA events, rank 0)
-        achieved = wl.bytes_per_unit * wl.units_per_step() / (launch_ms * 1e-3) / 1e9
-        fp64_peak = engine.fp64_peak_tflops()
-        fp64_ach = wl.flops_per_unit * wl.units_per_step() / (ms_per_step * 1e-3) / 1e12
-        line = {
-            "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(wl.describe(), l2=wl.l2_policy, parallelism="instance-index shard x%d, no step-path collective" % world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": wl.traffic, "peak_source": peak_src,
-                         "kernel": wl.kernel, "kernel_ms": launch_ms, "algorithmic_bytes_per_unit": wl.bytes_per_unit,
-                         "launches_per_step": list(wl.phases)},
-            "roofline_fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                              "frac": fp64_ach / fp64_peak if fp64_peak else None,
-                              "algorithmic_flops_per_unit": wl.flops_per_unit,
-                              "peak_source": "measured in this run (slb_bench_fp64_peak, DFMA)"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "status_clean": ok,
-            "ensemble_stats_allreduce_ms": gather_ms,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _ = cpu_baseline(wl)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

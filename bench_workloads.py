@@ -22,7 +22,6 @@ class EkfWorkload:
     kernel = "slbd::ekf_update_kernel<3> (+ ekf_predict_kernel)"
     phases = ("ekf_predict_kernel", "ekf_update_kernel")
     dominant = 1
-    traffic = (860.4e6 + 1005.5e6) / 65536 * 262144  # ncu dram read+write of ekf_update_kernel (65 536-instance launch) scaled
 
     def __init__(self, rank, seed=2024):
         self.sc = synth.ekf_scenario(self.NPRIOR, seed=seed + 1000 * rank)
@@ -112,7 +111,6 @@ class SafeFusionWorkload:
     kernel = "slbd::safe_fusion_kernel"
     phases = ("safe_fusion_kernel",)
     dominant = 0
-    traffic = (201.4e6 + 70.3e6) * 4                 # ncu dram read+write of a 1M-pair launch, scaled to 4M
 
     def __init__(self, rank, seed=5):
         self.sc = synth.safe_fusion_scenario(self.B, seed=seed + rank, log_spread=1.5)
@@ -174,7 +172,6 @@ class DeadReckonWorkload:
     kernel = "slbd::dr_update_pose_kernel"
     phases = ("dr_update_pose_kernel",)
     dominant = 0
-    traffic = 467.3e6 + 831.4e6                      # ncu dram read+write per 1M-pose launch
 
     def __init__(self, rank, seed=11):
         self.sc = synth.deadreckon_scenario(self.B, seed=seed + rank)
@@ -252,7 +249,6 @@ class MsckfEkfWorkload:
     kernel = "slbd::msckf_ekf_update_kernel (+ predict12_kernel)"
     phases = ("predict12_kernel", "msckf_ekf_update_kernel")
     dominant = 1
-    traffic = (46.4e6 + 1.06e6) / 2048 * 16384       # ncu dram read+write (2048-instance launch: the write-back stays in L2)
 
     def __init__(self, rank, seed=777):
         self.sc = synth.msckf_scenario(self.NPRIOR, seed=seed + 1000 * rank, k=self.K, nfeat=self.NFEAT)
