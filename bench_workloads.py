@@ -301,8 +301,8 @@ class MsckfEkfWorkload:
         return 2
 
     def status_ok(self):
-        c = self.f.status_counts()
-        return c[0] == 0 and c[1] == 0 and c[3] == 0
+        c = self.f.status_counts()   # gate rejections (bit 2) are expected; too few rows after the gate (QR_ROWS) is not
+        return c[0] == 0 and c[1] == 0 and c[3] == 0 and c[4] == 0
 
     def stats_tensor(self):
         return self.f.ensemble_stats().t

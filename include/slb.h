@@ -51,6 +51,7 @@ enum {
     SLB_ST_QR_ROWS = 16     /* Msckf EKF update: fewer measurement rows than DOF left after the
                                outlier removal [R.block(0,0,N,N) out of range, Msckf.hpp:808]  */
 };
+#define SLB_NSTATUS 5       /* number of status bits above */
 
 /* Filter kinds (which reference class the batch stands for). */
 enum {
@@ -261,6 +262,8 @@ int slb_dev_copy(void *dst, const void *src, size_t bytes, int kind, void *strea
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* counts[0..3] = instances with CHOL_FAIL / MEAN_NOCONV / GATE_REJECT / NONFINITE set. */
 int slb_status(slb_handle h, int64_t counts[4], void *stream);
+/* The same for the first nbits <= SLB_NSTATUS status bits (counts[4] = QR_ROWS). */
+int slb_status_ex(slb_handle h, int64_t *counts, int nbits, void *stream);
 int slb_clear_status(slb_handle h, void *stream);
 /* Ensemble statistics of the instance means over this device's shard (new; no reference
  * counterpart): out = { count, sum x[nv], sum x x^T[nv*nv] } with x = the vect<3> blocks and

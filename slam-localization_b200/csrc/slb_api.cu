@@ -100,14 +100,16 @@ __global__ void replicate_rec(double *a, int per, int B, int count) {
 }
 
 __global__ void status_count(const int32_t *st, int B, unsigned long long *counts) {
-    unsigned long long c[4] = {0, 0, 0, 0};
+    unsigned long long c[SLB_NSTATUS];
+#pragma unroll
+    for (int b = 0; b < SLB_NSTATUS; ++b) c[b] = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
         const int s = st[i];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) c[b] += (s >> b) & 1;
+        for (int b = 0; b < SLB_NSTATUS; ++b) c[b] += (s >> b) & 1;
     }
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < SLB_NSTATUS; ++b) {
         for (int o = 16; o > 0; o >>= 1) c[b] += __shfl_down_sync(0xffffffffu, c[b], o);
         if ((threadIdx.x & 31) == 0 && c[b]) atomicAdd(counts + b, c[b]);
     }
@@ -228,7 +230,11 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
     }
     if (cfg->device < 0 || cfg->device >= ndev) return set_error(SLB_ERR_INVALID, "slb_create: bad device ordinal");
     if (cfg->batch <= 0) return set_error(SLB_ERR_INVALID, "slb_create: batch must be positive");
-    SLB_CUDA(cudaSetDevice(cfg->device));
+    DeviceGuard guard(cfg->device);  // no lasting side effect on the caller's current device
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != cfg->device) return set_error(SLB_ERR_CUDA, "slb_create: cudaSetDevice failed");
+    }
     slb_batch_s *h = new (std::nothrow) slb_batch_s();
     if (!h) return set_error(SLB_ERR_ALLOC, "slb_create: host allocation failed");
     memset(h, 0, sizeof(*h));
@@ -283,7 +289,7 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->outliers, (size_t)h->B * 4);
     if (e == cudaSuccess) e = cudaMalloc(&h->stage, h->stage_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->shared_small, 128 * 1024);
-    if (e == cudaSuccess) e = cudaMalloc(&h->counts_dev, 4 * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&h->counts_dev, 8 * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMalloc(&h->misc_dev, 16 * sizeof(int32_t));
     for (int i = 0; i < SLB_NXS && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&h->xs[i], cudaStreamNonBlocking);
@@ -305,6 +311,7 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
 
 int slb_destroy(slb_handle h) {
     if (!h) return SLB_OK;
+    DeviceGuard guard(h->cfg.device);
     cudaFree(h->mu); cudaFree(h->P); cudaFree(h->status); cudaFree(h->outliers);
     cudaFree(h->stage); cudaFree(h->shared_small); cudaFree(h->counts_dev); cudaFree(h->misc_dev);
     for (int i = 0; i < SLB_NXS; ++i) {
@@ -334,6 +341,7 @@ int slb_device_ptr(slb_handle h, int field, void **dev) {
 
 static int transfer(slb_handle h, int field, void *host, size_t count, cudaStream_t s, bool up) {
     if (!h || !host) return set_error(SLB_ERR_INVALID, "slb_upload/download: null argument");
+    DeviceGuard guard(h->cfg.device);
     const bool soa = h->cfg.kind == SLB_KIND_UKF;
     if (field == SLB_FIELD_STATUS || field == SLB_FIELD_OUTLIERS) {
         if (up) return set_error(SLB_ERR_INVALID, "slb_upload: status fields are read-only");
@@ -396,6 +404,7 @@ int slb_download(slb_handle h, int field, void *host, size_t count, void *stream
 
 int slb_replicate(slb_handle h, int count, void *stream) {
     if (!h || count <= 0 || count > h->B) return set_error(SLB_ERR_INVALID, "slb_replicate: bad count");
+    DeviceGuard guard(h->cfg.device);
     cudaStream_t s = S(stream);
     if (count == h->B) return SLB_OK;
     const int tpb = 256;
@@ -421,6 +430,7 @@ static int ukf_call(slb_handle h, int pm, int mm, bool pred, bool upd, const dou
     if (!h || h->cfg.kind != SLB_KIND_UKF) return set_error(SLB_ERR_INVALID, "slb_ukf_*: handle is not a UKF batch");
     if (pred && (!u || !Q)) return set_error(SLB_ERR_INVALID, "slb_ukf_predict: u and Q are required");
     if (upd && (!z || !R)) return set_error(SLB_ERR_INVALID, "slb_ukf_update: z and R are required");
+    DeviceGuard guard(h->cfg.device);
     FilterArgs a = make_args(h);
     a.u = u; a.dt = dt; a.Q = Q; a.z = z; a.R = R; a.gate = gate; a.m = 3;
     return launch_ukf(h->cfg.layout, pm, mm, pred, upd, a, S(stream));
@@ -524,9 +534,25 @@ static bool is_pinned(const void *p) {
     }
     return at.type == cudaMemoryTypeHost;
 }
+// Device-side alias of a page-locked host buffer for the zero-copy paths.  For cudaHostRegister'ed memory on systems
+// without canUseHostPointerForRegisteredMem the alias differs from the host address; nullptr = no usable alias (the
+// caller falls back to the copy pipeline).
+static void *dev_alias_v(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return const_cast<void *>(p);
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+static const double *dev_alias(const double *p) { return (const double *)dev_alias_v(p); }
+static double *dev_alias_m(double *p) { return (double *)dev_alias_v(p); }
 
 static int step_host(slb_handle h, const HostStep &hs, void *stream) {
     if (!h || !hs.u || !hs.Q || !hs.z || !hs.R) return set_error(SLB_ERR_INVALID, "slb_*_step_host: null argument");
+    DeviceGuard guard(h->cfg.device);
     cudaStream_t s = S(stream);
     const size_t ub = (size_t)h->B * hs.nu * 8, zb = (size_t)h->B * hs.m * 8, mub = (size_t)h->B * h->QD * 8;
     const size_t small = (size_t)(hs.nq * hs.nq + hs.m * hs.m + hs.nparams) * 8;
@@ -545,13 +571,15 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream) {
     // from the mapped (page-locked, UVA) host buffers and writes the posterior means straight back: transfers overlap
     // compute warp by warp.  Only the small shared Q / R are copied.  (SLB_ZERO_COPY=0 selects the copy pipeline.)
     static const bool zero_copy = [] { const char *e = getenv("SLB_ZERO_COPY"); return !e || atoi(e) != 0; }();
-    if (zero_copy && (h->cfg.kind == SLB_KIND_UKF || h->cfg.kind == SLB_KIND_USCKF)) {
+    const double *zu = dev_alias(hs.u), *zz = dev_alias(hs.z);
+    double *zmu = dev_alias_m(hs.mu_out);
+    if (zero_copy && zu && zz && (zmu || !hs.mu_out) && (h->cfg.kind == SLB_KIND_UKF || h->cfg.kind == SLB_KIND_USCKF)) {
         double *dQ = h->shared_small, *dR = dQ + hs.nq * hs.nq;
         SLB_CUDA(cudaMemcpyAsync(dQ, hs.Q, (size_t)hs.nq * hs.nq * 8, cudaMemcpyHostToDevice, s));
         SLB_CUDA(cudaMemcpyAsync(dR, hs.R, (size_t)hs.m * hs.m * 8, cudaMemcpyHostToDevice, s));
         FilterArgs a = make_args(h);
-        a.u = hs.u; a.dt = hs.dt; a.Q = dQ; a.z = hs.z; a.R = dR; a.gate = hs.gate; a.m = hs.m;
-        a.mu_out = hs.mu_out;
+        a.u = zu; a.dt = hs.dt; a.Q = dQ; a.z = zz; a.R = dR; a.gate = hs.gate; a.m = hs.m;
+        a.mu_out = zmu;
         const int rc = h->cfg.kind == SLB_KIND_UKF ? launch_ukf(h->cfg.layout, hs.pm, hs.mm, true, true, a, s)
                                                    : launch_usckf(hs.pm, hs.mm, true, true, a, s);
         if (rc != SLB_OK) return rc;
@@ -607,6 +635,7 @@ static int usckf_call(slb_handle h, int pm, int mm, bool pred, bool upd, const d
     if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_*: handle is not a USCKF batch");
     if (pred && (!u || !Q)) return set_error(SLB_ERR_INVALID, "slb_usckf_predict: u and Q are required");
     if (upd && (!z || !R)) return set_error(SLB_ERR_INVALID, "slb_usckf_update: z and R are required");
+    DeviceGuard guard(h->cfg.device);
     FilterArgs a = make_args(h);
     a.u = u; a.dt = dt; a.Q = Q; a.z = z; a.R = R; a.gate = gate; a.m = h->cfg.nk;
     return launch_usckf(pm, mm, pred, upd, a, S(stream));
@@ -629,12 +658,14 @@ int slb_usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, doub
 }
 int slb_usckf_clone(slb_handle h, int mode, void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_clone: handle is not a USCKF batch");
+    DeviceGuard guard(h->cfg.device);
     FilterArgs a = make_args(h);
     return launch_usckf_clone(mode, a, S(stream));
 }
 int slb_usckf_set_measurement(slb_handle h, int mode, const double *z, const double *R, void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_set_measurement: handle is not a USCKF batch");
     if (!z || !R) return set_error(SLB_ERR_INVALID, "slb_usckf_set_measurement: z and R are required");
+    DeviceGuard guard(h->cfg.device);
     FilterArgs a = make_args(h);
     a.z = z; a.R = R;
     return launch_usckf_set_measurement(mode, a, S(stream));
@@ -644,6 +675,7 @@ int slb_usckf_set_measurement(slb_handle h, int mode, const double *z, const dou
 int slb_msckf_predict(slb_handle h, int pm, const double *u, double dt, const double *Q, void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_predict: handle is not an MSCKF batch");
     if (!u || !Q) return set_error(SLB_ERR_INVALID, "slb_msckf_predict: u and Q are required");
+    DeviceGuard guard(h->cfg.device);
     FilterArgs a = make_args(h);
     a.u = u; a.dt = dt; a.Q = Q;
     return launch_msckf_predict(pm, a, S(stream));
@@ -652,6 +684,7 @@ int slb_msckf_update(slb_handle h, int mm, const double *params, int m, const do
                      void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_update: handle is not an MSCKF batch");
     if (!params || !z || !R || m <= 0 || (m & 1)) return set_error(SLB_ERR_INVALID, "slb_msckf_update: bad arguments");
+    DeviceGuard guard(h->cfg.device);
     FilterArgs a = make_args(h);
     a.params = params; a.m = m; a.z = z; a.R = R; a.gate = gate;
     return launch_msckf_update(mm, a, S(stream));
@@ -661,6 +694,7 @@ int slb_msckf_update_ekf(slb_handle h, int mm, const double *params, int m, cons
                          void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_update_ekf: handle is not an MSCKF batch");
     if (!params || !z || !R || m <= 0 || (m & 1)) return set_error(SLB_ERR_INVALID, "slb_msckf_update_ekf: bad arguments");
+    DeviceGuard guard(h->cfg.device);
     FilterArgs a = make_args(h);
     a.params = params; a.m = m; a.z = z; a.R = R; a.gate = gate;
     return launch_msckf_update_ekf(mm, a, S(stream));
@@ -704,8 +738,11 @@ int slb_datamodel_fuse_host(int d, int64_t n, const double *x1, const double *C1
     // traffic of a 1M-pair step overlaps in both directions and with the arithmetic, and nothing is allocated.
     {
         static const bool zero_copy = [] { const char *e = getenv("SLB_ZERO_COPY"); return !e || atoi(e) != 0; }();
-        if (zero_copy && is_pinned(x1) && is_pinned(C1) && is_pinned(x2) && is_pinned(C2) && is_pinned(xo) && is_pinned(Co)) {
-            const int rc = launch_fusion(d, n, 0, x1, C1, x2, C2, xo, Co, 0);
+        const double *a1 = dev_alias(x1), *A1 = dev_alias(C1), *a2 = dev_alias(x2), *A2 = dev_alias(C2);
+        double *ao = dev_alias_m(xo), *Ao = dev_alias_m(Co);
+        if (zero_copy && is_pinned(x1) && is_pinned(C1) && is_pinned(x2) && is_pinned(C2) && is_pinned(xo) && is_pinned(Co) &&
+            a1 && A1 && a2 && A2 && ao && Ao) {
+            const int rc = launch_fusion(d, n, 0, a1, A1, a2, A2, ao, Ao, 0);
             if (rc != SLB_OK) return rc;
             SLB_CUDA(cudaStreamSynchronize(0));
             return SLB_OK;
@@ -753,21 +790,24 @@ int slb_dev_copy(void *dst, const void *src, size_t bytes, int kind, void *strea
 }
 
 // ---- diagnostics -------------------------------------------------------------------------------------
-int slb_status(slb_handle h, int64_t counts[4], void *stream) {
-    if (!h || !counts) return set_error(SLB_ERR_INVALID, "slb_status: null argument");
+int slb_status_ex(slb_handle h, int64_t *counts, int nbits, void *stream) {
+    if (!h || !counts || nbits < 1 || nbits > SLB_NSTATUS) return set_error(SLB_ERR_INVALID, "slb_status: bad argument");
+    DeviceGuard guard(h->cfg.device);
     cudaStream_t s = S(stream);
-    SLB_CUDA(cudaMemsetAsync(h->counts_dev, 0, 4 * sizeof(int64_t), s));
+    SLB_CUDA(cudaMemsetAsync(h->counts_dev, 0, 8 * sizeof(int64_t), s));
     int grid = (h->B + 255) / 256;
     if (grid > 1184) grid = 1184;
     status_count<<<grid, 256, 0, s>>>(h->status, h->B, (unsigned long long *)h->counts_dev);
     count_launch();
     SLB_CUDA(cudaGetLastError());
-    SLB_CUDA(cudaMemcpyAsync(counts, h->counts_dev, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SLB_CUDA(cudaMemcpyAsync(counts, h->counts_dev, (size_t)nbits * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     SLB_CUDA(cudaStreamSynchronize(s));
     return SLB_OK;
 }
+int slb_status(slb_handle h, int64_t counts[4], void *stream) { return slb_status_ex(h, counts, 4, stream); }
 int slb_clear_status(slb_handle h, void *stream) {
     if (!h) return set_error(SLB_ERR_INVALID, "slb_clear_status: null argument");
+    DeviceGuard guard(h->cfg.device);
     SLB_CUDA(cudaMemsetAsync(h->status, 0, (size_t)h->B * 4, S(stream)));
     SLB_CUDA(cudaMemsetAsync(h->outliers, 0, (size_t)h->B * 4, S(stream)));
     return SLB_OK;
@@ -811,6 +851,7 @@ int slb_bench_fp64_peak(double *tflops_out) {
 
 int slb_ensemble_stats(slb_handle h, double *out_dev, void *stream) {
     if (!h || !out_dev) return set_error(SLB_ERR_INVALID, "slb_ensemble_stats: null argument");
+    DeviceGuard guard(h->cfg.device);
     cudaStream_t s = S(stream);
     StatLayout l;
     memset(&l, 0, sizeof(l));

@@ -166,8 +166,8 @@ struct FuseCfg {
 
 // OP: 0 fusion, +1 operator+, -1 operator-
 template <int D, int OP>
-__global__ void __launch_bounds__(FUSE_WARPS * 32) datamodel_kernel(int64_t n, const double *__restrict__ x1,
-                                                                  const double *__restrict__ C1,
+__global__ void __launch_bounds__(FUSE_WARPS * 32) datamodel_kernel(int64_t n, const double *x1,  // xo / Co may alias x1 / C1 (in-place fusion): no restrict
+                                                                  const double *C1,
                                                                   const double *__restrict__ x2,
                                                                   const double *__restrict__ C2, double *xo,
                                                                   double *Co) {

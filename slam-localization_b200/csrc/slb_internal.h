@@ -49,6 +49,21 @@ void count_launch(int n = 1);
         if (e_ != cudaSuccess) return slb::set_error(SLB_ERR_CUDA, #call, e_); \
     } while (0)
 
+// Every entry point that takes a handle runs on the handle's device and leaves the caller's current device as it
+// found it (several handles on several devices may be driven from one thread).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 struct FilterArgs {
     double *mu;
     double *P;

@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "slb_predict12.cuh"
+#include "slb_usckf_step.cuh"
 
 namespace slbd {
 
@@ -456,16 +457,45 @@ static int launch_update_t(const FilterArgs &a, cudaStream_t s) {
     return minb == 4 ? launch_update_m<NK, NL, 4>(a, s) : launch_update_m<NK, NL, 3>(a, s);
 }
 
+// record-resident kernel (slb_usckf_step.cuh): PRED && UPD = the fused step, UPD alone = update
+template <int NK, int NL, bool PRED, bool UPD>
+static int launch_step_t(const FilterArgs &a, cudaStream_t s) {
+    typedef slbd::StepCfg<NK, NL> C;
+    constexpr int WPB = 4;
+    constexpr size_t smem = (size_t)WPB * C::SM * sizeof(double);
+    constexpr int fit = (int)((228 * 1024) / (smem + 1024));
+    constexpr int MINB = fit > 3 ? 3 : fit < 1 ? 1 : fit;
+    static_assert(smem <= 227 * 1024, "record + scratch of one CTA must fit in shared memory");
+    auto kern = slbd::usckf_step_kernel<SLB_PM_USCKF_TEST, NK, NL, PRED, UPD, WPB, MINB>;
+    SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(a.B + WPB - 1) / WPB, WPB * 32, smem, s>>>(a);
+    count_launch();
+    SLB_CUDA(cudaGetLastError());
+    return SLB_OK;
+}
+
+template <int NK, int NL>
+static int launch_step_nknl(bool predict, const FilterArgs &a, cudaStream_t s) {
+    return predict ? launch_step_t<NK, NL, true, true>(a, s) : launch_step_t<NK, NL, false, true>(a, s);
+}
+
 int launch_usckf(int pm, int mm, bool predict, bool update, const FilterArgs &a, cudaStream_t s) {
-    if (predict) {
-        if (pm != SLB_PM_USCKF_TEST) return set_error(SLB_ERR_INVALID, "usckf: unsupported process model");
+    if (predict && pm != SLB_PM_USCKF_TEST) return set_error(SLB_ERR_INVALID, "usckf: unsupported process model");
+    if (update && mm != SLB_MM_USCKF_VO) return set_error(SLB_ERR_INVALID, "usckf: unsupported measurement model");
+    // experiment knob: SLB_USCKF_LEGACY=1 selects the round-1 two-launch path (predict12_kernel + usckf_update_kernel)
+    static const bool legacy = [] { const char *e = getenv("SLB_USCKF_LEGACY"); return e && atoi(e) != 0; }();
+    if (predict && (!update || legacy)) {
         int rc = launch_predict_t<SLB_PM_USCKF_TEST>(a, s);
         if (rc != SLB_OK) return rc;
     }
-    if (update) {
-        if (mm != SLB_MM_USCKF_VO) return set_error(SLB_ERR_INVALID, "usckf: unsupported measurement model");
+    if (update && legacy) {
         if (a.nk == 3 && a.nl == 9) return launch_update_t<3, 9>(a, s);
         if (a.nk == 3 && a.nl == 0) return launch_update_t<3, 0>(a, s);
+        return set_error(SLB_ERR_INVALID, "usckf update (legacy): built for (nk,nl) = (3,9) and (3,0)");
+    }
+    if (update) {
+        if (a.nk == 3 && a.nl == 9) return launch_step_nknl<3, 9>(predict, a, s);
+        if (a.nk == 3 && a.nl == 0) return launch_step_nknl<3, 0>(predict, a, s);
         return set_error(SLB_ERR_INVALID, "usckf update: built for (nk,nl) = (3,9) and (3,0)");
     }
     return SLB_OK;

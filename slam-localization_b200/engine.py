@@ -20,13 +20,14 @@ MM_GPS_POS, MM_USCKF_VO, MM_MSCKF_REPROJ = 101, 102, 103
 STATEK, STATEK_L, STATEK_I = 1, 2, 3
 FIELD_MU, FIELD_P, FIELD_STATUS, FIELD_OUTLIERS = 1, 2, 3, 4
 ST_CHOL_FAIL, ST_MEAN_NOCONV, ST_GATE_REJECT, ST_NONFINITE, ST_QR_ROWS = 1, 2, 4, 8, 16
+NSTATUS = 5
 
 EXPORTS = [
     "slb_version", "slb_last_error", "slb_create", "slb_destroy", "slb_dof", "slb_qdim", "slb_upload",
     "slb_download", "slb_device_ptr", "slb_ukf_predict", "slb_ukf_update", "slb_ukf_step", "slb_ukf_step_host",
     "slb_usckf_predict", "slb_usckf_update", "slb_usckf_step", "slb_usckf_step_host", "slb_usckf_clone",
     "slb_usckf_set_measurement", "slb_msckf_predict", "slb_msckf_update", "slb_datamodel_fuse",
-    "slb_datamodel_addsub", "slb_datamodel_fuse_host", "slb_status", "slb_clear_status", "slb_ensemble_stats",
+    "slb_datamodel_addsub", "slb_datamodel_fuse_host", "slb_status", "slb_status_ex", "slb_clear_status", "slb_ensemble_stats",
     "slb_launch_count", "slb_bench_fp64_peak", "slb_replicate", "slb_dev_alloc", "slb_dev_free", "slb_dev_copy",
     "slb_msckf_step_host", "slb_ekf_predict", "slb_ekf_update", "slb_ekf_single_update", "slb_ekf_clone",
     "slb_datamodel_safe_fuse", "slb_msckf_update_ekf", "slb_transform_compose", "slb_deadreckon_update_pose",
@@ -88,6 +89,7 @@ def lib():
         L.slb_transform_compose.argtypes = [i64, dp, dp, dp, dp, dp, dp, vp]
         L.slb_deadreckon_update_pose.argtypes = [i64, dbl, dp, dp, dp, dp, dp, dp, dp, dp, dp, vp]
         L.slb_status.argtypes = [vp, C.POINTER(C.c_int64), vp]
+        L.slb_status_ex.argtypes = [vp, C.POINTER(C.c_int64), i32, vp]
         L.slb_clear_status.argtypes = [vp, vp]
         L.slb_ensemble_stats.argtypes = [vp, dp, vp]
         _lib = L
@@ -225,8 +227,9 @@ class Batch:
         return out
 
     def status_counts(self):
-        c = (C.c_int64 * 4)()
-        check(lib().slb_status(self.h, c, _stream()))
+        """Instances with CHOL_FAIL / MEAN_NOCONV / GATE_REJECT / NONFINITE / QR_ROWS set (all SLB_NSTATUS bits)."""
+        c = (C.c_int64 * NSTATUS)()
+        check(lib().slb_status_ex(self.h, c, NSTATUS, _stream()))
         return list(c)
 
     def clear_status(self):

@@ -67,7 +67,7 @@ def test_usckf_gate_and_indefinite_covariance(slo):
     sc = synth.usckf_scenario(B, seed=43)
     sc["z"][:5] += 100.0
     P = sc["P"].copy()
-    P[5, 40, 40] = -1.0
+    P[5, 30, 30] = -1.0      # inside the part of Pk the update factors (columns < 36 + nk, rounded up to a panel of 4)
     f = engine.Usckf(B)
     f.set_state(sc["mu"], P)
     f.update(engine.MM_USCKF_VO, sc["z"], sc["R"], gate_dof=3)
