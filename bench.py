@@ -248,7 +248,7 @@ class FusionWorkload:
 
 class UsckfWorkload:
     """BASELINE configs 1/4: Monte-Carlo USCKF fleet (n=12, N=36+3+9=48, m=3), 4M instances over 8 GPUs =
-    524,288 per GPU, predict (IMU-style process model) + update (VO features) per step, two launches.
+    524,288 per GPU, predict (IMU-style process model) + update (VO features) per step, ONE fused launch.
     The fleet is 2048 distinct seeded priors replicated on the device; inputs differ per instance."""
     name = "usckf"
     metric = "filter-steps/sec (predict+update)"
@@ -257,7 +257,7 @@ class UsckfWorkload:
     NPRIOR = 2048
     bytes_per_unit = 19704          # 2*8*(1176+51) + 72
     flops_per_unit = 1.5e5
-    kernel = "slbd::usckf_update_kernel<3,9> (+ usckf_predict_kernel)"
+    kernel = "slbd::usckf_step_kernel<PM_USCKF_TEST, 3, 9, predict+update fused>"
 
     def __init__(self, rank, seed=4321):
         self.sc = synth.usckf_scenario(self.NPRIOR, seed=seed + 1000 * rank)
@@ -285,19 +285,12 @@ class UsckfWorkload:
         self.hmu = torch.empty((self.B, 51), dtype=torch.float64).pin_memory()
         self.l2_policy = "fleet state %.0f MB per step > L2" % (self.B * (1184 + 52) * 8 / 1e6)
 
-    phases = ("predict12_kernel", "usckf_update_kernel")
-    dominant = 1
-
-    def step_phase(self, k, p):
-        e = self.engine
-        if p == 0:
-            self.f.predict(e.PM_USCKF_TEST, self.du, self.sc["dt"], self.Q)
-        else:
-            self.f.update(e.MM_USCKF_VO, self.dz, self.R)
+    phases = ("usckf_step_kernel",)   # predict + update fused: the record crosses HBM once per step
+    dominant = 0
 
     def step(self, k):
-        self.step_phase(k, 0)
-        self.step_phase(k, 1)
+        e = self.engine
+        self.f.step(e.PM_USCKF_TEST, e.MM_USCKF_VO, self.du, self.sc["dt"], self.Q, self.dz, self.R)
 
     def step_e2e(self, k):
         e = self.engine
@@ -310,7 +303,7 @@ class UsckfWorkload:
         return self.B
 
     def launches_per_step(self):
-        return 2
+        return 1
 
     def status_ok(self):
         return sum(self.f.status_counts()) == 0

@@ -81,6 +81,7 @@ struct FilterArgs {
     int gate;
     int nk, nl, k;
     int32_t *misc;
+    int prefetch;     // USCKF step: L2-prefetch the record of instance (i + prefetch); 0 = off
     double *mu_out;   // optional instance-major copy of the posterior means (may be mapped host memory), B x QD
 };
 

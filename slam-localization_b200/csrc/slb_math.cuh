@@ -65,6 +65,17 @@ SLB_DEV void sqrt_rsqrt(double x, double &s, double &rs) {
     rs = y;
 }
 
+// 1/sqrt(x) alone (same seed and Newton steps as sqrt_rsqrt)
+SLB_DEV double rsqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+}
+
 // MTK cos_sinc_sqrt: c = cos(sqrt(x)), s = sin(sqrt(x))/sqrt(x)
 SLB_DEV void cos_sinc_sqrt(double x, double &c, double &s) {
     if (x < 1.0) {  // |rotation| < 2 rad

@@ -468,7 +468,24 @@ static int launch_step_t(const FilterArgs &a, cudaStream_t s) {
     static_assert(smem <= 227 * 1024, "record + scratch of one CTA must fit in shared memory");
     auto kern = slbd::usckf_step_kernel<SLB_PM_USCKF_TEST, NK, NL, PRED, UPD, WPB, MINB>;
     SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(a.B + WPB - 1) / WPB, WPB * 32, smem, s>>>(a);
+    // L2 prefetch distance in instances: SLB_USCKF_PREFETCH waves of (SMs x resident warps); default 2 waves
+    static const int ahead = [] {
+        const char *e = getenv("SLB_USCKF_PREFETCH");
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return (e ? atoi(e) : 2) * sms * WPB * MINB;
+    }();
+    FilterArgs b = a;
+    b.prefetch = ahead;
+    // experiment knob: SLB_USCKF_CTAS=1|2 pads the dynamic shared memory so that only that many CTAs fit per SM
+    static const size_t pad = [] {
+        const char *e = getenv("SLB_USCKF_CTAS");
+        const int n = e ? atoi(e) : 0;
+        return n == 1 ? (size_t)(200 * 1024) - smem : n == 2 ? (size_t)(110 * 1024) - smem : (size_t)0;
+    }();
+    if (pad) SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad)));
+    kern<<<(a.B + WPB - 1) / WPB, WPB * 32, smem + pad, s>>>(b);
     count_launch();
     SLB_CUDA(cudaGetLastError());
     return SLB_OK;

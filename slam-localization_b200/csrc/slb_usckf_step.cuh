@@ -41,10 +41,15 @@ struct StepCfg {
     static constexpr int NCOL = 4 * NPAN;
     static constexpr int JLAST = (NCOL - 1) >> 3;      // last tile column that is ever updated
     static constexpr int NGRP = (NPAN + 3) / 4;        // sigma-point passes (16 columns = 32 points each)
-    static constexpr int PS4 = 4 * NPAD + 4;           // stride between the 4 panels of a group (+4: conflict-free column reads)
+    // A finished panel (NPAD rows x 4 columns) is stored as two planes of column PAIRS, element (i, c) at
+    // (c >> 1) * PL + 2 i + (c & 1): row accesses (one double2 per lane and plane) and DMMA fragment loads are then
+    // contiguous across the warp, and with PL = 2 mod 16, PS4 = 4 mod 16 the 16 columns of a group fall into 16
+    // different bank pairs for the sigma points' column reads.
+    static constexpr int PL = 2 * NPAD + 2;
+    static constexpr int PS4 = 2 * PL;                 // stride between the 4 panels of a group
     static constexpr int KP = (NK_ + 3) / 4 * 4;       // padded row length of K / covXZ (DMMA k-dimension)
     static constexpr int LF = 4 * PS4;                 // finished panel rows U of the current group
-    static constexpr int LRAW = 4 * NPAD;              // the current panel as extracted from the accumulators
+    static constexpr int LRAW = PS4;                   // the current panel as extracted from the accumulators (same planes)
     static constexpr int KK = 2 * NPAD * KP;           // K | covXZ rows, overlays LF | LRAW once the factorisation is over
     static constexpr int SCR0 = (LF + LRAW > KK ? LF + LRAW : KK);
     static constexpr int WGS = (16 * NK_ + 1) / 2 * 2; // W' of the current group
@@ -62,6 +67,9 @@ SLB_DEV void bulk_s2g(void *gdst, const void *ssrc, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n cp.async.bulk.commit_group;\n" ::"l"(gdst),
                  "r"(saddr(ssrc)), "r"(bytes)
                  : "memory");
+}
+SLB_DEV void bulk_prefetch_l2(const void *gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 SLB_DEV void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 SLB_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
@@ -143,13 +151,13 @@ SLB_DEV void sigma_group(UpdState<C> &s, const double *mus, const double *Lf, do
     constexpr int NK = C::NK, PS4 = C::PS4;
     constexpr int col0 = 16 * G;
     constexpr int ncols = C::NCOL - col0 < 16 ? C::NCOL - col0 : 16;
-    const int jl = lane >> 1;
-    const bool neg = lane & 1, act = jl < ncols;
-    double sq_, rs;
-    sqrt_rsqrt(dv[act ? col0 + jl : 0], sq_, rs);          // L(:,j) = U(:,j) / sqrt(d_j): the scale rides on the sign
-    const double sgn = neg ? -rs : rs;
-    const double *col = Lf + (jl >> 2) * PS4 + (jl & 3);   // U(r, j) = col[4 r]; rows above the diagonal hold zeros
-    auto Lc = [&](int r) -> double { return act ? sgn * col[4 * r] : 0.0; };
+    const bool neg = lane & 1, act = (lane >> 1) < ncols;
+    const int jl = act ? lane >> 1 : 0;                    // idle lanes (last group) shadow column 0 with a zero scale
+    const double rs = rsqrt_fast(dv[col0 + jl]);           // L(:,j) = U(:,j) / sqrt(d_j): the scale rides on the sign
+    const double sgn = act ? (neg ? -rs : rs) : 0.0;
+    // U(r, j) = col[2 r]; rows above the diagonal hold zeros
+    const double *col = Lf + (jl >> 2) * PS4 + ((jl & 3) >> 1) * C::PL + (jl & 1);
+    auto Lc = [&](int r) -> double { return sgn * col[2 * r]; };
     double xpk[3], xqk[4], xpi[3], xqi[4], xf[NK];
     if (col0 <= 5) {   // column j perturbs rows >= j only: statek is untouched from the second group on
 #pragma unroll
@@ -200,11 +208,10 @@ SLB_DEV void sigma_group(UpdState<C> &s, const double *mus, const double *Lf, do
     const bool has1 = lane + 32 < C::NPAD;
 #pragma unroll
     for (int qq = 0; qq < ncols / 4; ++qq) {
-        const double2 *r0 = reinterpret_cast<const double2 *>(Lf + qq * PS4 + 4 * lane);
-        const double2 *r1 = reinterpret_cast<const double2 *>(Lf + qq * PS4 + 4 * (lane + 32));
-        const double2 x01 = r0[0], x23 = r0[1];
+        const double *pa = Lf + qq * PS4 + 2 * lane, *pb = pa + C::PL;
+        const double2 x01 = *reinterpret_cast<const double2 *>(pa), x23 = *reinterpret_cast<const double2 *>(pb);
         double2 y01 = make_double2(0.0, 0.0), y23 = y01;
-        if (has1) { y01 = r1[0]; y23 = r1[1]; }
+        if (has1) { y01 = *reinterpret_cast<const double2 *>(pa + 64); y23 = *reinterpret_cast<const double2 *>(pb + 64); }
         const double x[4] = {x01.x, x01.y, x23.x, x23.y}, y[4] = {y01.x, y01.y, y23.x, y23.y};
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4)
@@ -226,22 +233,23 @@ struct PanelStep {
         constexpr int I1 = (K + 4) >> 3;     // first tile row / column with live entries after this panel
         const int a_ = lane & 3, b_ = lane >> 2;
         double *Lq = Lf + Q * PS4;
-        // (1) the 16 lanes holding columns K..K+3 park them (rows of tile row J0 and below)
+        constexpr int PL = C::PL;
+        // (1) the 16 lanes holding columns K..K+3 park them (rows of tile row J0 and below), a column pair per plane
         if ((a_ >> 1) == H) {
 #pragma unroll
             for (int I = J0; I < NT; ++I)
-                *reinterpret_cast<double2 *>(Lraw + 4 * (8 * I + b_) + 2 * (a_ & 1)) = make_double2(s.c0[I][J0], s.c1[I][J0]);
+                *reinterpret_cast<double2 *>(Lraw + (a_ & 1) * PL + 2 * (8 * I + b_)) = make_double2(s.c0[I][J0], s.c1[I][J0]);
         }
         __syncwarp();
         // (2) the 4 x 4 diagonal block, eliminated redundantly by every lane
         double m10, m20, m30, m21, m31, m32, r0, r1, r2, r3, d0, d1, d2, d3;
         {
-            const double *A = Lraw + 4 * K;
+            const double *A = Lraw + 2 * K, *Bp = A + PL;
             const double a00 = A[0];
-            const double2 a1 = *reinterpret_cast<const double2 *>(A + 4);
-            const double2 a2 = *reinterpret_cast<const double2 *>(A + 8);
-            const double a22 = A[10];
-            const double2 a3 = *reinterpret_cast<const double2 *>(A + 12), a3b = *reinterpret_cast<const double2 *>(A + 14);
+            const double2 a1 = *reinterpret_cast<const double2 *>(A + 2);
+            const double2 a2 = *reinterpret_cast<const double2 *>(A + 4);
+            const double a22 = Bp[4];
+            const double2 a3 = *reinterpret_cast<const double2 *>(A + 6), a3b = *reinterpret_cast<const double2 *>(Bp + 6);
             d0 = a00;
             r0 = rcp_fast(d0);
             m10 = a1.x * r0; m20 = a2.x * r0; m30 = a3.x * r0;
@@ -261,35 +269,41 @@ struct PanelStep {
             *reinterpret_cast<double2 *>(dv + K) = make_double2(d0, d1);
             *reinterpret_cast<double2 *>(dv + K + 2) = make_double2(d2, d3);
         }
-        // (3) lane i finishes rows i and i + 32 of the panel: U(i, K + c); zeros above the diagonal / above the panel
+        // (3) lane i finishes rows i and i + 32 of the panel: U(i, K + c); zeros above the diagonal / above the panel.
+        //     Branch-free: rows above the panel read whatever the planes hold and select zeros.
         auto finish = [&](int i, bool have) {
-            double2 u01 = make_double2(0.0, 0.0), u23 = u01;
-            if (have && i >= K && (K < 32 || i >= 32)) {
-                const double2 x01 = *reinterpret_cast<const double2 *>(Lraw + 4 * i);
-                const double2 x23 = *reinterpret_cast<const double2 *>(Lraw + 4 * i + 2);
-                const double u0 = x01.x;
-                const double u1 = fma(-u0, m10, x01.y);
-                const double u2 = fma(-u1, m21, fma(-u0, m20, x23.x));
-                const double u3 = fma(-u2, m32, fma(-u1, m31, fma(-u0, m30, x23.y)));
-                u01.x = u0;
-                u01.y = i >= K + 1 ? u1 : 0.0;
-                u23.x = i >= K + 2 ? u2 : 0.0;
-                u23.y = i >= K + 3 ? u3 : 0.0;
-            }
+            const double2 x01 = *reinterpret_cast<const double2 *>(Lraw + 2 * i);
+            const double2 x23 = *reinterpret_cast<const double2 *>(Lraw + PL + 2 * i);
+            const double u0 = x01.x;
+            const double u1 = fma(-u0, m10, x01.y);
+            const double u2 = fma(-u1, m21, fma(-u0, m20, x23.x));
+            const double u3 = fma(-u2, m32, fma(-u1, m31, fma(-u0, m30, x23.y)));
+            double2 u01, u23;
+            u01.x = i >= K ? u0 : 0.0;
+            u01.y = i >= K + 1 ? u1 : 0.0;
+            u23.x = i >= K + 2 ? u2 : 0.0;
+            u23.y = i >= K + 3 ? u3 : 0.0;
             if (have) {
-                *reinterpret_cast<double2 *>(Lq + 4 * i) = u01;
-                *reinterpret_cast<double2 *>(Lq + 4 * i + 2) = u23;
+                *reinterpret_cast<double2 *>(Lq + 2 * i) = u01;
+                *reinterpret_cast<double2 *>(Lq + PL + 2 * i) = u23;
             }
         };
-        finish(lane, true);
-        finish(lane + 32, lane + 32 < C::NPAD);
+        if (K < 32) {
+            finish(lane, true);
+        } else {   // rows 0..31 lie above the panel
+            *reinterpret_cast<double2 *>(Lq + 2 * lane) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2 *>(Lq + PL + 2 * lane) = make_double2(0.0, 0.0);
+        }
+        if (C::NPAD > 32) finish(lane + 32 < C::NPAD ? lane + 32 : lane, lane + 32 < C::NPAD);
         __syncwarp();
         // (4) rank-4 update of the live tiles: A fragment = U(8I + b, K + a), B fragment = -U(8J + b, K + a) / d_{K+a}
         if (I1 <= JLAST) {
             double f[NT];
+            const double *fp = Lq + (a_ >> 1) * PL + (a_ & 1) + 2 * b_;
 #pragma unroll
-            for (int I = I1; I < NT; ++I) f[I] = Lq[4 * (8 * I + b_) + a_];
-            const double nr = a_ == 0 ? -r0 : a_ == 1 ? -r1 : a_ == 2 ? -r2 : -r3;
+            for (int I = I1; I < NT; ++I) f[I] = fp[16 * I];
+            const double rlo = (a_ & 1) ? r1 : r0, rhi = (a_ & 1) ? r3 : r2;
+            const double nr = -((a_ & 2) ? rhi : rlo);
 #pragma unroll
             for (int J = I1; J <= JLAST; ++J) {
                 const double g = f[J] * nr;
@@ -654,6 +668,8 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_step_kernel(slb::FilterA
         mbar_expect_tx(bar, (C::PSTR + C::QS) * 8);
         bulk_g2s(Ps, Pg, C::PSTR * 8, bar);
         bulk_g2s(mus, mug, C::QS * 8, bar);
+        // the record a warp of a later wave of CTAs will want: pull it into L2 now (one wave = SMs x resident warps)
+        if (a.prefetch > 0 && inst + a.prefetch < a.B) bulk_prefetch_l2(Pg + (size_t)a.prefetch * a.pstride, C::PSTR * 8);
     }
     // the measurement and the control input are fetched now: with the zero-copy *_step_host they live in mapped host
     // memory and their PCIe latency must not sit in the middle of the step
