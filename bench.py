@@ -152,7 +152,7 @@ class UkfomWorkload:
         self.hz = torch.from_numpy(self.sc["z"].copy()).pin_memory()
         self.hQ = torch.from_numpy(self.sc["Q"].copy()).pin_memory()
         self.hR = torch.from_numpy(self.sc["R"].copy()).pin_memory()
-        self.hmu = torch.empty((self.B, self.QD), dtype=torch.float64).pin_memory()
+        self.hmu = [torch.empty((self.B, self.QD), dtype=torch.float64).pin_memory() for _ in range(2)]
         self.l2_policy = "rotating %d resident fleets (%.0f MB > L2)" % (self.nfleets, self.nfleets * per_fleet / 1e6)
 
     def step(self, k):
@@ -163,7 +163,12 @@ class UkfomWorkload:
     def step_e2e(self, k):
         e = self.engine
         self.fleets[k % self.nfleets].step_host(e.PM_UKFOM_IMU, e.MM_GPS_POS, self.hu, self.sc["dt"], self.hQ, self.hz,
-                                                self.hR, mu_out=self.hmu)
+                                                self.hR, mu_out=self.hmu[k & 1], wait=False)
+
+    e2e_api = "slb_ukf_step_host_async per step (pinned host u/z in, posterior means out to one of two host buffers), slb_wait at the end"
+
+    def e2e_drain(self):
+        self.fleets[0].wait()
 
     def e2e_bytes(self):
         return (self.B * 9 + 81 + 9) * 8, self.B * self.QD * 8
@@ -282,7 +287,7 @@ class UsckfWorkload:
         self.hz = torch.from_numpy(self.z).pin_memory()
         self.hQ = torch.from_numpy(self.sc["Q"].copy()).pin_memory()
         self.hR = torch.from_numpy(self.sc["R"].copy()).pin_memory()
-        self.hmu = torch.empty((self.B, 51), dtype=torch.float64).pin_memory()
+        self.hmu = [torch.empty((self.B, 51), dtype=torch.float64).pin_memory() for _ in range(2)]
         self.l2_policy = "fleet state %.0f MB per step > L2" % (self.B * (1184 + 52) * 8 / 1e6)
 
     phases = ("usckf_step_kernel",)   # predict + update fused: the record crosses HBM once per step
@@ -294,7 +299,13 @@ class UsckfWorkload:
 
     def step_e2e(self, k):
         e = self.engine
-        self.f.step_host(e.PM_USCKF_TEST, e.MM_USCKF_VO, self.hu, self.sc["dt"], self.hQ, self.hz, self.hR, mu_out=self.hmu)
+        self.f.step_host(e.PM_USCKF_TEST, e.MM_USCKF_VO, self.hu, self.sc["dt"], self.hQ, self.hz, self.hR,
+                         mu_out=self.hmu[k & 1], wait=False)
+
+    e2e_api = "slb_usckf_step_host_async per step (pinned host u/z in, posterior means out to one of two host buffers), slb_wait at the end"
+
+    def e2e_drain(self):
+        self.f.wait()
 
     def e2e_bytes(self):
         return (self.B * 9 + 144 + 9) * 8, self.B * 51 * 8
@@ -389,7 +400,12 @@ class MsckfWorkload:
     def step_e2e(self, k):
         e = self.engine
         self.f.step_host(e.PM_MSCKF_DELTAPOSE, e.MM_MSCKF_REPROJ, self.hu, 0.0, self.hQ, self.hlm, self.hz, self.hR,
-                         mu_out=self.hmu)
+                         mu_out=self.hmu, wait=False)
+
+    e2e_api = "slb_msckf_step_host_async per step (chunked H2D / kernels / D2H pipeline replayed as a CUDA graph), slb_wait at the end"
+
+    def e2e_drain(self):
+        self.f.wait()
 
     def e2e_bytes(self):
         return (self.B * (13 + 2 * self.NFEAT) + 144 + 3 * self.NFEAT + (2 * self.NFEAT) ** 2) * 8, self.B * (13 + 7 * self.K) * 8
@@ -591,14 +607,23 @@ def measure(wl, args, ctx, sample_clocks):
                "api": getattr(wl, "e2e_api", None)}
 
     # ---- end-of-run ensemble statistics (the only collective; not on the step path) -----------------
-    gather_ms = None
+    # slb_gather_stats: per-shard (count, sum x, sum x x^T) + ncclAllReduce inside the C library (its own communicator,
+    # created through the C ABI; at N = 1 there is no communicator and the call is the local reduction alone)
+    gather_ms, gather_count = None, None
     if wl.stats_tensor() is not None:
+        comm = fleet.make_nccl_comm(engine, rank, world) if world > 1 else None
+        fl = wl.fleets[0] if hasattr(wl, "fleets") else wl.f
+        out = engine.DeviceArray(shape=(1 + fl.N + fl.N * fl.N,))
+        fl.gather_stats(comm, out)          # warm-up (NCCL connects lazily)
         barrier()
         e0.record()
-        wl.gather_stats() if hasattr(wl, "gather_stats") else fleet.merge_stats(wl.stats_tensor())
+        fl.gather_stats(comm, out)
         e1.record()
         barrier()
         gather_ms = e0.elapsed_time(e1)
+        gather_count = float(out.t[0].item())   # instances behind the merged statistics: world x fleet
+        if comm is not None:
+            comm.close()
 
     if rank != 0:
         return None
@@ -625,7 +650,7 @@ def measure(wl, args, ctx, sample_clocks):
         "roofline": r_f64 if binding == "fp64" else r_hbm,       # the binding roofline
         "roofline_other": r_hbm if binding == "fp64" else r_f64,  # the non-binding one, for information
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "status_clean": ok,
-        "ensemble_stats_allreduce_ms": gather_ms,
+        "ensemble_stats_allreduce_ms": gather_ms, "ensemble_stats_instances": gather_count,
     }
 
 
@@ -682,7 +707,7 @@ def main():
             if rank == 0:
                 keep = {k: r[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "config", "l2_policy", "roofline",
                                           "roofline_other", "e2e", "gpu_launches", "status_clean",
-                                          "ensemble_stats_allreduce_ms")}
+                                          "ensemble_stats_allreduce_ms", "ensemble_stats_instances")}
                 if world == 1 and not args.no_cpu_baseline:
                     keep["cpu_baseline"], _ = cpu_baseline(w2, budget_s=5.0)
                 also[name] = keep

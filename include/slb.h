@@ -102,7 +102,8 @@ typedef struct {
     int32_t kind;      /* SLB_KIND_*                                                     */
     int32_t layout;    /* SLB_LAYOUT_* for KIND_UKF; ignored otherwise                   */
     int32_t batch;     /* number of independent filter instances on this device          */
-    int32_t nk, nl;    /* USCKF: featuresk.size(), featuresk_l.size() (State.hpp:539-540)*/
+    int32_t nk, nl;    /* USCKF: featuresk.size(), featuresk_l.size() (State.hpp:539-540);
+                          built shapes: nk in {3,6,9}, nl in {0,3,6,9}, nk + nl <= 12         */
     int32_t nclones;   /* MSCKF: sensorsk.size() (State.hpp:342)                         */
     int32_t device;    /* CUDA device ordinal                                            */
     int32_t reserved[9];
@@ -150,6 +151,17 @@ int slb_ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double
                       const double *Q_host, const double *z_host, const double *R_host,
                       int gate_dof, double *mu_out_host, void *stream);
 
+/* Pipelined flavour: identical, but returns as soon as the step is enqueued on `stream` (no
+ * synchronisation), so consecutive steps overlap their host<->device traffic with each other's
+ * kernels.  The host buffers must stay valid (and mu_out_host unread) until slb_wait(h, stream);
+ * pageable (not page-locked) buffers fall back to the synchronous behaviour.  Exists for all three
+ * filter kinds (slb_usckf_step_host_async, slb_msckf_step_host_async below). */
+int slb_ukf_step_host_async(slb_handle h, int pm, int mm, const double *u_host, double dt,
+                            const double *Q_host, const double *z_host, const double *R_host,
+                            int gate_dof, double *mu_out_host, void *stream);
+/* Completes every step enqueued on `stream` by the *_step_host_async entry points. */
+int slb_wait(slb_handle h, void *stream);
+
 /* ---- localization::Usckf --------------------------------------------------------------- */
 /* predict(f, Q) Usckf.hpp:107-244 */
 int slb_usckf_predict(slb_handle h, int pm, const double *u_dev, double dt, const double *Q_dev,
@@ -163,6 +175,9 @@ int slb_usckf_step(slb_handle h, int pm, int mm, const double *u_dev, double dt,
 int slb_usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt,
                         const double *Q_host, const double *z_host, const double *R_host,
                         int gate_dof, double *mu_out_host, void *stream);
+int slb_usckf_step_host_async(slb_handle h, int pm, int mm, const double *u_host, double dt,
+                              const double *Q_host, const double *z_host, const double *R_host,
+                              int gate_dof, double *mu_out_host, void *stream);
 /* cloning(mode) Usckf.hpp:391-433 */
 int slb_usckf_clone(slb_handle h, int mode, void *stream);
 /* setMeasurement(mode, z, R) Usckf.hpp:322-389; z_dev: batch x len, R_dev: len x len shared.
@@ -197,6 +212,11 @@ int slb_msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, doub
                         const double *Q_host, const double *params_host, int nparams, int m,
                         const double *z_host, const double *R_host, int gate, double *mu_out_host,
                         void *stream);
+
+int slb_msckf_step_host_async(slb_handle h, int pm, int mm, const double *u_host, double dt,
+                              const double *Q_host, const double *params_host, int nparams, int m,
+                              const double *z_host, const double *R_host, int gate,
+                              double *mu_out_host, void *stream);
 
 /* ---- localization::DataModel<double,D> ---------------------------------------------------
  * fusion(data2) DataModel.hpp:48-60 over n independent pairs.  Instance-major device arrays:
@@ -270,6 +290,26 @@ int slb_clear_status(slb_handle h, void *stream);
  * the SO3 log of every block of the q-vector; out_dev has 1 + nv + nv*nv doubles, nv = N.
  * Multi-GPU callers all-reduce out_dev (NCCL sum) -- see bench.py. */
 int slb_ensemble_stats(slb_handle h, double *out_dev, void *stream);
+/* The same, merged over the ranks of an NCCL communicator (the only collective of the path, end of
+ * run): slb_ensemble_stats on this device's shard, then ncclAllReduce(sum, double) of the 1 + nv + nv*nv
+ * values in place on `stream`.  nccl_comm is an ncclComm_t passed as void* (NULL = this shard only).  NCCL is
+ * resolved at run time (dlopen libnccl.so.2); SLB_ERR_NCCL if it is missing or a call fails. */
+int slb_gather_stats(slb_handle h, void *nccl_comm, double *out_dev, void *stream);
+/* Communicator helpers for callers without an NCCL binding of their own (ctypes, cgo, the C++ facade):
+ * rank 0 calls slb_nccl_unique_id (id128: 128 bytes) and ships the bytes to the other ranks by any means,
+ * every rank then calls slb_nccl_comm_init with its rank and CUDA device. */
+int slb_nccl_unique_id(void *id128);
+int slb_nccl_comm_init(void **comm, int nranks, const void *id128, int rank, int device);
+int slb_nccl_comm_destroy(void *comm);
+
+/* checkSigmaPoints() Usckf.hpp:769-789 / Msckf.hpp:818-838 for every instance of a USCKF / MSCKF batch:
+ * sigma points of (mu_state, Pk), their manifold mean muX and covariance Pktest.  The reference asserts
+ * max|Pktest - Pk| <= 1e-6 and mu_state == muX; the batch reports per instance
+ *   flags_dev[i] (int32): bit 0 covariance off by more than 1e-6, bit 1 mean moved by more than 1e-12 (tangent
+ *                         space, inf-norm; the reference's exact == is rounding noise), bit 2 LLT of Pk failed
+ *   diff_dev[2i], [2i+1]: max|Pktest - Pk| and |muX [-] mu|_inf (diff_dev may be NULL). */
+int slb_check_sigma_points(slb_handle h, int32_t *flags_dev, double *diff_dev, void *stream);
+
 /* Measures the device's FP64 FMA rate (TFLOP/s, FMA = 2) with a register-resident DFMA kernel:
  * the roofline denominator for the FP64-bound configs (MEASURED_PEAKS.json has no FP64 entry). */
 int slb_bench_fp64_peak(double *tflops_out);

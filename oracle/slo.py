@@ -213,6 +213,17 @@ def msckf_update(mm, k, mu, P, landmarks, z, R, gate=True, nthreads=1):
     return mu, P, out, st, it
 
 
+def check_sigma_points(kind, mu, P, nk=0, nl=0, k=0, nthreads=1):
+    """checkSigmaPoints() of Usckf (kind 2) / Msckf (kind 3): returns (flags, diff[B,2])."""
+    mu, P = _d(mu), _d(P)
+    B = mu.shape[0]
+    flags = np.zeros(B, np.int32)
+    diff = np.zeros((B, 2))
+    rc = lib().slo_check_sigma_points(kind, B, nk, nl, k, _p(mu), _p(P), _p(flags), _p(diff), nthreads)
+    assert rc == 0
+    return flags, diff
+
+
 def msckf_remove_outliers(innov, S, N=12):
     innov, S = _d(innov), _d(S)
     m = innov.shape[0]

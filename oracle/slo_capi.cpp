@@ -199,6 +199,44 @@ int slo_msckf_update(int mm, int B, int k, double *mu, double *P, const double *
     });
     return 0;
 }
+// checkSigmaPoints() Usckf.hpp:769-789 (kind 2) / Msckf.hpp:818-838 (kind 3): sigma points of (mu, Pk), their manifold
+// mean muX and covariance Pktest.  The reference asserts max|Pktest - Pk| <= 1e-6 and mu == muX; here the two quantities
+// are returned (diff[2i] = max|Pktest - Pk|, diff[2i+1] = |muX [-] mu|_inf) with flags bit 0: covariance off by more
+// than 1e-6, bit 1: mean moved by more than 1e-12 (the reference's exact == is rounding noise), bit 2: LLT failed.
+int slo_check_sigma_points(int kind, int B, int nk, int nl, int k, const double *mu, const double *P, int *flags,
+                           double *diff, int nthreads) {
+    const int N = kind == 2 ? 36 + nk + nl : 12 + 6 * k, q = kind == 2 ? 39 + nk + nl : 13 + 7 * k;
+    if (kind != 2 && kind != 3) return -1;
+    parallel_for(B, nthreads, [&](int i) {
+        const Vec m(mu + (size_t)i * q, mu + (size_t)(i + 1) * q);
+        const Mat Pk = load_mat(P + (size_t)i * N * N, N, N);
+        std::vector<Vec> X;
+        Layout lay;
+        int info;
+        if (kind == 2) {
+            Usckf f(m, nk, nl, Pk);
+            lay = f.aug();
+            info = f.sigma_points_aug(Vec(N, 0.0), X);
+        } else {
+            lay = Layout::multi(k);
+            info = sigma_points_vec(lay, m, Vec(N, 0.0), Pk, X);
+        }
+        int fl = info >= 0 ? 4 : 0, st = 0;
+        double dP = 0.0, dm = 0.0;
+        if (info < 0) {
+            const Vec muX = mean_manifold(lay, X, &st);
+            const Mat Pt = cov_manifold(lay, muX, X);
+            for (int r = 0; r < N; ++r)
+                for (int c = 0; c <= r; ++c) dP = std::max(dP, std::fabs(Pt(r, c) - Pk(r, c)));
+            for (double d : boxminus(lay, muX, m)) dm = std::max(dm, std::fabs(d));
+            if (dP > 1e-6) fl |= 1;
+            if (dm > 1e-12) fl |= 2;
+        }
+        flags[i] = fl;
+        if (diff) { diff[2 * i] = dP; diff[2 * i + 1] = dm; }
+    });
+    return 0;
+}
 // removeOutliers alone (Msckf.hpp:723-754, quirk Q6): returns the kept original row indices
 int slo_msckf_remove_outliers(int m, int N, const double *innov, const double *S, int *kept, int *nkept) {
     Msckf f(0, Layout::state12().identity(), Mat(12, 12));

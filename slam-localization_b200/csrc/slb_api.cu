@@ -6,6 +6,9 @@
 #include <atomic>
 #include <new>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "slb_internal.h"
 #include "slb_math.cuh"
 
@@ -250,9 +253,10 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
             h->QD = cfg->layout + 1;
             break;
         case SLB_KIND_USCKF:
-            if (cfg->nk < 0 || cfg->nl < 0 || cfg->nk % 3 != 0 || cfg->nk + cfg->nl > 28) {
+            if (!usckf_shape_supported(cfg->nk, cfg->nl)) {
                 delete h;
-                return set_error(SLB_ERR_INVALID, "slb_create: USCKF needs nk % 3 == 0 and nk + nl <= 28");
+                return set_error(SLB_ERR_INVALID,
+                                 "slb_create: USCKF batches are built for nk in {3,6,9}, nl in {0,3,6,9} with nk + nl <= 12");
             }
             h->N = 36 + cfg->nk + cfg->nl;
             h->QD = 39 + cfg->nk + cfg->nl;
@@ -550,7 +554,7 @@ static void *dev_alias_v(const void *p) {
 static const double *dev_alias(const double *p) { return (const double *)dev_alias_v(p); }
 static double *dev_alias_m(double *p) { return (double *)dev_alias_v(p); }
 
-static int step_host(slb_handle h, const HostStep &hs, void *stream) {
+static int step_host(slb_handle h, const HostStep &hs, void *stream, bool wait = true) {
     if (!h || !hs.u || !hs.Q || !hs.z || !hs.R) return set_error(SLB_ERR_INVALID, "slb_*_step_host: null argument");
     DeviceGuard guard(h->cfg.device);
     cudaStream_t s = S(stream);
@@ -583,7 +587,7 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream) {
         const int rc = h->cfg.kind == SLB_KIND_UKF ? launch_ukf(h->cfg.layout, hs.pm, hs.mm, true, true, a, s)
                                                    : launch_usckf(hs.pm, hs.mm, true, true, a, s);
         if (rc != SLB_OK) return rc;
-        SLB_CUDA(cudaStreamSynchronize(s));
+        if (wait) SLB_CUDA(cudaStreamSynchronize(s));
         return SLB_OK;
     }
     const int ki[8] = {hs.pm, hs.mm, hs.nu, hs.m, hs.nq, hs.nparams, hs.gate, 0};
@@ -618,15 +622,31 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream) {
     }
     SLB_CUDA(cudaGraphLaunch(h->step_exec, s));
     count_launch(h->step_kernels);
-    SLB_CUDA(cudaStreamSynchronize(s));
+    if (wait) SLB_CUDA(cudaStreamSynchronize(s));
     return SLB_OK;
 }
-int slb_ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
-                      const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+static int ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                         const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream, bool wait) {
     if (!h || h->cfg.kind != SLB_KIND_UKF) return set_error(SLB_ERR_INVALID, "slb_ukf_step_host: handle is not a UKF batch");
     if (mm != SLB_MM_GPS_POS) return set_error(SLB_ERR_INVALID, "ukf: unsupported measurement model");
     const HostStep hs = {pm, mm, pm_nu(pm), 3, h->N, 0, gate_dof, dt, u_host, Q_host, nullptr, z_host, R_host, mu_out_host};
-    return step_host(h, hs, stream);
+    return step_host(h, hs, stream, wait);
+}
+int slb_ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                      const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+    return ukf_step_host(h, pm, mm, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, true);
+}
+int slb_ukf_step_host_async(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                            const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+    return ukf_step_host(h, pm, mm, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, false);
+}
+// Completes every step enqueued on `stream` by the *_step_host_async entry points (the host buffers passed to them
+// may be reused / read afterwards).
+int slb_wait(slb_handle h, void *stream) {
+    if (!h) return set_error(SLB_ERR_INVALID, "slb_wait: null argument");
+    DeviceGuard guard(h->cfg.device);
+    SLB_CUDA(cudaStreamSynchronize(S(stream)));
+    return SLB_OK;
 }
 
 // ---- localization::Usckf -----------------------------------------------------------------------------
@@ -650,11 +670,19 @@ int slb_usckf_step(slb_handle h, int pm, int mm, const double *u, double dt, con
                    const double *R, int gate_dof, void *stream) {
     return usckf_call(h, pm, mm, true, true, u, dt, Q, z, R, gate_dof, stream);
 }
-int slb_usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
-                        const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+static int usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                           const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream, bool wait) {
     if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_step_host: handle is not a USCKF batch");
     const HostStep hs = {pm, mm, pm_nu(pm), h->cfg.nk, 12, 0, gate_dof, dt, u_host, Q_host, nullptr, z_host, R_host, mu_out_host};
-    return step_host(h, hs, stream);
+    return step_host(h, hs, stream, wait);
+}
+int slb_usckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                        const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+    return usckf_step_host(h, pm, mm, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, true);
+}
+int slb_usckf_step_host_async(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                              const double *z_host, const double *R_host, int gate_dof, double *mu_out_host, void *stream) {
+    return usckf_step_host(h, pm, mm, u_host, dt, Q_host, z_host, R_host, gate_dof, mu_out_host, stream, false);
 }
 int slb_usckf_clone(slb_handle h, int mode, void *stream) {
     if (!h || h->cfg.kind != SLB_KIND_USCKF) return set_error(SLB_ERR_INVALID, "slb_usckf_clone: handle is not a USCKF batch");
@@ -702,15 +730,28 @@ int slb_msckf_update_ekf(slb_handle h, int mm, const double *params, int m, cons
 
 // predict + update with HOST buffers (the end-to-end arm of bench.py): u | z staged on the device, the
 // posterior means copied back.  Q, R and the landmark parameters are small shared inputs.
+static int msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                           const double *params_host, int nparams, int m, const double *z_host, const double *R_host,
+                           int gate, double *mu_out_host, void *stream, bool wait);
 int slb_msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
                         const double *params_host, int nparams, int m, const double *z_host, const double *R_host,
                         int gate, double *mu_out_host, void *stream) {
+    return msckf_step_host(h, pm, mm, u_host, dt, Q_host, params_host, nparams, m, z_host, R_host, gate, mu_out_host, stream, true);
+}
+int slb_msckf_step_host_async(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                              const double *params_host, int nparams, int m, const double *z_host, const double *R_host,
+                              int gate, double *mu_out_host, void *stream) {
+    return msckf_step_host(h, pm, mm, u_host, dt, Q_host, params_host, nparams, m, z_host, R_host, gate, mu_out_host, stream, false);
+}
+static int msckf_step_host(slb_handle h, int pm, int mm, const double *u_host, double dt, const double *Q_host,
+                           const double *params_host, int nparams, int m, const double *z_host, const double *R_host,
+                           int gate, double *mu_out_host, void *stream, bool wait) {
     if (!h || h->cfg.kind != SLB_KIND_MSCKF) return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: handle is not an MSCKF batch");
     if (!u_host || !Q_host || !params_host || !z_host || !R_host || m <= 0 || nparams <= 0)
         return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: null argument");
     const HostStep hs = {pm, mm, pm_nu(pm), m, 12, nparams, gate, dt, u_host, Q_host, params_host, z_host, R_host, mu_out_host};
     if (mm != SLB_MM_MSCKF_REPROJ || (m & 1)) return set_error(SLB_ERR_INVALID, "slb_msckf_step_host: bad measurement model / m");
-    return step_host(h, hs, stream);
+    return step_host(h, hs, stream, wait);
 }
 
 // ---- localization::DataModel -------------------------------------------------------------------------
@@ -876,6 +917,90 @@ int slb_ensemble_stats(slb_handle h, double *out_dev, void *stream) {
     count_launch();
     SLB_CUDA(cudaGetLastError());
     return SLB_OK;
+}
+
+// ---- checkSigmaPoints() -----------------------------------------------------------------------------------
+int slb_check_sigma_points(slb_handle h, int32_t *flags_dev, double *diff_dev, void *stream) {
+    if (!h || !flags_dev) return set_error(SLB_ERR_INVALID, "slb_check_sigma_points: null argument");
+    DeviceGuard guard(h->cfg.device);
+    return launch_check_sigma_points(h, flags_dev, diff_dev, S(stream));
+}
+
+// ---- multi-GPU: ensemble statistics merged over an NCCL communicator ------------------------------------------
+// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the process already carries, e.g. torch's, or the
+// system one), so libslb.so has no link-time dependency on it and loads on machines without NCCL.
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi &nccl_api() {
+    static NcclApi a = [] {
+        NcclApi x;
+        x.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!x.lib) x.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!x.lib) return x;
+        x.GetUniqueId = (decltype(x.GetUniqueId))dlsym(x.lib, "ncclGetUniqueId");
+        x.CommInitRank = (decltype(x.CommInitRank))dlsym(x.lib, "ncclCommInitRank");
+        x.CommDestroy = (decltype(x.CommDestroy))dlsym(x.lib, "ncclCommDestroy");
+        x.AllReduce = (decltype(x.AllReduce))dlsym(x.lib, "ncclAllReduce");
+        x.GetErrorString = (decltype(x.GetErrorString))dlsym(x.lib, "ncclGetErrorString");
+        x.ok = x.GetUniqueId && x.CommInitRank && x.CommDestroy && x.AllReduce;
+        return x;
+    }();
+    return a;
+}
+int nccl_fail(const char *what, ncclResult_t r) {
+    NcclApi &a = nccl_api();
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, a.GetErrorString ? a.GetErrorString(r) : "NCCL error");
+    return set_error(SLB_ERR_NCCL, buf);
+}
+}  // namespace
+
+int slb_nccl_unique_id(void *id128) {
+    if (!id128) return set_error(SLB_ERR_INVALID, "slb_nccl_unique_id: null argument");
+    NcclApi &a = nccl_api();
+    if (!a.ok) return set_error(SLB_ERR_NCCL, "NCCL is not available (dlopen libnccl.so.2 failed)");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    const ncclResult_t r = a.GetUniqueId((ncclUniqueId *)id128);
+    return r == ncclSuccess ? SLB_OK : nccl_fail("ncclGetUniqueId", r);
+}
+int slb_nccl_comm_init(void **comm, int nranks, const void *id128, int rank, int device) {
+    if (!comm || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return set_error(SLB_ERR_INVALID, "slb_nccl_comm_init: bad argument");
+    NcclApi &a = nccl_api();
+    if (!a.ok) return set_error(SLB_ERR_NCCL, "NCCL is not available (dlopen libnccl.so.2 failed)");
+    DeviceGuard guard(device);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t c = nullptr;
+    const ncclResult_t r = a.CommInitRank(&c, nranks, id, rank);
+    if (r != ncclSuccess) return nccl_fail("ncclCommInitRank", r);
+    *comm = c;
+    return SLB_OK;
+}
+int slb_nccl_comm_destroy(void *comm) {
+    if (!comm) return SLB_OK;
+    NcclApi &a = nccl_api();
+    if (!a.ok) return set_error(SLB_ERR_NCCL, "NCCL is not available");
+    const ncclResult_t r = a.CommDestroy((ncclComm_t)comm);
+    return r == ncclSuccess ? SLB_OK : nccl_fail("ncclCommDestroy", r);
+}
+int slb_gather_stats(slb_handle h, void *nccl_comm, double *out_dev, void *stream) {
+    if (!h || !out_dev) return set_error(SLB_ERR_INVALID, "slb_gather_stats: null argument");
+    const int rc = slb_ensemble_stats(h, out_dev, stream);
+    if (rc != SLB_OK || !nccl_comm) return rc;   // no communicator: this device's shard only
+    NcclApi &a = nccl_api();
+    if (!a.ok) return set_error(SLB_ERR_NCCL, "NCCL is not available (dlopen libnccl.so.2 failed)");
+    DeviceGuard guard(h->cfg.device);
+    const size_t n = (size_t)1 + h->N + (size_t)h->N * h->N;
+    const ncclResult_t r = a.AllReduce(out_dev, out_dev, n, ncclDouble, ncclSum, (ncclComm_t)nccl_comm, S(stream));
+    return r == ncclSuccess ? SLB_OK : nccl_fail("ncclAllReduce", r);
 }
 
 }  // extern "C"

@@ -89,12 +89,15 @@ struct FilterArgs {
 int launch_ukf(int layout, int pm, int mm, bool predict, bool update, const FilterArgs &a, cudaStream_t s);
 // slb_usckf.cu
 int launch_usckf(int pm, int mm, bool predict, bool update, const FilterArgs &a, cudaStream_t s);
+bool usckf_shape_supported(int nk, int nl);
 int launch_usckf_clone(int mode, const FilterArgs &a, cudaStream_t s);
 int launch_usckf_set_measurement(int mode, const FilterArgs &a, cudaStream_t s);
 // slb_msckf.cu
 int launch_msckf_predict(int pm, const FilterArgs &a, cudaStream_t s);
 int launch_msckf_update(int mm, const FilterArgs &a, cudaStream_t s);
 int launch_msckf_update_ekf(int mm, const FilterArgs &a, cudaStream_t s);
+// slb_check.cu
+int launch_check_sigma_points(const slb_batch_s *h, int32_t *flags, double *diff, cudaStream_t s);
 // slb_fusion.cu
 int launch_fusion(int d, int64_t n, int op, const double *x1, const double *C1, const double *x2,
                   const double *C2, double *xo, double *Co, cudaStream_t s);

@@ -31,6 +31,8 @@ EXPORTS = [
     "slb_launch_count", "slb_bench_fp64_peak", "slb_replicate", "slb_dev_alloc", "slb_dev_free", "slb_dev_copy",
     "slb_msckf_step_host", "slb_ekf_predict", "slb_ekf_update", "slb_ekf_single_update", "slb_ekf_clone",
     "slb_datamodel_safe_fuse", "slb_msckf_update_ekf", "slb_transform_compose", "slb_deadreckon_update_pose",
+    "slb_ukf_step_host_async", "slb_usckf_step_host_async", "slb_msckf_step_host_async", "slb_wait",
+    "slb_check_sigma_points", "slb_gather_stats", "slb_nccl_unique_id", "slb_nccl_comm_init", "slb_nccl_comm_destroy",
 ]
 
 
@@ -72,12 +74,21 @@ def lib():
         L.slb_usckf_update.argtypes = [vp, i32, dp, dp, i32, vp]
         L.slb_usckf_step.argtypes = [vp, i32, i32, dp, dbl, dp, dp, dp, i32, vp]
         L.slb_usckf_step_host.argtypes = [vp, i32, i32, dp, dbl, dp, dp, dp, i32, dp, vp]
+        L.slb_ukf_step_host_async.argtypes = L.slb_ukf_step_host.argtypes
+        L.slb_usckf_step_host_async.argtypes = L.slb_usckf_step_host.argtypes
+        L.slb_wait.argtypes = [vp, vp]
+        L.slb_check_sigma_points.argtypes = [vp, vp, vp, vp]
+        L.slb_gather_stats.argtypes = [vp, vp, dp, vp]
+        L.slb_nccl_unique_id.argtypes = [vp]
+        L.slb_nccl_comm_init.argtypes = [C.POINTER(vp), i32, vp, i32, i32]
+        L.slb_nccl_comm_destroy.argtypes = [vp]
         L.slb_usckf_clone.argtypes = [vp, i32, vp]
         L.slb_usckf_set_measurement.argtypes = [vp, i32, dp, dp, vp]
         L.slb_msckf_predict.argtypes = [vp, i32, dp, dbl, dp, vp]
         L.slb_msckf_update.argtypes = [vp, i32, dp, i32, dp, dp, i32, vp]
         L.slb_msckf_update_ekf.argtypes = [vp, i32, dp, i32, dp, dp, i32, vp]
         L.slb_msckf_step_host.argtypes = [vp, i32, i32, dp, dbl, dp, dp, i32, i32, dp, dp, i32, dp, vp]
+        L.slb_msckf_step_host_async.argtypes = L.slb_msckf_step_host.argtypes
         L.slb_datamodel_fuse.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp, vp]
         L.slb_datamodel_addsub.argtypes = [i32, i64, i32, dp, dp, dp, dp, dp, dp, vp]
         L.slb_datamodel_fuse_host.argtypes = [i32, i64, dp, dp, dp, dp, dp, dp]
@@ -232,6 +243,10 @@ class Batch:
         check(lib().slb_status_ex(self.h, c, NSTATUS, _stream()))
         return list(c)
 
+    def wait(self):
+        """Completes the steps enqueued with step_host(..., wait=False) on the current stream."""
+        check(lib().slb_wait(self.h, _stream()))
+
     def clear_status(self):
         check(lib().slb_clear_status(self.h, _stream()))
 
@@ -239,6 +254,41 @@ class Batch:
         out = out if out is not None else DeviceArray(shape=(1 + self.N + self.N * self.N,))
         check(lib().slb_ensemble_stats(self.h, out.ptr, _stream()))
         return out
+
+    def gather_stats(self, comm=None, out=None):
+        """slb_gather_stats: this shard's (count, sum x, sum x x^T) all-reduced over an NcclComm (None: local only)."""
+        out = out if out is not None else DeviceArray(shape=(1 + self.N + self.N * self.N,))
+        check(lib().slb_gather_stats(self.h, comm.c if comm is not None else None, out.ptr, _stream()))
+        return out
+
+    def check_sigma_points(self):
+        """checkSigmaPoints() (Usckf.hpp:769-789, Msckf.hpp:818-838): returns (flags[B] int32, diff[B, 2])."""
+        torch = _torch()
+        flags = torch.zeros(self.B, dtype=torch.int32, device="cuda")
+        diff = DeviceArray(shape=(self.B, 2))
+        check(lib().slb_check_sigma_points(self.h, C.c_void_p(flags.data_ptr()), diff.ptr, _stream()))
+        return flags.cpu().numpy(), diff.numpy()
+
+
+class NcclComm:
+    """An ncclComm_t created through the C ABI (slb_nccl_unique_id / slb_nccl_comm_init).  `exchange(bytes_or_None)`
+    ships rank 0's 128-byte unique id to every rank (e.g. a torch.distributed broadcast)."""
+
+    def __init__(self, rank, world, exchange, device=None):
+        torch = _torch()
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(lib().slb_nccl_unique_id(ident))
+        raw = exchange(bytes(ident) if rank == 0 else None)
+        ident = (C.c_ubyte * 128).from_buffer_copy(raw)
+        self.c = C.c_void_p()
+        dev = torch.cuda.current_device() if device is None else device
+        check(lib().slb_nccl_comm_init(C.byref(self.c), world, ident, rank, dev))
+
+    def close(self):
+        if self.c:
+            lib().slb_nccl_comm_destroy(self.c)
+            self.c = C.c_void_p()
 
 
 class Ukf(Batch):
@@ -259,10 +309,12 @@ class Ukf(Batch):
         u, Q, z, R = dev(u), dev(Q), dev(z), dev(R)
         check(lib().slb_ukf_step(self.h, pm, mm, u.ptr, dt, Q.ptr, z.ptr, R.ptr, gate_dof, _stream()))
 
-    def step_host(self, pm, mm, u, dt, Q, z, R, gate_dof=0, mu_out=None):
-        """u, z, Q, R are HOST arrays (numpy or pinned torch); returns/fills the posterior means."""
-        check(lib().slb_ukf_step_host(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(z), _ptr_of(R), gate_dof,
-                                      _ptr_of(mu_out) if mu_out is not None else None, _stream()))
+    def step_host(self, pm, mm, u, dt, Q, z, R, gate_dof=0, mu_out=None, wait=True):
+        """u, z, Q, R are HOST arrays (numpy or pinned torch); returns/fills the posterior means.  wait=False is the
+        pipelined flavour (slb_ukf_step_host_async): call .wait() before touching the buffers again."""
+        fn = lib().slb_ukf_step_host if wait else lib().slb_ukf_step_host_async
+        check(fn(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(z), _ptr_of(R), gate_dof,
+                 _ptr_of(mu_out) if mu_out is not None else None, _stream()))
 
 
 class Usckf(Batch):
@@ -283,9 +335,10 @@ class Usckf(Batch):
         u, Q, z, R = dev(u), dev(Q), dev(z), dev(R)
         check(lib().slb_usckf_step(self.h, pm, mm, u.ptr, dt, Q.ptr, z.ptr, R.ptr, gate_dof, _stream()))
 
-    def step_host(self, pm, mm, u, dt, Q, z, R, gate_dof=0, mu_out=None):
-        check(lib().slb_usckf_step_host(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(z), _ptr_of(R), gate_dof,
-                                        _ptr_of(mu_out) if mu_out is not None else None, _stream()))
+    def step_host(self, pm, mm, u, dt, Q, z, R, gate_dof=0, mu_out=None, wait=True):
+        fn = lib().slb_usckf_step_host if wait else lib().slb_usckf_step_host_async
+        check(fn(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(z), _ptr_of(R), gate_dof,
+                 _ptr_of(mu_out) if mu_out is not None else None, _stream()))
 
     def cloning(self, mode):
         check(lib().slb_usckf_clone(self.h, mode, _stream()))
@@ -316,13 +369,13 @@ class Msckf(Batch):
         m = z.t.shape[1]
         check(lib().slb_msckf_update_ekf(self.h, mm, params.ptr, m, z.ptr, R.ptr, int(gate), _stream()))
 
-    def step_host(self, pm, mm, u, dt, Q, params, z, R, gate=True, mu_out=None):
+    def step_host(self, pm, mm, u, dt, Q, params, z, R, gate=True, mu_out=None, wait=True):
         """predict + update with HOST arrays (numpy or pinned torch); fills the posterior means."""
         m = z.shape[1]
         nparams = int(np.prod(params.shape))
-        check(lib().slb_msckf_step_host(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(params), nparams, m,
-                                        _ptr_of(z), _ptr_of(R), int(gate),
-                                        _ptr_of(mu_out) if mu_out is not None else None, _stream()))
+        fn = lib().slb_msckf_step_host if wait else lib().slb_msckf_step_host_async
+        check(fn(self.h, pm, mm, _ptr_of(u), dt, _ptr_of(Q), _ptr_of(params), nparams, m, _ptr_of(z), _ptr_of(R), int(gate),
+                 _ptr_of(mu_out) if mu_out is not None else None, _stream()))
 
 
 def _ptr_of(a):

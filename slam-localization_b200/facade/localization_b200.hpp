@@ -111,6 +111,28 @@ class Batch {
         check(slb_download(h_, SLB_FIELD_STATUS, s.data(), s.size(), nullptr), "slb_download(status)");
         return s;
     }
+    // Ensemble statistics (count, sum x, sum x x^T) of this batch's means, merged over an NCCL communicator when one
+    // is given (ncclComm_t as void*, see slb_gather_stats): the path's only collective, end of run.
+    Vec gatherStats(void *nccl_comm = nullptr) const {
+        DevOut out((size_t)1 + N_ + (size_t)N_ * N_);
+        check(slb_gather_stats(h_, nccl_comm, out.get(), nullptr), "slb_gather_stats");
+        Vec v;
+        out.download(v);
+        return v;
+    }
+  protected:
+    // checkSigmaPoints() (Usckf.hpp:769-789, Msckf.hpp:818-838).  The reference assert()s; a batch returns per-instance
+    // flags: bit 0 max|Pktest - Pk| > 1e-6, bit 1 the sigma-point mean moved away from mu_state, bit 2 LLT failed.
+    std::vector<int32_t> checkSigmaPointsImpl() const {
+        void *fl = nullptr;
+        check(slb_dev_alloc((size_t)B_ * sizeof(int32_t), &fl), "slb_dev_alloc");
+        const int rc = slb_check_sigma_points(h_, static_cast<int32_t *>(fl), nullptr, nullptr);
+        std::vector<int32_t> out(B_);
+        if (rc == SLB_OK) slb_dev_copy(out.data(), fl, (size_t)B_ * sizeof(int32_t), 2, nullptr);
+        slb_dev_free(fl);
+        check(rc, "slb_check_sigma_points");
+        return out;
+    }
 };
 
 // ---- ukfom::ukf<state>: ukf(mu, sigma), predict(g, R), update(z, h, Q[, mt]), mu(), sigma() ---------
@@ -218,6 +240,7 @@ class Usckf : public Batch {
         setPk(P);
     }
     Vec PkAugmentedState() const { return Pk(); }
+    std::vector<int32_t> checkSigmaPoints() const { return checkSigmaPointsImpl(); }               // Usckf.hpp:769-789
 };
 
 // ---- localization::Msckf ----------------------------------------------------------------------------
@@ -252,6 +275,22 @@ class Msckf : public Batch {
         return out;
     }
     Vec getPk() const { return Pk(); }                                                    // Msckf.hpp:386
+    std::vector<int32_t> checkSigmaPoints() const { return checkSigmaPointsImpl(); }      // Msckf.hpp:818-838
+    // muSingleState(state) (Msckf.hpp:351-354): mu_state.statek = state; batch x 13
+    void muSingleState(const Vec &state) {
+        Vec mu = muState();
+        for (int b = 0; b < B_; ++b)
+            for (int c = 0; c < 13; ++c) mu[(size_t)b * QD_ + c] = state[(size_t)b * 13 + c];
+        setMu(mu);
+    }
+    // setPkSingleState(Pk_i) (Msckf.hpp:363-366): Pk.block(0, 0, 12, 12) = Pk_i; batch x 12 x 12
+    void setPkSingleState(const Vec &Pk_i) {
+        Vec P = Pk();
+        for (int b = 0; b < B_; ++b)
+            for (int r = 0; r < 12; ++r)
+                for (int c = 0; c < 12; ++c) P[(size_t)b * N_ * N_ + r * N_ + c] = Pk_i[(size_t)b * 144 + r * 12 + c];
+        setPk(P);
+    }
     Vec muSingleState() const {                                                           // Msckf.hpp:356
         const Vec mu = muState();
         Vec out((size_t)B_ * 13);

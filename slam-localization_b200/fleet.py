@@ -36,6 +36,18 @@ def merge_stats(stats, group=None):
     return stats
 
 
+def make_nccl_comm(engine, rank, world):
+    """An NCCL communicator for the C-level gather (slb_gather_stats): rank 0's unique id travels through the
+    already-initialised torch.distributed group (any backend), every rank then joins through the C ABI."""
+    import torch.distributed as dist
+
+    def exchange(raw):
+        box = [raw]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return engine.NcclComm(rank, world, exchange)
+
+
 def moments(stats, n):
     """Ensemble mean and covariance from merged (count, sum x, sum x x^T)."""
     s = np.asarray(stats, dtype=np.float64)

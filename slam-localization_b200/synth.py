@@ -84,6 +84,73 @@ def ukfom_inputs(B, step, seed=0, r_sigma=1e-2, truth_pos=None):
     return u, z
 
 
+def _qmul(a, b):
+    w = a[:, 0] * b[:, 0] - a[:, 1] * b[:, 1] - a[:, 2] * b[:, 2] - a[:, 3] * b[:, 3]
+    x = a[:, 0] * b[:, 1] + a[:, 1] * b[:, 0] + a[:, 2] * b[:, 3] - a[:, 3] * b[:, 2]
+    y = a[:, 0] * b[:, 2] + a[:, 2] * b[:, 0] + a[:, 3] * b[:, 1] - a[:, 1] * b[:, 3]
+    z = a[:, 0] * b[:, 3] + a[:, 3] * b[:, 0] + a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    return np.stack([w, x, y, z], axis=1)
+
+
+def _qexp(v):
+    th = np.linalg.norm(v, axis=1, keepdims=True)
+    s = np.where(th > 1e-12, np.sin(th / 2) / np.maximum(th, 1e-300), 0.5)
+    return np.concatenate([np.cos(th / 2), s * v], axis=1)
+
+
+def _qrot(q, v, inverse=False):
+    w, u = q[:, 0:1], (-q[:, 1:4] if inverse else q[:, 1:4])
+    t = 2.0 * np.cross(u, v)
+    return v + w * t + np.cross(u, t)
+
+
+class UkfomTruthRun:
+    """A well-posed long replay for the UKFoM layout (pos, SO3, vel): B simulated vehicles fly a bounded Lissajous
+    trajectory; each step yields the IMU sample u = (body acceleration, body rate) that drives the truth through the
+    very process model the filter uses (test/UKFoMUnitTest.cpp:45-70: vel += (R(q) a + (0,0,9.81)) dt, so a carries
+    the -9.81 that cancels it) plus sensor noise, and a GPS fix z = true position + noise.  The state is observable and
+    bounded, so an estimator's rounding differences contract instead of growing -- unlike a replay whose measurements
+    are drawn around the estimator's own mean, whose position runs away with the uncompensated 9.81 term and which is
+    exponentially sensitive to 1e-15 perturbations (measured: two runs of the same CPU oracle differing by 1e-15 at
+    step 0 are 5e-4 apart after 10k such steps)."""
+
+    def __init__(self, B, seed=0, dt=0.01, r_sigma=1e-2, acc_sigma=2e-2, gyro_sigma=2e-3):
+        self.B, self.dt, self.k = B, dt, 0
+        self.rng = np.random.default_rng([seed, 777])
+        self.r_sigma, self.acc_sigma, self.gyro_sigma = r_sigma, acc_sigma, gyro_sigma
+        self.p = self.rng.normal(size=(B, 3))
+        self.q = random_unit_quat(self.rng, B, max_angle=0.5)
+        self.v = 0.3 * self.rng.normal(size=(B, 3))
+        self.amp = 1.0 + self.rng.uniform(size=(B, 3))           # world-frame acceleration amplitudes, m/s^2
+        self.om = 0.5 + 1.5 * self.rng.uniform(size=(B, 3))      # rad/s
+        self.ph = 2 * np.pi * self.rng.uniform(size=(B, 3))
+        self.wamp = 0.3 * self.rng.normal(size=(B, 3))           # body-rate amplitudes, rad/s
+
+    def initial(self, p_scale=1e-4):
+        """Prior mean = truth + a draw from the prior covariance p_scale * I."""
+        sd = np.sqrt(p_scale)
+        mu = np.concatenate([self.p + sd * self.rng.normal(size=(self.B, 3)),
+                             _qmul(self.q, _qexp(sd * self.rng.normal(size=(self.B, 3)))),
+                             self.v + sd * self.rng.normal(size=(self.B, 3))], axis=1)
+        return mu, np.tile(p_scale * np.eye(9), (self.B, 1, 1))
+
+    def step(self):
+        t = self.k * self.dt
+        a_w = self.amp * np.sin(self.om * t + self.ph) - 0.05 * self.p - 0.2 * self.v   # bounded: weak spring + damper
+        a_b = _qrot(self.q, a_w - np.array([0.0, 0.0, 9.81]), inverse=True)
+        w_b = self.wamp * np.cos(0.7 * self.om * t + self.ph)
+        # truth through the filter's own process model (old orientation rotates a, old velocity moves pos)
+        p = self.p + self.v * self.dt
+        v = self.v + (_qrot(self.q, a_b) + np.array([0.0, 0.0, 9.81])) * self.dt
+        q = _qmul(self.q, _qexp(w_b * self.dt))
+        self.p, self.v, self.q = p, v, q / np.linalg.norm(q, axis=1, keepdims=True)
+        self.k += 1
+        u = np.concatenate([a_b + self.acc_sigma * self.rng.normal(size=(self.B, 3)),
+                            w_b + self.gyro_sigma * self.rng.normal(size=(self.B, 3))], axis=1)
+        z = self.p + self.r_sigma * self.rng.normal(size=(self.B, 3))
+        return u, z
+
+
 # ---- configs 1 / 4: USCKF (test/UsckfUnitTest.cpp) -----------------------------------------------
 def usckf_process_noise(dt):
     """processNoiseCov(dt), test/UsckfUnitTest.cpp:51-60."""

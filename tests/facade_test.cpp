@@ -75,6 +75,7 @@ int main() {
             print("usckf_mu", filter.muState(), 51);
             Vec z = {2.33, 3.35, 3.35}, R(9, 0.0);
             for (int i = 0; i < 3; ++i) R[i * 3 + i] = 0.01;
+            std::printf("usckf_check %d\n", filter.checkSigmaPoints()[0]);   // indefinite ctor-#2 covariance: LLT fails (bit 2)
             filter.update(z, SLB_MM_USCKF_VO, R);
             std::printf("usckf_status %d\n", filter.status()[0]);
         }
@@ -93,6 +94,17 @@ int main() {
             for (int i = 0; i < 2; ++i) filter.predict(SLB_PM_MSCKF_DELTAPOSE, u, 0.0, Q);
             print("msckf_mu", filter.muSingleState(), 13);
             print("msckf_P", filter.getPkSingleState(), 144);
+            // checkSigmaPoints (Msckf.hpp:818-838), the setters muSingleState(state) / setPkSingleState (:351,:363) and the
+            // (single-GPU, communicator-less) ensemble-statistics gather
+            std::printf("msckf_check %d\n", filter.checkSigmaPoints()[0]);
+            Vec st13 = filter.muSingleState(), P12 = filter.getPkSingleState();
+            st13[0] += 1.0;
+            for (int i = 0; i < 12; ++i) P12[i * 12 + i] *= 2.0;
+            filter.muSingleState(st13);
+            filter.setPkSingleState(P12);
+            print("msckf_mu_set", filter.muSingleState(), 13);
+            print("msckf_P_set", filter.getPkSingleState(), 144);
+            print("msckf_stats", filter.gatherStats(), 4);
         }
         {   // SURVEY 8f rows f2 / f4 through the facade: one error-state EKF cycle, one dead-reckoning step
             Vec state(48, 0.0), error(45, 0.0), P0(45 * 45, 0.0), F(225, 0.0), Q(225, 0.0), H(3 * 45, 0.0), R(9, 0.0);

@@ -83,6 +83,13 @@ def test_facade_replays_reference_tests(slo):
         m, Pm, st = slo.msckf_predict(slo.PM_MSCKF_DELTAPOSE, k, m, Pm, u, 0.0, 0.01 * np.eye(12))
     parity.assert_parity(slo, synth.STATE_BLOCKS, v("msckf_mu")[None], v("msckf_P").reshape(1, 12, 12), m[:, :13],
                          parity.symmetrize_lower(Pm)[:, :12, :12])
+    assert int(out["msckf_check"][0][0]) == 0           # checkSigmaPoints: Pktest == Pk, mean unmoved
+    assert int(out["usckf_check"][0][0]) == 4           # ... and the LLT failure of the indefinite ctor-#2 covariance
+    np.testing.assert_array_equal(v("msckf_mu_set"), v("msckf_mu") + np.r_[1.0, np.zeros(12)])
+    Pset = v("msckf_P").reshape(12, 12).copy()
+    Pset[np.diag_indices(12)] *= 2.0
+    np.testing.assert_array_equal(v("msckf_P_set").reshape(12, 12), Pset)
+    np.testing.assert_allclose(v("msckf_stats")[:2], [1.0, v("msckf_mu_set")[0]], rtol=1e-15)   # count, sum of pos.x
     # SURVEY 8f rows f2 / f4 through the facade
     state = np.zeros((1, 48))
     state[0, [6, 22, 38]] = 1.0

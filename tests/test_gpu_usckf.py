@@ -24,7 +24,7 @@ def _oracle_update(slo, sc, mu, P, gate=0):
                           gate_dof=gate, predict=False, nthreads=8)
 
 
-@pytest.mark.parametrize("nk,nl", [(3, 9), (3, 0)])
+@pytest.mark.parametrize("nk,nl", [(3, 9), (3, 0), (3, 3), (3, 6), (6, 0), (6, 3), (6, 6), (9, 0), (9, 3)])
 def test_usckf_predict_then_update_parity(slo, nk, nl):
     B = 203                                       # ragged against the 4- and 8-warp CTAs
     sc = synth.usckf_scenario(B, seed=41, nk=nk, nl=nl)
@@ -176,26 +176,89 @@ def test_usckf_sliding_window_sequence(slo):
     parity.assert_parity(slo, AUG, f.mu(), f.P(), mo, parity.symmetrize_lower(Po), nfeat=12, tol=parity.LONG_TOL)
 
 
-def test_usckf_fleet_properties():
-    """Fleet-size run (65,536 instances here; config 4 shards 4M of these over 8 GPUs): instance i of the
-    fleet equals instance i run alone, bit for bit (no cross-instance arithmetic => results independent of
-    the sharding), covariances stay PSD, no status flags."""
-    B = 65536
-    sc = synth.usckf_scenario(2048, seed=49)
-    rep = B // 2048
-    tile = lambda x: np.tile(x, (rep,) + (1,) * (x.ndim - 1))
+@pytest.mark.parametrize("nk,nl", [(3, 6), (6, 6), (9, 3)])
+def test_usckf_fused_step_other_shapes(slo, nk, nl):
+    """The fused predict+update launch for feature sizes other than the bench's (3, 9), with the m-dof gate on."""
+    B = 77
+    sc = synth.usckf_scenario(B, seed=141, nk=nk, nl=nl)
+    sc["z"][:4] += 50.0
+    f = engine.Usckf(B, nk=nk, nl=nl)
+    f.set_state(sc["mu"], sc["P"])
+    f.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"], gate_dof=nk)
+    mu2, P2, st2, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, nk, nl, sc["mu"], sc["P"], sc["u"], sc["dt"], sc["Q"],
+                                     sc["z"], sc["R"], gate_dof=nk, nthreads=8)
+    st = f.status()
+    assert np.all(st[:4] & engine.ST_GATE_REJECT)
+    np.testing.assert_array_equal(st, st2)                 # the same instances pass / fail the m-dof gate as in the oracle
+    # a gated instance keeps its predicted state (predict ran, update did not), an accepted one is fully updated
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mu2, parity.symmetrize_lower(P2), nfeat=nk + nl)
+    f2 = engine.Usckf(B, nk=nk, nl=nl)                     # and without the gate every instance is updated
+    f2.set_state(sc["mu"], sc["P"])
+    f2.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"])
+    mu3, P3, st3, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, nk, nl, sc["mu"], sc["P"], sc["u"], sc["dt"], sc["Q"],
+                                     sc["z"], sc["R"], nthreads=8)
+    assert not f2.status().any() and not st3.any()
+    parity.assert_parity(slo, AUG, f2.mu(), f2.P(), mu3, parity.symmetrize_lower(P3), nfeat=nk + nl)
+
+
+def test_usckf_create_rejects_shapes_the_update_is_not_built_for():
+    """slb_create and the update agree on what exists (a batch must not be creatable if update cannot run)."""
+    for nk, nl in [(3, 12), (4, 0), (0, 9), (12, 0), (6, 9)]:
+        with pytest.raises(engine.SlbError, match="USCKF batches are built for"):
+            engine.Usckf(8, nk=nk, nl=nl)
+
+
+@pytest.mark.parametrize("theta", [3.0, np.pi - 1e-6])
+def test_usckf_update_with_sigma_rotations_near_pi(slo, theta):
+    """Quirk Q10 (State.hpp:595-634, Usckf.hpp:731-732): the reference carries sigma-point deltas through an exp/log round
+    trip (set / getVectorizedState), which is the identity for |delta theta| < pi and wraps beyond.  The engine uses
+    X_j [-] mu = +-L e_j directly, i.e. it matches the reference for every column rotation below pi -- tested here with
+    statek's orientation variance set so that L(3,3) = theta exactly (row / column 3 decoupled), which also drives
+    so3_exp / so3_log through their large-angle (libm) paths.  Rotations >= pi are not matched (the reference's wrapped
+    deviation has the opposite sign); a covariance with a 180-degree standard deviation carries no information anyway."""
+    B = 16
+    sc = synth.usckf_scenario(B, seed=151)
+    P = sc["P"].copy()
+    P[:, 3, :] = 0.0
+    P[:, :, 3] = 0.0
+    P[:, 3, 3] = theta * theta
     f = engine.Usckf(B)
-    f.set_state(tile(sc["mu"]), tile(sc["P"]))
-    f.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, tile(sc["u"]), sc["dt"], sc["Q"], tile(sc["z"]), sc["R"])
+    f.set_state(sc["mu"], P)
+    f.update(engine.MM_USCKF_VO, sc["z"], sc["R"])
+    mu2, P2, st2, _ = _oracle_update(slo, sc, sc["mu"], P)
+    assert not st2.any() and not f.status().any()
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), mu2, parity.symmetrize_lower(P2), nfeat=12)
+
+
+def test_usckf_fleet_full_size_oracle_parity(slo):
+    """BASELINE configs[3] at its per-GPU size: 524,288 instances, one fused step.  The first 65,536 instances (2048
+    seeded priors replicated, per-instance u / z) are compared with the oracle one by one (<= 1e-9); beyond the sample
+    the fleet repeats it (inputs tiled), so every instance must equal its image in the sample bit for bit (no
+    cross-instance arithmetic => results independent of batch size and sharding); covariances PSD, no status flags."""
+    B, S, npri = 524288, 65536, 2048
+    sc = synth.usckf_scenario(npri, seed=49)
+    rng = np.random.default_rng(50)
+    tile = lambda x, n: np.tile(x, (n // x.shape[0],) + (1,) * (x.ndim - 1))
+    u = tile(sc["u"], S) + 0.05 * rng.normal(size=(S, 6))
+    z = tile(sc["z"], S) + 0.05 * rng.normal(size=(S, 3))
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], sc["P"], replicate=True)
+    f.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, tile(u, B), sc["dt"], sc["Q"], tile(z, B), sc["R"])
     assert sum(f.status_counts()) == 0
-    mu, P = f.mu(), f.P()
-    g = engine.Usckf(2048)
-    g.set_state(sc["mu"], sc["P"])
-    g.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, sc["u"], sc["dt"], sc["Q"], sc["z"], sc["R"])
-    for r in (0, 7, rep - 1):
-        np.testing.assert_array_equal(mu[r * 2048:(r + 1) * 2048], g.mu())
-        np.testing.assert_array_equal(P[r * 2048:(r + 1) * 2048], g.P())
+    mu = f.mu()
+    P = f.P(first=S)
+    mu_r, P_r, st_r, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, 3, 9, tile(sc["mu"], S), tile(sc["P"], S), u, sc["dt"],
+                                        sc["Q"], z, sc["R"], nthreads=16)
+    assert not st_r.any()
+    parity.assert_parity(slo, AUG, mu[:S], P, mu_r, parity.symmetrize_lower(P_r), nfeat=12)
+    for r in (1, 3, B // S - 1):
+        np.testing.assert_array_equal(mu[r * S:(r + 1) * S], mu[:S])
     assert np.linalg.eigvalsh(P[::511]).min() > 0
+    g = engine.Usckf(npri)
+    g.set_state(sc["mu"], sc["P"])
+    g.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u[:npri], sc["dt"], sc["Q"], z[:npri], sc["R"])
+    np.testing.assert_array_equal(mu[:npri], g.mu())
+    np.testing.assert_array_equal(P[:npri], g.P())
 
 
 def test_usckf_step_host_chunked_pipeline_is_bitwise_the_device_path():
@@ -271,3 +334,92 @@ def test_usckf_config1_10k_steps_free_running(slo):
     P = f.P()
     parity.assert_parity(slo, AUG, f.mu(), P, mo, parity.symmetrize_lower(Po), nfeat=12, tol=parity.LONG_TOL)
     assert np.linalg.eigvalsh(P).min() > -1e-12 * np.abs(P).max()
+
+
+def test_usckf_step_host_async_pipeline_equals_synchronous_steps():
+    """slb_usckf_step_host_async x3 + slb_wait == three synchronous slb_usckf_step_host calls, bit for bit
+    (pinned buffers: zero-copy path; the posterior means of every step land in their own host buffer)."""
+    import torch
+    B, npri = 6000, 300
+    sc = synth.usckf_scenario(npri, seed=81)
+    rep = -(-B // npri)
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    rng = np.random.default_rng(82)
+    us = [pin(np.tile(sc["u"], (rep, 1))[:B] + 0.01 * rng.normal(size=(B, 6))) for _ in range(3)]
+    zs = [pin(np.tile(sc["z"], (rep, 1))[:B] + 0.01 * rng.normal(size=(B, 3))) for _ in range(3)]
+    hQ, hR = pin(sc["Q"]), pin(sc["R"])
+    a, b = engine.Usckf(B), engine.Usckf(B)
+    for f in (a, b):
+        f.set_state(sc["mu"], sc["P"], replicate=True)
+    outs_a = [torch.empty((B, 51), dtype=torch.float64).pin_memory() for _ in range(3)]
+    outs_b = [torch.empty((B, 51), dtype=torch.float64).pin_memory() for _ in range(3)]
+    for k in range(3):
+        a.step_host(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, us[k], sc["dt"], hQ, zs[k], hR, mu_out=outs_a[k])
+    for k in range(3):
+        b.step_host(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, us[k], sc["dt"], hQ, zs[k], hR, mu_out=outs_b[k], wait=False)
+    b.wait()
+    for k in range(3):
+        np.testing.assert_array_equal(outs_a[k].numpy(), outs_b[k].numpy())
+    np.testing.assert_array_equal(a.P(first=256), b.P(first=256))
+    assert not np.array_equal(outs_a[0].numpy(), outs_a[2].numpy())
+
+
+def test_two_handles_on_two_devices_in_one_thread(slo):
+    """every entry point runs on its handle's device and restores the caller's current device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    B = 64
+    sc = synth.usckf_scenario(B, seed=83)
+    torch.cuda.set_device(0)
+    f0 = engine.Usckf(B, device=0)
+    f1 = engine.Usckf(B, device=1)
+    assert torch.cuda.current_device() == 0           # slb_create left the current device alone
+    with torch.cuda.device(1):
+        u1, z1, Q1, R1 = (engine.DeviceArray(sc[k]) for k in ("u", "z", "Q", "R"))
+    u0, z0, Q0, R0 = (engine.DeviceArray(sc[k]) for k in ("u", "z", "Q", "R"))
+    for f in (f0, f1):
+        f.set_state(sc["mu"], sc["P"])
+    # handle on device 1 driven while device 0 is current (NULL stream of the handle's device)
+    import ctypes as C
+    L = engine.lib()
+    engine.check(L.slb_usckf_step(f1.h, engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u1.ptr, sc["dt"], Q1.ptr, z1.ptr, R1.ptr, 0, None))
+    engine.check(L.slb_wait(f1.h, None))
+    f0.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u0, sc["dt"], Q0, z0, R0)
+    assert torch.cuda.current_device() == 0
+    out = np.empty((B, 51))
+    engine.check(L.slb_download(f1.h, engine.FIELD_MU, out.ctypes.data_as(C.c_void_p), out.size, None))
+    np.testing.assert_array_equal(out, f0.mu())
+    assert sum(f0.status_counts()) == 0
+
+
+def test_check_sigma_points_usckf_and_msckf(slo):
+    """checkSigmaPoints() (Usckf.hpp:769-789, Msckf.hpp:818-838) per instance against the oracle's restatement: the
+    regenerated sigma points reproduce (mu, Pk) for healthy instances (flags 0, |Pktest - Pk| ~ 1e-18), an indefinite
+    covariance is reported as an LLT failure, and a column rotation beyond pi (quirk Q10: the [+] / [-] round trip
+    wraps) is reported as a covariance mismatch -- the case the reference's assert exists for."""
+    B = 40
+    sc = synth.usckf_scenario(B, seed=161)
+    P = sc["P"].copy()
+    P[3, 20, 20] = -1.0
+    P[7, 3, :] = 0.0
+    P[7, :, 3] = 0.0
+    P[7, 3, 3] = 3.3 ** 2                                   # sigma rotation of 3.3 rad > pi about statek's x axis
+    f = engine.Usckf(B)
+    f.set_state(sc["mu"], P)
+    fl, diff = f.check_sigma_points()
+    fl_o, diff_o = slo.check_sigma_points(2, sc["mu"], P, nk=3, nl=9, nthreads=4)
+    np.testing.assert_array_equal(fl, fl_o)
+    assert fl[3] == 4 and (fl[7] & 1) and not np.delete(fl, [3, 7]).any()
+    np.testing.assert_allclose(diff[7, 0], diff_o[7, 0], rtol=1e-9)
+    assert diff[fl == 0].max() < 1e-12 and diff_o[fl_o == 0].max() < 1e-12
+    k = 6
+    sm = synth.msckf_scenario(B, seed=162, k=k, nfeat=8)
+    g = engine.Msckf(B, nclones=k)
+    g.set_state(sm["mu"], sm["P"])
+    fl, diff = g.check_sigma_points()
+    fl_o, diff_o = slo.check_sigma_points(3, sm["mu"], sm["P"], k=k, nthreads=4)
+    np.testing.assert_array_equal(fl, fl_o)
+    assert not fl.any() and diff.max() < 1e-12
+    with pytest.raises(engine.SlbError, match="Usckf / Msckf batches only"):
+        engine.Ukf(8).check_sigma_points()
