@@ -151,6 +151,11 @@ int slb_ukf_step_host(slb_handle h, int pm, int mm, const double *u_host, double
                       const double *Q_host, const double *z_host, const double *R_host,
                       int gate_dof, double *mu_out_host, void *stream);
 
+/* Which part of the posterior q-vector the *_step_host entry points copy back: scalars [offset, offset +
+ * count) of every instance, mu_out_host being batch x count.  Default: the whole q-vector (muState(),
+ * Usckf.hpp:518).  (26, 13) on a USCKF batch is statek_i, what Usckf::muSingleState() returns by default
+ * (Usckf.hpp:457-478); (0, 13) on an MSCKF batch is Msckf::muSingleState() (Msckf.hpp:356). */
+int slb_set_output_slice(slb_handle h, int offset, int count);
 /* Pipelined flavour: identical, but returns as soon as the step is enqueued on `stream` (no
  * synchronisation), so consecutive steps overlap their host<->device traffic with each other's
  * kernels.  The host buffers must stay valid (and mu_out_host unread) until slb_wait(h, stream);

@@ -34,11 +34,11 @@ __global__ void aos_to_soa_mu(const double *aos, double *soa, int B0, int cnt, i
     const int i = t / QD, c = t - i * QD;
     soa[(size_t)c * stride + B0 + i] = aos[t];
 }
-__global__ void soa_to_aos_mu(const double *soa, double *aos, int B0, int cnt, int QD, int stride) {
+__global__ void soa_to_aos_mu(const double *soa, double *aos, int B0, int cnt, int QD, int stride, int off = 0) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt * QD) return;
     const int i = t / QD, c = t - i * QD;
-    aos[t] = soa[(size_t)c * stride + B0 + i];
+    aos[t] = soa[(size_t)(off + c) * stride + B0 + i];
 }
 __global__ void dense_to_soa_P(const double *dense, double *soa, int B0, int cnt, int N, int stride) {
     const int NP = N * (N + 1) / 2;
@@ -66,11 +66,11 @@ __global__ void aos_to_rec_mu(const double *aos, double *rec, int B0, int cnt, i
     const int i = t / QD, c = t - i * QD;
     rec[(size_t)(B0 + i) * qstride + c] = aos[t];
 }
-__global__ void rec_to_aos_mu(const double *rec, double *aos, int B0, int cnt, int QD, int qstride) {
+__global__ void rec_to_aos_mu(const double *rec, double *aos, int B0, int cnt, int QD, int qstride, int off = 0) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt * QD) return;
     const int i = t / QD, c = t - i * QD;
-    aos[t] = rec[(size_t)(B0 + i) * qstride + c];
+    aos[t] = rec[(size_t)(B0 + i) * qstride + off + c];
 }
 __global__ void dense_to_rec_P(const double *dense, double *rec, int B0, int cnt, int N, int pstride) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +208,7 @@ static FilterArgs make_args(slb_handle h) {
     a.B = h->B; a.stride = h->stride; a.pstride = h->pstride; a.qstride = h->qstride;
     a.nk = h->cfg.nk; a.nl = h->cfg.nl; a.k = h->cfg.nclones;
     a.misc = h->misc_dev;
+    a.out_off = h->out_off; a.out_len = h->out_len;
     return a;
 }
 
@@ -274,6 +275,8 @@ int slb_create(const slb_config *cfg, slb_handle *out) {
             return set_error(SLB_ERR_INVALID, "slb_create: unknown kind");
     }
     h->NP = h->N * (h->N + 1) / 2;
+    h->out_off = 0;
+    h->out_len = h->QD;
     h->stride = (h->B + 31) / 32 * 32;
     h->pstride = (h->NP + 15) / 16 * 16;
     h->qstride = (h->QD + 1) / 2 * 2;
@@ -329,6 +332,13 @@ int slb_destroy(slb_handle h) {
     return SLB_OK;
 }
 
+int slb_set_output_slice(slb_handle h, int offset, int count) {
+    if (!h || offset < 0 || count < 1 || offset + count > h->QD)
+        return set_error(SLB_ERR_INVALID, "slb_set_output_slice: the slice must lie inside the q-vector");
+    h->out_off = offset;
+    h->out_len = count;
+    return SLB_OK;
+}
 int slb_dof(slb_handle h) { return h ? h->N : SLB_ERR_INVALID; }
 int slb_qdim(slb_handle h) { return h ? h->QD : SLB_ERR_INVALID; }
 
@@ -513,13 +523,13 @@ static int step_host_enqueue(slb_handle h, const HostStep &hs, cudaStream_t s) {
         const int rc = launch_chunk(h, hs, b0, cnt, du + (size_t)b0 * hs.nu, dz + (size_t)b0 * hs.m, dQ, dp, dR, st);
         if (rc != SLB_OK) return rc;
         if (hs.mu_out) {
-            const int work = cnt * h->QD, tpb = 256;
-            double *dst = dmu + (size_t)b0 * h->QD;
-            if (soa) soa_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, st>>>(h->mu, dst, b0, cnt, h->QD, h->stride);
-            else rec_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, st>>>(h->mu, dst, b0, cnt, h->QD, h->qstride);
+            const int OL = h->out_len, work = cnt * OL, tpb = 256;
+            double *dst = dmu + (size_t)b0 * OL;
+            if (soa) soa_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, st>>>(h->mu, dst, b0, cnt, OL, h->stride, h->out_off);
+            else rec_to_aos_mu<<<(work + tpb - 1) / tpb, tpb, 0, st>>>(h->mu, dst, b0, cnt, OL, h->qstride, h->out_off);
             count_launch();
             SLB_CUDA(cudaGetLastError());
-            SLB_CUDA(cudaMemcpyAsync(hs.mu_out + (size_t)b0 * h->QD, dst, (size_t)cnt * h->QD * 8, cudaMemcpyDeviceToHost, st));
+            SLB_CUDA(cudaMemcpyAsync(hs.mu_out + (size_t)b0 * OL, dst, (size_t)cnt * OL * 8, cudaMemcpyDeviceToHost, st));
         }
     }
     for (int i = 0; i < used; ++i) {
@@ -590,7 +600,7 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream, bool wait =
         if (wait) SLB_CUDA(cudaStreamSynchronize(s));
         return SLB_OK;
     }
-    const int ki[8] = {hs.pm, hs.mm, hs.nu, hs.m, hs.nq, hs.nparams, hs.gate, 0};
+    const int ki[8] = {hs.pm, hs.mm, hs.nu, hs.m, hs.nq, hs.nparams, hs.gate, h->out_off * 4096 + h->out_len};
     const void *kp[6] = {hs.u, hs.Q, hs.params, hs.z, hs.R, hs.mu_out};
     bool same = h->step_exec != nullptr && h->step_key_dt == hs.dt;
     for (int i = 0; i < 8 && same; ++i) same = h->step_key_i[i] == ki[i];

@@ -36,6 +36,7 @@ struct slb_batch_s {
     double step_key_dt;
     const void *step_key_p[6];
     cudaEvent_t ev_start, ev_done[SLB_NXS];
+    int out_off, out_len;      // slb_set_output_slice: part of the q-vector the *_step_host entry points copy back
 };
 
 namespace slb {
@@ -82,7 +83,8 @@ struct FilterArgs {
     int nk, nl, k;
     int32_t *misc;
     int prefetch;     // USCKF step: L2-prefetch the record of instance (i + prefetch); 0 = off
-    double *mu_out;   // optional instance-major copy of the posterior means (may be mapped host memory), B x QD
+    double *mu_out;   // optional instance-major copy of the posterior means (may be mapped host memory), B x out_len
+    int out_off, out_len;  // the slice [out_off, out_off + out_len) of the q-vector that goes to mu_out
 };
 
 // slb_ukf.cu

@@ -488,12 +488,14 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
     // Optional instance-major copy of the posterior means (the *_step_host entry points pass mapped host memory here:
     // the warp's 8 q-vectors are 640 contiguous bytes, written with full-width coalesced stores straight over PCIe).
     if (a.mu_out) {
-        for (int e = lane; e < IPW * QD; e += 32) {
-            const int li = e / QD, c = e - li * QD;
+        const int OL = a.out_len;
+        for (int e = lane; e < IPW * OL; e += 32) {
+            const int li = e / OL, c = a.out_off + (e - li * OL);
             if (wbase + li < a.B) {
                 const double *src = wsm + li * R::IS;
                 // a failed instance keeps its prior, which is what the state arrays still hold
-                a.mu_out[(size_t)(wbase + li) * QD + c] = src[R::FLAG] != 0.0 ? src[R::MU + c] : a.mu[(size_t)c * a.stride + wbase + li];
+                a.mu_out[(size_t)(wbase + li) * OL + (c - a.out_off)] =
+                    src[R::FLAG] != 0.0 ? src[R::MU + c] : a.mu[(size_t)c * a.stride + wbase + li];
             }
         }
     }

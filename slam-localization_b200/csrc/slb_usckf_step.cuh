@@ -701,7 +701,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_step_kernel(slb::FilterA
     // the step decided (accepted, gated, factorisation failed) the resident record holds the posterior
     if (a.mu_out) {
         __syncwarp();
-        for (int e = lane; e < C::QD; e += 32) a.mu_out[(size_t)inst * C::QD + e] = mus[e];
+        for (int e = lane; e < a.out_len; e += 32) a.mu_out[(size_t)inst * a.out_len + e] = mus[a.out_off + e];
     }
     if (st && lane == 0) a.status[inst] |= st;
     if (dirty && lane == 0) bulk_store_wait();

@@ -32,7 +32,7 @@ EXPORTS = [
     "slb_msckf_step_host", "slb_ekf_predict", "slb_ekf_update", "slb_ekf_single_update", "slb_ekf_clone",
     "slb_datamodel_safe_fuse", "slb_msckf_update_ekf", "slb_transform_compose", "slb_deadreckon_update_pose",
     "slb_ukf_step_host_async", "slb_usckf_step_host_async", "slb_msckf_step_host_async", "slb_wait",
-    "slb_check_sigma_points", "slb_gather_stats", "slb_nccl_unique_id", "slb_nccl_comm_init", "slb_nccl_comm_destroy",
+    "slb_set_output_slice", "slb_check_sigma_points", "slb_gather_stats", "slb_nccl_unique_id", "slb_nccl_comm_init", "slb_nccl_comm_destroy",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
         L.slb_ukf_step_host_async.argtypes = L.slb_ukf_step_host.argtypes
         L.slb_usckf_step_host_async.argtypes = L.slb_usckf_step_host.argtypes
         L.slb_wait.argtypes = [vp, vp]
+        L.slb_set_output_slice.argtypes = [vp, i32, i32]
         L.slb_check_sigma_points.argtypes = [vp, vp, vp, vp]
         L.slb_gather_stats.argtypes = [vp, vp, dp, vp]
         L.slb_nccl_unique_id.argtypes = [vp]
@@ -242,6 +243,10 @@ class Batch:
         c = (C.c_int64 * NSTATUS)()
         check(lib().slb_status_ex(self.h, c, NSTATUS, _stream()))
         return list(c)
+
+    def set_output_slice(self, offset, count):
+        """Part of the posterior q-vector step_host copies back (default: all); e.g. (26, 13) = statek_i of a USCKF."""
+        check(lib().slb_set_output_slice(self.h, offset, count))
 
     def wait(self):
         """Completes the steps enqueued with step_host(..., wait=False) on the current stream."""

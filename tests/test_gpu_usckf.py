@@ -423,3 +423,29 @@ def test_check_sigma_points_usckf_and_msckf(slo):
     assert not fl.any() and diff.max() < 1e-12
     with pytest.raises(engine.SlbError, match="Usckf / Msckf batches only"):
         engine.Ukf(8).check_sigma_points()
+
+
+def test_usckf_step_host_output_slice_returns_statek_i():
+    """slb_set_output_slice(26, 13): the host step copies back statek_i only (Usckf::muSingleState()), on the zero-copy
+    path (pinned buffers) and on the chunked copy pipeline (pageable buffers) alike."""
+    import torch
+    B, npri = 9000, 300
+    sc = synth.usckf_scenario(npri, seed=171)
+    rep = -(-B // npri)
+    u, z = np.tile(sc["u"], (rep, 1))[:B].copy(), np.tile(sc["z"], (rep, 1))[:B].copy()
+    a, b, c = engine.Usckf(B), engine.Usckf(B), engine.Usckf(B)
+    for f in (a, b, c):
+        f.set_state(sc["mu"], sc["P"], replicate=True)
+    a.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u, sc["dt"], sc["Q"], z, sc["R"])
+    want = a.mu()[:, 26:39]
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    hout = torch.empty((B, 13), dtype=torch.float64).pin_memory()
+    b.set_output_slice(26, 13)
+    b.step_host(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, pin(u), sc["dt"], pin(sc["Q"]), pin(z), pin(sc["R"]), mu_out=hout)
+    np.testing.assert_array_equal(hout.numpy(), want)
+    out = np.empty((B, 13))
+    c.set_output_slice(26, 13)
+    c.step_host(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, u, sc["dt"], sc["Q"], z, sc["R"], mu_out=out)
+    np.testing.assert_array_equal(out, want)
+    with pytest.raises(engine.SlbError):
+        c.set_output_slice(40, 13)
