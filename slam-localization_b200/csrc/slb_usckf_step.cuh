@@ -43,17 +43,18 @@ struct StepCfg {
     static constexpr int NGRP = (NPAN + 3) / 4;        // sigma-point passes (16 columns = 32 points each)
     // A finished panel (NPAD rows x 4 columns) is stored as two planes of column PAIRS, element (i, c) at
     // (c >> 1) * PL + 2 i + (c & 1): row accesses (one double2 per lane and plane) and DMMA fragment loads are then
-    // contiguous across the warp, and with PL = 2 mod 16, PS4 = 4 mod 16 the 16 columns of a group fall into 16
-    // different bank pairs for the sigma points' column reads.
-    static constexpr int PL = 2 * NPAD + 2;
-    static constexpr int PS4 = 2 * PL;                 // stride between the 4 panels of a group
+    // contiguous across the warp.  PL = 8 mod 16 puts the two planes half a bank cycle apart (the 16-lane panel
+    // extraction writes both planes in one instruction), and with PS4 = 2 mod 16 the 16 columns of a group fall into 16
+    // different bank pairs for the sigma points' column reads: (c & 1) + 8 (c >> 1) + 2 q covers 0..15.
+    static constexpr int PL = 2 * NPAD + 8;
+    static constexpr int PS4 = 2 * PL + 2;             // stride between the 4 panels of a group
     static constexpr int KP = (NK_ + 3) / 4 * 4;       // padded row length of K / covXZ (DMMA k-dimension)
     static constexpr int LF = 4 * PS4;                 // finished panel rows U of the current group
-    static constexpr int LRAW = PS4;                   // the current panel as extracted from the accumulators (same planes)
-    static constexpr int KK = 2 * NPAD * KP;           // K | covXZ rows, overlays LF | LRAW once the factorisation is over
+    static constexpr int LRAW = 2 * PL;                // the current panel as extracted from the accumulators (same planes)
+    static constexpr int KK = 2 * NPAD * KP + NPAD;    // K | covXZ rows | K nu, overlay LF | LRAW once the factorisation is over
     static constexpr int SCR0 = (LF + LRAW > KK ? LF + LRAW : KK);
-    static constexpr int WGS = (16 * NK_ + 1) / 2 * 2; // W' of the current group
-    static constexpr int UPD_SCR = SCR0 + WGS + 2 * NPAD;   // + d_k + (K nu)_i
+    static constexpr int WGS = 16 * NK_;               // W' of the current group, [c][16]: column pairs are one double2
+    static constexpr int UPD_SCR = SCR0 + WGS + NPAD;       // + d_k
     static constexpr int PRED_SCR = PRED_LS + 28 * PRED_DS + 144 + 12 * PRED_DS + 16;
     static constexpr int SCR = (UPD_SCR > PRED_SCR ? UPD_SCR : PRED_SCR);
     static constexpr int ZS = (NK_ + 1) / 2 * 2;
@@ -197,7 +198,7 @@ SLB_DEV void sigma_group(UpdState<C> &s, const double *mus, const double *Lf, do
         e[c] = act ? z[c] - s.z0[c] : 0.0;
         s.esum[c] += e[c];
         const double zp = __shfl_xor_sync(FULL, z[c], 1);
-        if (act && !neg) Wg[jl * NK + c] = (0.5 * rs) * (z[c] - zp);   // W'_j = (Z+ - Z-) / (2 sqrt d_j)
+        if (act && !neg) Wg[c * 16 + jl] = (0.5 * rs) * (z[c] - zp);   // W'_j = (Z+ - Z-) / (2 sqrt d_j)
     }
 #pragma unroll
     for (int r = 0; r < NK; ++r)
@@ -212,15 +213,13 @@ SLB_DEV void sigma_group(UpdState<C> &s, const double *mus, const double *Lf, do
         const double2 x01 = *reinterpret_cast<const double2 *>(pa), x23 = *reinterpret_cast<const double2 *>(pb);
         double2 y01 = make_double2(0.0, 0.0), y23 = y01;
         if (has1) { y01 = *reinterpret_cast<const double2 *>(pa + 64); y23 = *reinterpret_cast<const double2 *>(pb + 64); }
-        const double x[4] = {x01.x, x01.y, x23.x, x23.y}, y[4] = {y01.x, y01.y, y23.x, y23.y};
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-#pragma unroll
-            for (int c = 0; c < NK; ++c) {
-                const double wv = Wg[(4 * qq + c4) * NK + c];
-                s.px0[c] = fma(x[c4], wv, s.px0[c]);
-                s.px1[c] = fma(y[c4], wv, s.px1[c]);
-            }
+        for (int c = 0; c < NK; ++c) {
+            const double2 w01 = *reinterpret_cast<const double2 *>(Wg + c * 16 + 4 * qq);
+            const double2 w23 = *reinterpret_cast<const double2 *>(Wg + c * 16 + 4 * qq + 2);
+            s.px0[c] = fma(x23.y, w23.y, fma(x23.x, w23.x, fma(x01.y, w01.y, fma(x01.x, w01.x, s.px0[c]))));
+            s.px1[c] = fma(y23.y, w23.y, fma(y23.x, w23.x, fma(y01.y, w01.y, fma(y01.x, w01.x, s.px1[c]))));
+        }
     }
 }
 
@@ -328,7 +327,7 @@ SLB_DEV int usckf_update_smem(double *Ps, double *mus, double *scr, const double
     constexpr int N = C::N, NT = C::NT, NPAD = C::NPAD, JLAST = C::JLAST, KP = C::KP;
     const int a_ = lane & 3, b_ = lane >> 2;
     double *Lf = scr, *Lraw = scr + C::LF, *Ks = scr, *Cs = scr + NPAD * KP, *Wg = scr + C::SCR0, *dv = Wg + C::WGS,
-           *dl = dv + NPAD;
+           *dl = Cs + NPAD * KP;
     UpdState<C> s;
     s.ok = true;
     // ---- the lower triangle of Pk from the resident record into the accumulator tiles; diagonal tiles are filled
