@@ -495,6 +495,7 @@ static int launch_chunk(slb_handle h, const HostStep &hs, int b0, int cnt, const
 static int step_host_enqueue(slb_handle h, const HostStep &hs, cudaStream_t s) {
     double *du = h->stage, *dz = du + (size_t)h->B * hs.nu, *dmu = dz + (size_t)h->B * hs.m;
     double *dQ = h->shared_small, *dp = dQ + hs.nq * hs.nq, *dR = dp + hs.nparams;
+    h->qr_nq = h->qr_m = 0;   // shared_small is rewritten: the zero-copy path's Q | R cache no longer describes it
     SLB_CUDA(cudaMemcpyAsync(dQ, hs.Q, (size_t)hs.nq * hs.nq * 8, cudaMemcpyHostToDevice, s));
     if (hs.nparams) SLB_CUDA(cudaMemcpyAsync(dp, hs.params, (size_t)hs.nparams * 8, cudaMemcpyHostToDevice, s));
     SLB_CUDA(cudaMemcpyAsync(dR, hs.R, (size_t)hs.m * hs.m * 8, cudaMemcpyHostToDevice, s));
@@ -589,8 +590,21 @@ static int step_host(slb_handle h, const HostStep &hs, void *stream, bool wait =
     double *zmu = dev_alias_m(hs.mu_out);
     if (zero_copy && zu && zz && (zmu || !hs.mu_out) && (h->cfg.kind == SLB_KIND_UKF || h->cfg.kind == SLB_KIND_USCKF)) {
         double *dQ = h->shared_small, *dR = dQ + hs.nq * hs.nq;
-        SLB_CUDA(cudaMemcpyAsync(dQ, hs.Q, (size_t)hs.nq * hs.nq * 8, cudaMemcpyHostToDevice, s));
-        SLB_CUDA(cudaMemcpyAsync(dR, hs.R, (size_t)hs.m * hs.m * 8, cudaMemcpyHostToDevice, s));
+        const size_t qb = (size_t)hs.nq * hs.nq * 8, rb = (size_t)hs.m * hs.m * 8;
+        const bool cacheable = hs.nq <= 12 && hs.m <= 9;
+        if (!(cacheable && h->qr_nq == hs.nq && h->qr_m == hs.m && memcmp(h->qr_cache, hs.Q, qb) == 0 &&
+              memcmp(h->qr_cache + 144, hs.R, rb) == 0)) {
+            // (stream order protects the kernels of earlier steps that still read the previous values)
+            SLB_CUDA(cudaMemcpyAsync(dQ, hs.Q, qb, cudaMemcpyHostToDevice, s));
+            SLB_CUDA(cudaMemcpyAsync(dR, hs.R, rb, cudaMemcpyHostToDevice, s));
+            h->qr_nq = h->qr_m = 0;
+            if (cacheable) {
+                memcpy(h->qr_cache, hs.Q, qb);
+                memcpy(h->qr_cache + 144, hs.R, rb);
+                h->qr_nq = hs.nq;
+                h->qr_m = hs.m;
+            }
+        }
         FilterArgs a = make_args(h);
         a.u = zu; a.dt = hs.dt; a.Q = dQ; a.z = zz; a.R = dR; a.gate = hs.gate; a.m = hs.m;
         a.mu_out = zmu;

@@ -37,6 +37,10 @@ struct slb_batch_s {
     const void *step_key_p[6];
     cudaEvent_t ev_start, ev_done[SLB_NXS];
     int out_off, out_len;      // slb_set_output_slice: part of the q-vector the *_step_host entry points copy back
+    // zero-copy *_step_host: host copy of the Q | R last uploaded to shared_small (the upload is skipped while the caller
+    // keeps passing the same values: two tiny DMA operations per step are 10 % of a UKFoM step)
+    double qr_cache[144 + 81];
+    int qr_nq, qr_m;           // 0 = nothing cached
 };
 
 namespace slb {

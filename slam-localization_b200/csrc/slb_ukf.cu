@@ -23,6 +23,7 @@
 //   * predict+update fused in one launch moves each instance through HBM exactly once.
 #include "slb_internal.h"
 #include "slb_models.cuh"
+#include "slb_predict12.cuh"   // TMA bulk copy / mbarrier helpers
 
 namespace slbd {
 
@@ -80,6 +81,12 @@ struct Rec {
     static constexpr int IS = RAW + ((G - RAW % 16) % 16 + 16) % 16;
     // update scratch inside SIG
     static constexpr int ZO = 0, DZO = NS * M, KO = DZO + N * M, KSO = KO + N * M, DLO = KSO + N * M;
+};
+
+// doubles of shared memory per warp: 32/G records, the packed Q, and (16-byte aligned) an mbarrier slot
+template <class L, int M, int G>
+struct UkfWarp {
+    static constexpr int DOUBLES = ((32 / G) * Rec<L, M, G>::IS + L::NP + 1) / 2 * 2 + 2;
 };
 
 // Cholesky of the packed P at `ps` into `lf` (both in this instance's record); every lane of the
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
     typedef Rec<L, MM::M, G> R;
     constexpr int N = L::N, QD = L::QD, NP = L::NP, NS = 2 * N + 1, M = MM::M, MP = M * (M + 1) / 2;
     constexpr int IPW = 32 / G, WPB = TPB / 32, ROUNDS = (NS + G - 1) / G, RROWS = (N + G - 1) / G;
-    constexpr int WSZ = IPW * R::IS + NP;  // per-warp shared memory: IPW records + packed Q
+    constexpr int WSZ = UkfWarp<L, MM::M, G>::DOUBLES;  // per-warp shared memory: IPW records + packed Q + mbarrier
     static_assert(M == 3, "only 3-dof measurement models are wired to the UKF kernel");
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
     double *wsm = sm + (size_t)warp * WSZ;
     double *rec = wsm + grp * R::IS;
     double *Qp = wsm + IPW * R::IS;
+    uint64_t *ubar = reinterpret_cast<uint64_t *>(wsm + WSZ - 2);
     const int wbase = (blockIdx.x * WPB + warp) * IPW;  // first instance of this warp
     if (wbase >= a.B) return;
     const int inst = wbase + grp;
@@ -229,19 +237,32 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
             }
         }
         // u and z ride along: when they live in mapped host memory (zero-copy *_step_host) their PCIe latency is paid
-        // once, together with the record's, instead of twice in the middle of the step
+        // once, together with the record's, instead of twice in the middle of the step.  A warp's 8 instances are one
+        // contiguous run of each array (384 B of u, 192 B of z), fetched with ONE TMA bulk copy per array: over PCIe
+        // that is a few large read requests instead of 18 sector-sized ones (the read-tag pool, not the link, bounded
+        // the zero-copy step at ~23 GB/s).  They land in record 0's (not yet live) sigma-point area as u[8][NU] | z[8][M].
         {
             constexpr int NU = ProcessModel<PM>::NU, PERI = NU + M;
-            static_assert(NU <= 6, "record slot for u");
-            for (int e = lane; e < IPW * PERI; e += 32) {
-                const int li2 = e / PERI, c = e - li2 * PERI;
-                double *d = wsm + li2 * R::IS + R::UZ + c;
-                const bool need = c < NU ? PRED : UPD;
-                if (need && wbase + li2 < a.B) {
-                    const double *src = c < NU ? a.u + (size_t)(wbase + li2) * NU + c : a.z + (size_t)(wbase + li2) * M + (c - NU);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(src) : "memory");
-                } else {
-                    *d = 0.0;
+            static_assert(NU <= 6 && (IPW * NU * 8) % 16 == 0 && (IPW * M * 8) % 16 == 0, "bulk copy granularity");
+            static_assert(IPW * PERI <= R::SIGSZ, "staging area");
+            if (wbase + IPW <= a.B) {
+                if (lane == 0) {
+                    mbar_init(ubar, 1);
+                    mbar_expect_tx(ubar, (PRED ? IPW * NU * 8 : 0) + (UPD ? IPW * M * 8 : 0));
+                    if (PRED) bulk_g2s(wsm, a.u + (size_t)wbase * NU, IPW * NU * 8, ubar);
+                    if (UPD) bulk_g2s(wsm + IPW * NU, a.z + (size_t)wbase * M, IPW * M * 8, ubar);
+                }
+            } else {   // ragged tail of the batch: element-wise
+                for (int e = lane; e < IPW * PERI; e += 32) {
+                    const int li2 = e / PERI, c = e - li2 * PERI;
+                    double *d = c < NU ? wsm + li2 * NU + c : wsm + IPW * NU + li2 * M + (c - NU);
+                    const bool need = c < NU ? PRED : UPD;
+                    if (need && wbase + li2 < a.B) {
+                        const double *src = c < NU ? a.u + (size_t)(wbase + li2) * NU + c : a.z + (size_t)(wbase + li2) * M + (c - NU);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(d)), "l"(src) : "memory");
+                    } else {
+                        *d = 0.0;
+                    }
                 }
             }
         }
@@ -255,12 +276,13 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
         asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
     }
     __syncwarp();
+    if (wbase + IPW <= a.B) mbar_wait(ubar, 0);
     double *sig = rec + R::SIG, *lf = rec + R::LF, *ps = rec + R::PS;
     double ureg[ProcessModel<PM>::NU], zreg[MM::M];
 #pragma unroll
-    for (int c = 0; c < ProcessModel<PM>::NU; ++c) ureg[c] = rec[R::UZ + c];
+    for (int c = 0; c < ProcessModel<PM>::NU; ++c) ureg[c] = PRED ? wsm[grp * ProcessModel<PM>::NU + c] : 0.0;
 #pragma unroll
-    for (int c = 0; c < MM::M; ++c) zreg[c] = rec[R::UZ + ProcessModel<PM>::NU + c];
+    for (int c = 0; c < MM::M; ++c) zreg[c] = UPD ? wsm[IPW * ProcessModel<PM>::NU + grp * MM::M + c] : 0.0;
     __syncwarp();
     if (!valid && sub == 0) {  // tail of the batch: a benign identity prior keeps the idle lanes finite
 #pragma unroll
@@ -305,7 +327,10 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
 
     if (UPD) {
         // ---- update(z, h, R, mt) ----------------------------------------------------------------
-        if (!group_chol<N>(ps, lf, sub) && alive) { st |= SLB_ST_CHOL_FAIL; alive = false; }
+        // `alive` = the record holds something to publish (in the fused step: the predicted state); a failing update
+        // leaves that state as it is, exactly like calling predict and update separately
+        bool upd = alive;
+        if (!group_chol<N>(ps, lf, sub) && alive) { st |= SLB_ST_CHOL_FAIL; upd = false; }
         double *Z = sig + R::ZO, *DZ = sig + R::DZO, *Ks = sig + R::KO, *KSs = sig + R::KSO, *DL = sig + R::DLO;
         double zsum[M];
 #pragma unroll
@@ -404,8 +429,13 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
         }
         __syncwarp();
         const bool accept = chi2_accept(m2, a.gate);
-        if (alive && !accept) st |= SLB_ST_GATE_REJECT;
-        const bool apply = alive && accept;
+        if (upd && !accept) st |= SLB_ST_GATE_REJECT;
+        const bool apply = upd && accept;
+        // the prior covariance of this update, kept until the update is known to go through
+        double Psave[(NP + G - 1) / G];
+#pragma unroll
+        for (int k = 0; k < (NP + G - 1) / G; ++k) Psave[k] = (sub + G * k < NP) ? ps[sub + G * k] : 0.0;
+        __syncwarp();
         // sigma -= K S K^T   (lower triangle; the reference's LLT reads only that, Q8)
         if (apply) {
 #pragma unroll
@@ -424,15 +454,13 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
         __syncwarp();
         // apply_delta(K * innovation): re-draw sigma points around mu [+] delta.  Groups that do not
         // apply (gate, earlier failure) run the same instructions on their untouched P and drop the result.
-        double Psave[(NP + G - 1) / G];
         if (!apply) {
-#pragma unroll
-            for (int k = 0; k < (NP + G - 1) / G; ++k) Psave[k] = (sub + G * k < NP) ? ps[sub + G * k] : 0.0;
 #pragma unroll
             for (int r = 0; r < N; ++r) delta[r] = 0.0;
         }
         const bool ok3 = group_chol<N>(ps, lf, sub);
-        if (apply && !ok3) { st |= SLB_ST_CHOL_FAIL; alive = false; }
+        if (apply && !ok3) st |= SLB_ST_CHOL_FAIL;
+        const bool done = apply && ok3;
 #pragma unroll 1
         for (int t = 0; t < ROUNDS; ++t) {
             const int s = sub + G * t;
@@ -448,14 +476,14 @@ __global__ void __launch_bounds__(TPB, MINB) ukf_kernel(slb::FilterArgs a) {
         }
         __syncwarp();
         double nm[QD];
-        const bool conv = group_mean<L, G>(sig, sub, apply && ok3, nm);
-        if (apply && ok3) {
+        const bool conv = group_mean<L, G>(sig, sub, done, nm);
+        if (done) {
             if (!conv) st |= SLB_ST_MEAN_NOCONV;
 #pragma unroll
             for (int c = 0; c < QD; ++c) mu[c] = nm[c];
         }
         group_cov<L, G, false>(sig, ps, Qp, sub, nm);
-        if (!apply) {  // rejected update: sigma and mu stay as they were (Usckf.hpp:294 / ukf::update)
+        if (!done) {  // rejected / failed update: sigma and mu stay as they were (Usckf.hpp:294 / ukf::update)
 #pragma unroll
             for (int k = 0; k < (NP + G - 1) / G; ++k)
                 if (sub + G * k < NP) ps[sub + G * k] = Psave[k];
@@ -509,7 +537,7 @@ template <class L, int PM, class MM>
 static int launch_ukf_t(bool predict, bool update, const FilterArgs &a, cudaStream_t s) {
     constexpr int G = 4, TPB = 128, MINB = 3;
     typedef slbd::Rec<L, MM::M, G> R;
-    constexpr size_t smem = (size_t)(TPB / 32) * ((32 / G) * R::IS + L::NP) * sizeof(double);
+    constexpr size_t smem = (size_t)(TPB / 32) * slbd::UkfWarp<L, MM::M, G>::DOUBLES * sizeof(double);
     static_assert(smem <= 227 * 1024, "instance records exceed shared memory");
     const int ipb = TPB / G;
     const int grid = (a.B + ipb - 1) / ipb;

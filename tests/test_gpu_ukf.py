@@ -233,3 +233,51 @@ def test_ukf_step_host_async_pipeline_equals_synchronous_steps():
     for k in range(3):
         np.testing.assert_array_equal(oa[k].numpy(), ob[k].numpy())
     np.testing.assert_array_equal(a.P(), b.P())
+
+
+def test_ukf_fused_step_keeps_the_predicted_state_when_the_update_fails(slo):
+    """step() must equal predict() followed by update() also when the update cannot go through.  A negative
+    definite R (invalid input) makes P - K S K^T indefinite: the post-update Cholesky fails, the instance is flagged and
+    keeps its PREDICTED state -- in the fused launch exactly as in the two-call sequence and in the oracle."""
+    B = 200
+    sc = synth.ukfom_scenario(B, seed=36, p_scale=1e-4)
+    Rbad = -2e-5 * np.eye(3)
+    a, b = engine.Ukf(B), engine.Ukf(B)
+    for f in (a, b):
+        f.set_state(sc["mu"], sc["P"])
+    a.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], sc["Q"], sc["z"], Rbad)
+    b.predict(engine.PM_UKFOM_IMU, sc["u"], sc["dt"], sc["Q"])
+    mu_p, P_p = b.mu(), b.P()
+    b.update(engine.MM_GPS_POS, sc["z"], Rbad)
+    failed = (b.status() & engine.ST_CHOL_FAIL) != 0
+    assert failed.sum() > B // 2
+    np.testing.assert_array_equal(a.status(), b.status())
+    np.testing.assert_array_equal(a.mu(), b.mu())
+    np.testing.assert_array_equal(a.P(), b.P())
+    np.testing.assert_array_equal(b.mu()[failed], mu_p[failed])          # the failed update left the predicted state alone
+    np.testing.assert_array_equal(b.P()[failed], P_p[failed])
+    mu_r, P_r, st_r, _ = slo.ukf_step(9, slo.PM_UKFOM_IMU, slo.MM_GPS_POS, sc["mu"], sc["P"], sc["u"], sc["dt"], sc["Q"],
+                                      None, None, update=False, nthreads=4)
+    parity.assert_parity(slo, [0, 1, 0], a.mu()[failed], a.P()[failed], mu_r[failed], P_r[failed])
+
+
+def test_ukf_step_host_sees_a_changed_Q_and_R():
+    """The zero-copy host step uploads the shared Q / R only when their values change; a change must take effect."""
+    import torch
+    B = 4096
+    sc = synth.ukfom_scenario(B, seed=93)
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+    hu, hz = pin(sc["u"]), pin(sc["z"])
+    hQ, hR = pin(sc["Q"]), pin(sc["R"])
+    a, b = engine.Ukf(B), engine.Ukf(B)
+    for f in (a, b):
+        f.set_state(sc["mu"], sc["P"])
+    out = torch.empty((B, 10), dtype=torch.float64).pin_memory()
+    for k in range(3):
+        Q, R = sc["Q"] * (1.0 + k), sc["R"] * (1.0 + 0.5 * k)
+        hQ.copy_(torch.from_numpy(Q))                       # same host buffers, new values
+        hR.copy_(torch.from_numpy(R))
+        a.step(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, sc["u"], sc["dt"], Q, sc["z"], R)
+        b.step_host(engine.PM_UKFOM_IMU, engine.MM_GPS_POS, hu, sc["dt"], hQ, hz, hR, mu_out=out)
+        np.testing.assert_array_equal(out.numpy(), a.mu())
+    np.testing.assert_array_equal(a.P(), b.P())
