@@ -116,20 +116,32 @@ bool usckf_shape_supported(int nk, int nl) {
 template <int NK, int NL, bool PRED, bool UPD>
 static int launch_step_t(const FilterArgs &a, cudaStream_t s) {
     typedef slbd::StepCfg<NK, NL> C;
-    constexpr int WPB = 4;
-    constexpr size_t smem = (size_t)WPB * C::SM * sizeof(double);
-    constexpr int fit = (int)((228 * 1024) / (smem + 1024));
-    constexpr int MINB = fit > 3 ? 3 : fit < 1 ? 1 : fit;
-    static_assert(smem <= 227 * 1024, "record + scratch of one CTA must fit in shared memory");
+    // CTA shape: the register file (168 registers) holds 12 warps per SM.  Measured on the (3,9) fleet, 524 288 instances
+    // (profiles/r02_usckf_cta_shape.txt): 1 / 2 / 3 / 4 / 6 / 12 warps per CTA = 6.37 / 6.94 / 6.06 / 6.19 / 5.77 / 6.53 ms per
+    // step.  Two CTAs of six warps win: warps that start together walk the 104 KB unrolled instruction stream together
+    // (the L1.5 instruction cache is 32 KB), while a single 12-warp CTA leaves the SM idle between its tail and the next
+    // CTA's record loads.  Explicit CTA barriers to keep the warps aligned did not help (6.21 ms).
+    constexpr size_t pw = (size_t)C::SM * sizeof(double);
+    constexpr size_t SM_BYTES = 228 * 1024, CTA_MAX = 227 * 1024, RSV = 1024;
+#ifdef SLB_USCKF_WPB
+    constexpr int WPB = SLB_USCKF_WPB;   // experiment knob (compile time)
+#else
+    constexpr int WPB = 2 * (6 * pw + RSV) <= SM_BYTES ? 6 : 4;
+#endif
+    constexpr size_t smem = (size_t)WPB * pw;
+    constexpr int fit = (int)(SM_BYTES / (smem + RSV));
+    constexpr int cap = 12 / WPB < 1 ? 1 : 12 / WPB;
+    constexpr int MINB = fit > cap ? cap : fit < 1 ? 1 : fit;
     auto kern = slbd::usckf_step_kernel<SLB_PM_USCKF_TEST, NK, NL, PRED, UPD, WPB, MINB>;
     SLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // L2 prefetch distance in instances: SLB_USCKF_PREFETCH waves of (SMs x resident warps); default 2 waves
+    // L2 prefetch distance in instances: SLB_USCKF_PREFETCH waves of (SMs x resident warps); default off (measured: no
+    // gain at 0 / 1 / 2 / 4 waves, and 16 % more DRAM reads at the full fleet size)
     static const int ahead = [] {
         const char *e = getenv("SLB_USCKF_PREFETCH");
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        return (e ? atoi(e) : 2) * sms * WPB * MINB;
+        return (e ? atoi(e) : 0) * sms * WPB * MINB;
     }();
     FilterArgs b = a;
     b.prefetch = ahead;

@@ -24,6 +24,17 @@
 #pragma once
 #include "slb_predict12.cuh"
 
+// Experiment knob (compile time): -DSLB_USCKF_CTA_SYNC=1 re-aligns the warps of a CTA a few times per instance so that
+// they walk the (104 KB, fully unrolled) instruction stream together and share instruction-cache lines.
+#ifndef SLB_USCKF_CTA_SYNC
+#define SLB_USCKF_CTA_SYNC 0
+#endif
+#if SLB_USCKF_CTA_SYNC
+#define SLB_CTA_SYNC() __syncthreads()
+#else
+#define SLB_CTA_SYNC() ((void)0)
+#endif
+
 namespace slbd {
 
 template <int NK_, int NL_>
@@ -148,8 +159,19 @@ struct UpdState {
 
 // ---- sigma points of columns 16 G .. 16 G + 15 through h, W' of those columns, covXZ += U W' ---------------------
 template <class C, int G>
-SLB_DEV void sigma_group(UpdState<C> &s, const double *mus, const double *Lf, double *Wg, const double *dv, int lane) {
+SLB_DEV void sigma_group(UpdState<C> &s, const double *mus_, const double *Lf, double *Wg, const double *dv, int lane) {
     constexpr int NK = C::NK, PS4 = C::PS4;
+    // the mean scalars h needs, as 16-byte broadcast loads (statek pos|quat = mus[0..6], statek_i = mus[26..32])
+    double mus[40 + NK];
+    {
+        const double2 *m2 = reinterpret_cast<const double2 *>(mus_);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const double2 v = m2[e]; mus[2 * e] = v.x; mus[2 * e + 1] = v.y; }
+#pragma unroll
+        for (int e = 13; e < 17; ++e) { const double2 v = m2[e]; mus[2 * e] = v.x; mus[2 * e + 1] = v.y; }
+#pragma unroll
+        for (int c = 0; c < NK; ++c) mus[39 + c] = mus_[39 + c];
+    }
     constexpr int col0 = 16 * G;
     constexpr int ncols = C::NCOL - col0 < 16 ? C::NCOL - col0 : 16;
     const bool neg = lane & 1, act = (lane >> 1) < ncols;
@@ -310,7 +332,10 @@ struct PanelStep {
                 for (int I = J; I < NT; ++I) dmma884(s.c0[I][J], s.c1[I][J], f[I], g);
             }
         }
-        if (Q == 3 || P == C::NPAN - 1) sigma_group<C, (P >> 2)>(s, mus, Lf, Wg, dv, lane);
+        if (Q == 3 || P == C::NPAN - 1) {
+            sigma_group<C, (P >> 2)>(s, mus, Lf, Wg, dv, lane);
+            SLB_CTA_SYNC();
+        }
         PanelStep<C, P + 1>::run(s, mus, Lf, Lraw, Wg, dv, lane);
     }
 };
@@ -542,7 +567,8 @@ SLB_DEV int usckf_predict_smem(double *Ps, double *mus, double *scr, const doubl
         boxminus<L>(Y, ref, dY);
         if (lane < 28) {
 #pragma unroll
-            for (int r = 0; r < 12; ++r) D[lane * PRED_DS + r] = act ? dY[r] : 0.0;
+            for (int r = 0; r < 12; r += 2)   // (row stride 160 B: 16-byte stores, 2-way instead of 8-way bank conflicts)
+                *reinterpret_cast<double2 *>(D + lane * PRED_DS + r) = act ? make_double2(dY[r], dY[r + 1]) : make_double2(0.0, 0.0);
         }
     }
     __syncwarp();
@@ -684,9 +710,11 @@ __global__ void __launch_bounds__(WPB * 32, MINB) usckf_step_kernel(slb::FilterA
     }
     __syncwarp();
     mbar_wait(bar, 0);
+    SLB_CTA_SYNC();
     int st = 0;
     bool dirty = false;
     if (PRED) st |= usckf_predict_smem<PM, NK + NL>(Ps, mus, scr, u, a.dt, a.Q, lane, dirty);
+    if (PRED) SLB_CTA_SYNC();
     if (UPD) st |= usckf_update_smem<NK, NL>(Ps, mus, scr, zs, a, lane, dirty);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");   // (an update that bailed out early has not waited for z)
     // ---- record out ----------------------------------------------------------------------------------------------

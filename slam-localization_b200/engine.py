@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libslb.so")
+LIB_PATH = os.environ.get("SLB_LIB") or os.path.join(_HERE, "csrc", "libslb.so")   # SLB_LIB: experiment builds of the library
 
 # ---- ids of include/slb.h ------------------------------------------------------------------------
 KIND_UKF, KIND_USCKF, KIND_MSCKF = 1, 2, 3
