@@ -63,8 +63,7 @@ enum {
 /* Fixed-DOF manifold layouts for SLB_KIND_UKF. */
 enum {
     SLB_LAYOUT_POSE6 = 6,   /* vect3 pos, SO3 orient           (SensorState, State.hpp:242-252) */
-    SLB_LAYOUT_MTK9 = 9,    /* vect3 pos, SO3 orient, vect3 vel (test/UKFoMUnitTest.cpp:31-35)  */
-    SLB_LAYOUT_STATE12 = 12 /* pos, orient, velo, angvelo       (State, State.hpp:137-149)      */
+    SLB_LAYOUT_MTK9 = 9     /* vect3 pos, SO3 orient, vect3 vel (test/UKFoMUnitTest.cpp:31-35)  */
 };
 
 /* Device model catalogue.  The reference takes arbitrary host functors f/h (Usckf.hpp:113-114,

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SLB_LIB") or os.path.join(_HERE, "csrc", "libslb.so")
 
 # ---- ids of include/slb.h ------------------------------------------------------------------------
 KIND_UKF, KIND_USCKF, KIND_MSCKF = 1, 2, 3
-LAYOUT_POSE6, LAYOUT_MTK9, LAYOUT_STATE12 = 6, 9, 12
+LAYOUT_POSE6, LAYOUT_MTK9 = 6, 9
 PM_UKFOM_IMU, PM_UKFOM_IMU_REFBUG, PM_POSE6_ODOM, PM_USCKF_TEST, PM_MSCKF_DELTAPOSE = 1, 2, 3, 4, 5
 MM_GPS_POS, MM_USCKF_VO, MM_MSCKF_REPROJ = 101, 102, 103
 STATEK, STATEK_L, STATEK_I = 1, 2, 3
