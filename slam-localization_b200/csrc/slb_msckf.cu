@@ -31,13 +31,17 @@ constexpr int MS_NSPAD = 148;                    // sigma-point count padded to 
 static_assert(MS_NSMAX == 2 * MS_NMAX + 1 && MS_NSPAD >= MS_NSMAX && MS_NSPAD % 4 == 0, "sigma-point padding");
 constexpr int MS_A = 5056;                       // >= 100*101/2 and >= 72*73/2
 constexpr int MS_ZS = 100;                       // row stride of Z and of covXZ / Y   (= 4 mod 16)
-constexpr int MS_QS = 84;                        // row stride of the sigma points X / deviations D (= 4 mod 16)
+constexpr int MS_QS = 84;                        // q-vector scalars per sigma point (13 + 7 * 10, padded)
+constexpr int MS_XS = MS_NSPAD;                  // the sigma points X / deviations D are stored TRANSPOSED, Xt[scalar][sigma point],
+                                                 // row stride 148 (= 4 mod 16): a lane per sigma point reads consecutive doubles
+                                                 // (the [sigma point][scalar] layout made those accesses 8-way bank conflicts) and
+                                                 // the DMMA fragments of D^T D (4 sigma points x 8 scalars) still hit 32 banks
 constexpr int MS_B = MS_NSPAD * MS_ZS;           // 14800
 constexpr int MS_C = MS_NMAX * MS_ZS;            // 7200
 constexpr int MS_D = 896;                        // small vectors
 constexpr int MS_SMEM_DOUBLES = MS_A + MS_B + MS_C + MS_D;
 static_assert(MS_SMEM_DOUBLES * 8 <= 227 * 1024, "MSCKF update working set exceeds shared memory");
-static_assert(MS_NSPAD * MS_QS <= MS_B, "sigma points do not fit region B");
+static_assert(MS_QS * MS_XS <= MS_B && MS_XS % 16 == 4, "sigma points do not fit region B");
 static_assert(MS_MMAX * (MS_MMAX + 1) / 2 <= MS_A && MS_A + 2 * 1600 <= MS_B, "compacted S + two panel stagings do not fit region B");
 static_assert(2400 >= 32 * MS_NMAX && 2400 + MS_NMAX * (MS_NMAX + 1) / 2 <= MS_C, "parked factor does not fit region C");
 
@@ -83,6 +87,14 @@ __device__ int chol_dbg_call;
 #define CHOL_T(panel, slot) do { if (blockIdx.x == 0 && chol_dbg_call == SLB_CHOL_TIMING && (threadIdx.x & 31) == 0 && (panel) < 16) chol_dbg[((panel) * 16 + (threadIdx.x >> 5)) * 8 + (slot)] = clock64(); } while (0)
 #else
 #define CHOL_T(panel, slot) do { } while (0)
+#endif
+// -DSLB_MSCKF_PHASES: clock64() stamp of thread 0 of CTA 0 at every phase boundary of msckf_update_kernel, for its
+// second and third instance (steady state: the factor of P arrives from the previous iteration) -- profiles/msckf_phases.py
+#ifdef SLB_MSCKF_PHASES
+__device__ long long ms_phase_dbg[4 * 32];
+#define MS_PH(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && ms_it < 4) ms_phase_dbg[ms_it * 32 + (slot)] = clock64(); } while (0)
+#else
+#define MS_PH(slot) do { } while (0)
 #endif
 constexpr int MS_PS = 1600;
 constexpr int MS_NXL = 2400;   // offset in region C of the next instance's factor (above the <= 32 x 72 partial sums of the mean)
@@ -477,11 +489,18 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
     // CTA-uniform: the previous iteration already factored this instance's covariance (chol_dual, in lockstep with its own
     // chol(P_new)) and parked L at RC + MS_NXL, its pivot flag in flags[5]
     bool have_l = false;
+#ifdef SLB_MSCKF_PHASES
+    int ms_it = -1;
+#endif
     for (int inst = blockIdx.x; inst < a.B; inst += gridDim.x) {
         double *Pg = a.P + (size_t)inst * a.pstride;
         double *mug = a.mu + (size_t)inst * a.qstride;
         const double *zg = a.z + (size_t)inst * M;
         __syncthreads();
+#ifdef SLB_MSCKF_PHASES
+        ++ms_it;
+#endif
+        MS_PH(0);
         // cp.async keeps every load of the record in flight at once
         if (have_l) {
             for (int e = tid; e < NP; e += MS_T) RA[e] = RC[MS_NXL + e];
@@ -492,6 +511,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         if (tid == 0) { flags[0] = have_l ? flags[5] : 1; flags[1] = M; flags[2] = 0; }
         pred_cp_async_wait_all();
         __syncthreads();
+        MS_PH(1);
         // ---- L = chol(Pk) (:229 -> :412), unless the previous iteration already did it ------------------
         if (!have_l) chol_blocked(RA, N, flags, invd, PS);
         have_l = false;
@@ -500,9 +520,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
         }
+        MS_PH(2);
         // ---- sigma points through h (:229-232), thread per sigma point ---------------------------------
         // h = SLB_MM_MSCKF_REPROJ: feature f is landmark f seen from clone f % k (statek is not observed)
         // work item = (sigma point, clone): NS * k items over the whole CTA
+        // (Skipping the (sigma point, clone) pairs the factor's column cannot reach -- 37 % of them, copies of row 0 -- was
+        // tried: the uneven rounds and the extra copy pass cost more than the projections they save, 11.4k -> 15.2k cycles.)
         for (int w = tid; w < NS * k; w += MS_T) {
             const int s = w / k, c = w - s * k, j = s >= 1 ? (s - 1) >> 1 : 0;
             const double sgn = (s & 1) ? 1.0 : -1.0;
@@ -529,14 +552,25 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
+        MS_PH(3);
         // ---- mean_z, innovation (:234-236) -------------------------------------------------------------
         if (tid < M) {
-            double s = 0.0;
-            for (int t = 0; t < NS; ++t) s += RB[t * MS_ZS + tid];
+            // four interleaved partial sums: the additions of a column no longer form one 145-long dependent chain
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int t = 0;
+            for (; t + 3 < NS; t += 4) {
+                s0 += RB[t * MS_ZS + tid];
+                s1 += RB[(t + 1) * MS_ZS + tid];
+                s2 += RB[(t + 2) * MS_ZS + tid];
+                s3 += RB[(t + 3) * MS_ZS + tid];
+            }
+            for (; t < NS; ++t) s0 += RB[t * MS_ZS + tid];
+            const double s = (s0 + s1) + (s2 + s3);
             const double zb = s * (1.0 / (double)NS);
             zbar[tid] = zb;
             nu[tid] = zg[tid] - zb;
         }
+        MS_PH(4);
         // ---- W_j = 0.5 (Z+_j - Z-_j) into region C ---------------------------------------------------
         //      and, in the same pass over the pair of rows, centre Z for the covariance (each element is read once; the four
         //      column chunks of a row pair are independent chains).  The pad rows NS..NSPAD-1 are zeroed so that the k-loop
@@ -558,6 +592,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         for (int e = tid; e < M; e += MS_T) RB[e] -= zbar[e];
         for (int e = tid; e < (MS_NSPAD - NS) * M; e += MS_T) RB[(NS + e / M) * MS_ZS + e % M] = 0.0;
         __syncthreads();   // W complete before the TRMM reads other warps' rows
+        MS_PH(5);
         // ---- covXZ = L W (:239 -> :635-657): in-place TRMM on region C.  A warp owns an 8-column strip and
         //      walks the row tiles bottom-up (row tile tr reads only rows <= 8 tr + 7 of its own strip) ------
         for (int tc = warp; tc < ((M + 7) >> 3); tc += MS_W) {
@@ -585,6 +620,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
+        MS_PH(6);
         // ---- S = 0.5 Zc^T Zc + R (:238) into region A (L is dead): lower 8x8 tiles, K = sigma points ----------
         {
             const int nt = (M + 7) >> 3, ntiles = nt * (nt + 1) / 2;
@@ -605,6 +641,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
+        MS_PH(7);
         // ---- removeOutliers (:241 -> :723-754), index quirk Q6 reproduced ---------------------------------
         if (a.gate) {
             // every feature against the 2-dof 5% bound in parallel first: while nothing is rejected the reference's
@@ -648,6 +685,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             }
         }
         __syncthreads();
+        MS_PH(8);
         const int mk = flags[1];
         if (tid == 0) a.outliers[inst] = flags[2];
         if (mk <= 0) continue;  // :250 nothing left to update with
@@ -687,11 +725,13 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         //      exactly N rows): [covXZ; nu^T] Ls^-T has w^T = (Ls^-1 nu)^T as its last row.
         if (tid < mk) wv[tid] = nu[tid];
         __syncthreads();
+        MS_PH(9);
         chol_blocked(Sp, mk, flags, invd, PS, Xz, N, MS_ZS, wv);
         if (!flags[0]) {
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
         }
+        MS_PH(10);
         // region B (the compacted S' and the panel staging) is dead: the next instance's covariance record goes there now, to be
         // factored together with this instance's P_new below
         const bool more = inst + (int)gridDim.x < a.B;
@@ -707,6 +747,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             s = warp_sum(s);
             if (lane == 0) dl[i] = s;
         }
+        MS_PH(11);
         // ---- P_new = Pk - Y Y^T (:262) into region A from the HBM record: lower 8x8 tiles, K = mk ------------
         __syncthreads();
         {
@@ -735,6 +776,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         }
         pred_cp_async_wait_all();
         __syncthreads();
+        MS_PH(12);
         // ---- applyDelta(K nu) (:263 -> :659-666): L2 = chol(P_new), X = mu [+] (delta +- L2 e_j).  A factorisation without
         //      right-hand sides keeps one warp busy and fifteen waiting, so chol(P) of the NEXT instance runs in lockstep with
         //      it (chol_dual) and is parked in region C (Y is dead; the mean's partial sums stay below MS_NXL) ----------------
@@ -750,10 +792,12 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             if (tid == 0) a.status[inst] |= SLB_ST_CHOL_FAIL;
             continue;
         }
-        for (int w = tid; w < NS * NB; w += MS_T) {   // work item = (sigma point, block)
-            const int s = w / NB, b = w - s * NB, j = s >= 1 ? (s - 1) >> 1 : 0;
+        MS_PH(13);
+        for (int w = tid; w < NS * NB; w += MS_T) {   // work item = (block, sigma point), block-major: a warp's 32 items share
+                                                      // the block type (SO3 / vector) instead of diverging over both paths
+            const int b = w / NS, s = w - b * NS, j = s >= 1 ? (s - 1) >> 1 : 0;
             const double sgn = (s & 1) ? 1.0 : -1.0;
-            double *X = RB + s * MS_QS;
+            double *X = RB + s;   // Xt[scalar][s]
             {
                 double d[3];
 #pragma unroll
@@ -763,15 +807,16 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                     double e[4], q[4];
                     so3_exp(d, 1.0, e);
                     quat_mul(mu + qo, e, q);
-                    X[qo] = q[0]; X[qo + 1] = q[1]; X[qo + 2] = q[2]; X[qo + 3] = q[3];
+                    X[qo * MS_XS] = q[0]; X[(qo + 1) * MS_XS] = q[1]; X[(qo + 2) * MS_XS] = q[2]; X[(qo + 3) * MS_XS] = q[3];
                 } else {
-                    X[qo] = mu[qo] + d[0]; X[qo + 1] = mu[qo + 1] + d[1]; X[qo + 2] = mu[qo + 2] + d[2];
+                    X[qo * MS_XS] = mu[qo] + d[0]; X[(qo + 1) * MS_XS] = mu[qo + 1] + d[1]; X[(qo + 2) * MS_XS] = mu[qo + 2] + d[2];
                 }
             }
         }
         __syncthreads();
+        MS_PH(14);
         // manifold mean (:499-525): ref = X0; do { d = mean(Xi [-] ref); ref [+]= d } while (|d| > 1e-6 ...)
-        for (int e = tid; e < QD; e += MS_T) ref[e] = RB[e];
+        for (int e = tid; e < QD; e += MS_T) ref[e] = RB[e * MS_XS];
         __syncthreads();
         // Work item = (block b, group g): group g sums X_s [-] ref over the sigma points s = g, g + G, ... in that order and
         // parks its partial in region C (Y is dead); the partials are then added in group order, so the result of an
@@ -786,15 +831,17 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
                 if (ms_so3(mb)) {
                     for (int sp = mg; sp < NS; sp += G) {
+                        const double *X = RB + qo * MS_XS + sp;
+                        const double xq[4] = {X[0], X[MS_XS], X[2 * MS_XS], X[3 * MS_XS]};
                         double r[4], d[3];
-                        quat_cmul(ref + qo, RB + sp * MS_QS + qo, r);
+                        quat_cmul(ref + qo, xq, r);
                         so3_log(r, d);
                         s0 += d[0]; s1 += d[1]; s2 += d[2];
                     }
                 } else {
                     for (int sp = mg; sp < NS; sp += G) {
-                        const double *X = RB + sp * MS_QS + qo;
-                        s0 += X[0] - ref[qo]; s1 += X[1] - ref[qo + 1]; s2 += X[2] - ref[qo + 2];
+                        const double *X = RB + qo * MS_XS + sp;
+                        s0 += X[0] - ref[qo]; s1 += X[MS_XS] - ref[qo + 1]; s2 += X[2 * MS_XS] - ref[qo + 2];
                     }
                 }
                 double *pp = part + mg * MS_NMAX + 3 * mb;
@@ -828,27 +875,47 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
             for (int o = 16; o; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
             if (!(sqrt(n2) > 1e-6 && ++iters < 10000)) break;
         }
+        MS_PH(15);
         if (iters >= 10000) st |= SLB_ST_MEAN_NOCONV;
-        // deviations d_s = X_s [-] mean, in place (72 <= 83 slots per sigma point); the pad rows NS..NSPAD-1 are zeroed
-        if (tid >= NS && tid < MS_NSPAD)
-            for (int e = 0; e < N; ++e) RB[tid * MS_QS + e] = 0.0;
-        if (tid < NS) {
-            double *X = RB + tid * MS_QS;
-            for (int b = 0; b < NB; ++b) {
-                const int qo = ms_qoff(b);
-                double d[3];
-                if (ms_so3(b)) {
-                    double r[4];
-                    quat_cmul(ref + qo, X + qo, r);
-                    so3_log(r, d);
-                } else {
-                    d[0] = X[qo] - ref[qo]; d[1] = X[qo + 1] - ref[qo + 1]; d[2] = X[qo + 2] - ref[qo + 2];
+        // deviations d_s = X_s [-] mean, in place (72 <= 83 slots per sigma point); the pad rows NS..NSPAD-1 are zeroed.
+        // Thread (g, sp), g = tid / NSPAD < 3, takes the blocks b = g, g + 3, ... of sigma point sp (a warp's lanes walk the same
+        // block sequence: no divergence between the SO3 and the vector path, no index divisions).  Every block is evaluated
+        // into registers first and written after a barrier: the tangent slots 3b..3b+2 overlap q-blocks other threads read.
+        {
+            constexpr int DEV_G = MS_T / MS_NSPAD, DEV_R = (4 + 2 * 10 + DEV_G - 1) / DEV_G;   // 3 groups, <= 8 blocks each
+            const int g = tid / MS_NSPAD, sp = tid - g * MS_NSPAD;
+            const bool on = g < DEV_G && sp < NS;
+            double dv[DEV_R][3];
+#pragma unroll
+            for (int t = 0; t < DEV_R; ++t) {
+                const int b = g + DEV_G * t;
+                dv[t][0] = dv[t][1] = dv[t][2] = 0.0;
+                if (on && b < NB) {
+                    const int qo = ms_qoff(b);
+                    const double *X = RB + qo * MS_XS + sp;
+                    if (ms_so3(b)) {
+                        const double xq[4] = {X[0], X[MS_XS], X[2 * MS_XS], X[3 * MS_XS]};
+                        double r[4];
+                        quat_cmul(ref + qo, xq, r);
+                        so3_log(r, dv[t]);
+                    } else {
+                        dv[t][0] = X[0] - ref[qo]; dv[t][1] = X[MS_XS] - ref[qo + 1]; dv[t][2] = X[2 * MS_XS] - ref[qo + 2];
+                    }
                 }
-                // 3b <= qoff(b): writing the tangent block never overtakes the q-blocks still to be read
-                X[3 * b] = d[0]; X[3 * b + 1] = d[1]; X[3 * b + 2] = d[2];
             }
+            __syncthreads();
+#pragma unroll
+            for (int t = 0; t < DEV_R; ++t) {
+                const int b = g + DEV_G * t;
+                if (on && b < NB) {
+                    double *X = RB + 3 * b * MS_XS + sp;   // Dt[tangent scalar][sp]
+                    X[0] = dv[t][0]; X[MS_XS] = dv[t][1]; X[2 * MS_XS] = dv[t][2];
+                }
+            }
+            for (int e = tid; e < (MS_NSPAD - NS) * N; e += MS_T) RB[(e / (MS_NSPAD - NS)) * MS_XS + NS + e % (MS_NSPAD - NS)] = 0.0;
         }
         __syncthreads();
+        MS_PH(16);
         // ---- Pk = 0.5 sum d d^T (:574-589) straight to the HBM record: lower 8x8 tiles, K = sigma points ------
         {
             const int ntiles = nrt * (nrt + 1) / 2;
@@ -856,10 +923,10 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 int tr, tc;
                 tri_tile(t, tr, tc);
                 const int ar = 8 * tr + fr;
-                const double *pa = RB + fk * MS_QS + min(ar, N - 1), *pb = RB + fk * MS_QS + min(8 * tc + fr, N - 1);
+                const double *pa = RB + min(ar, N - 1) * MS_XS + fk, *pb = RB + min(8 * tc + fr, N - 1) * MS_XS + fk;
                 double d0 = 0.0, d1 = 0.0;
 #pragma unroll 4
-                for (int k0 = 0; k0 < MS_NSPAD; k0 += 4) dmma884(d0, d1, pa[k0 * MS_QS], pb[k0 * MS_QS]);  // pad rows are zero
+                for (int k0 = 0; k0 < MS_NSPAD; k0 += 4) dmma884(d0, d1, pa[k0], pb[k0]);  // pad sigma points are zero
                 const int r = ar, c = 8 * tc + 2 * fk;
                 if (r < N) {
                     if (c <= r) Pg[tri(r, c)] = 0.5 * d0;
@@ -867,6 +934,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
                 }
             }
         }
+        MS_PH(17);
         bool finite = true;
         for (int e = tid; e < QD; e += MS_T) {
             mug[e] = ref[e];
@@ -874,6 +942,7 @@ __global__ void __launch_bounds__(MS_T, 1) msckf_update_kernel(slb::FilterArgs a
         }
         if (!finite) st |= SLB_ST_NONFINITE;
         if (st) atomicOr(a.status + inst, st);
+        MS_PH(18);
     }
 }
 
@@ -1507,6 +1576,11 @@ int launch_msckf_update_ekf(int mm, const FilterArgs &a, cudaStream_t s) {
 
 }  // namespace slb
 
+#ifdef SLB_MSCKF_PHASES
+extern "C" int slb_debug_msckf_phases(long long *out) {
+    return (int)cudaMemcpyFromSymbol(out, slbd::ms_phase_dbg, sizeof(long long) * 4 * 32);
+}
+#endif
 #ifdef SLB_CHOL_TIMING
 extern "C" int slb_debug_chol(long long *out) {
     return (int)cudaMemcpyFromSymbol(out, slbd::chol_dbg, sizeof(long long) * 16 * 16 * 8);
