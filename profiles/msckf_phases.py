@@ -1,6 +1,6 @@
 """Phase timeline of msckf_update_kernel (clock64 stamps of CTA 0, one instance per CTA round, BASELINE config-3 shapes).
 On the GPU box:
-    nvcc ... -DSLB_MSCKF_PHASES -c slb_msckf.cu && link as libslb_phases.so (see the `phases` target of csrc/Makefile)
+    make -C slam-localization_b200/csrc phases            (-> libslb_phases.so, an instrumented copy, not the product library)
     SLB_LIB=$PWD/slam-localization_b200/csrc/libslb_phases.so python profiles/msckf_phases.py"""
 import ctypes
 import os

@@ -72,3 +72,34 @@ def test_next_row_entry_points_validate_arguments_without_a_gpu():
         assert L.slb_datamodel_safe_fuse(1, p, p, p, p, p, p, None) == -2
         assert L.slb_deadreckon_update_pose(1, C.c_double(0.01), p, p, p, p, p, p, p, p, p, None) == -2
         assert b"no CPU fallback" in L.slb_last_error()
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu():
+    """The handle-taking entry points added in round 2 reject a null handle before touching the device, and the NCCL helpers
+    validate their arguments (NCCL itself is resolved with dlopen only when a communicator is actually requested)."""
+    import ctypes as C
+    L = engine.lib()
+    buf = (C.c_ubyte * 128)()
+    comm = C.c_void_p()
+    assert L.slb_wait(None, None) == -1
+    assert L.slb_set_output_slice(None, 0, 1) == -1
+    assert L.slb_check_sigma_points(None, None, None, None) == -1
+    assert L.slb_gather_stats(None, None, None, None) == -1
+    assert L.slb_nccl_unique_id(None) == -1
+    assert L.slb_nccl_comm_init(C.byref(comm), 0, buf, 0, 0) == -1          # nranks < 1
+    assert L.slb_nccl_comm_init(C.byref(comm), 2, buf, 2, 0) == -1          # rank out of range
+    assert L.slb_nccl_comm_destroy(None) == 0                                # nothing to destroy
+    assert L.slb_status_ex(None, None, 5, None) == -1
+    assert L.slb_usckf_step_host_async(None, 4, 102, None, C.c_double(0.01), None, None, None, 0, None, None) == -1
+
+
+def test_usckf_shapes_are_validated_at_create_without_a_gpu():
+    """slb_create checks the device first (no CPU fallback); on a GPU box the shape check is covered by the GPU tests."""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = engine.SlbConfig()
+    cfg.kind, cfg.batch, cfg.nk, cfg.nl = engine.KIND_USCKF, 8, 3, 12
+    h = C.c_void_p()
+    assert engine.lib().slb_create(C.byref(cfg), C.byref(h)) == -2
