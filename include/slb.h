@@ -44,7 +44,11 @@ typedef enum {
 
 /* Per-instance status bits (never abort the batch; reference behaviour in brackets). */
 enum {
-    SLB_ST_CHOL_FAIL = 1,   /* LLT pivot <= 0 [Eigen::LLT info() ignored, Usckf.hpp:537-538]  */
+    SLB_ST_CHOL_FAIL = 1,   /* LLT pivot <= 0 [Eigen::LLT info() ignored, Usckf.hpp:537-538].
+                               Usckf::update factors only the columns of Pk that can move h
+                               (j < 36 + nk, rounded up to 4): a non-positive pivot beyond them is
+                               neither computed nor flagged (the reference would write NaN into the
+                               featuresk_l rows there); slb_check_sigma_points tests all of Pk      */
     SLB_ST_MEAN_NOCONV = 2, /* manifold mean hit max_it [assert(false), Usckf.hpp:620-624]     */
     SLB_ST_GATE_REJECT = 4, /* significance test rejected the update [Usckf.hpp:294]           */
     SLB_ST_NONFINITE = 8,   /* NaN/Inf met in the state                                        */
