@@ -178,7 +178,7 @@ SLB_DEV void jacobi_pair(Mx<3, 3> &W, Mx<3, 3> &U, double &max_diag, bool &finis
         max_diag = fmax(max_diag, fmax(fabs(W(P, P)), fabs(W(Q, Q))));
     }
 }
-SLB_DEV void jacobi_svd3(const Mx<3, 3> &A, Mx<3, 3> &U, double *sv) {
+__device__ __noinline__ void jacobi_svd3(const Mx<3, 3> &A, Mx<3, 3> &U, double *sv) {
     double scale = 0.0;
 #pragma unroll
     for (int e = 0; e < 9; ++e) scale = fmax(scale, fabs(A.a[e]));
