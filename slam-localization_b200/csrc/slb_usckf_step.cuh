@@ -66,7 +66,7 @@ struct StepCfg {
     static constexpr int SCR0 = (LF + LRAW > KK ? LF + LRAW : KK);
     static constexpr int WGS = 16 * NK_;               // W' of the current group, [c][16]: column pairs are one double2
     static constexpr int UPD_SCR = SCR0 + WGS + NPAD;       // + d_k
-    static constexpr int PRED_SCR = PRED_LS + 28 * PRED_DS + 144 + 12 * PRED_DS + 16;
+    static constexpr int PRED_SCR = PRED_LS + 28 * PRED_DS + 144 + 12 * PRED_DS + 16 + 16;   // ... + rsd + reduction slots
     static constexpr int SCR = (UPD_SCR > PRED_SCR ? UPD_SCR : PRED_SCR);
     static constexpr int ZS = (NK_ + 1) / 2 * 2;
     static constexpr int SM = PSTR + QS + SCR + ZS + 2;    // doubles per warp (even); last slot = mbarrier
@@ -145,6 +145,48 @@ SLB_DEV void vo_model(const double *pk, const double *qk, const double *pi, cons
         z[c] = rz[0] + (pk[0] - pi[0]);
         z[c + 1] = rz[1] + (pk[1] - pi[1]);
         z[c + 2] = rz[2] + (pk[2] - pi[2]);
+    }
+}
+
+// Sums of 12 values over the 32 lanes, result on every lane.  A butterfly per value costs 5 shuffles each (120 SHFL.32 for
+// 12 doubles, and shuffles travel through the same data pipe as shared memory, the kernel's limiter); here the lanes halve
+// the VALUE set while they halve the lane set (8 + 4 + 2 + 1 + 1 exchanges), the 16 partial owners park their sums in
+// shared memory and everybody reads them back with broadcast loads: 32 SHFL.32 + 1 STS + 6 LDS.128.  Fixed order: bitwise
+// reproducible.
+SLB_DEV void warp_sum12(const double *v, double *out, double *slots, int lane) {
+    double a[8], b[4], c[2], d1;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {   // values 12..15 are zero padding
+        const double lo = v[i], hi = i < 4 ? v[8 + i] : 0.0;
+        const double r = __shfl_xor_sync(FULL, h16 ? lo : hi, 16);
+        a[i] = (h16 ? hi : lo) + r;                     // lanes < 16 own values 0..7, lanes >= 16 own 8..15
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double r = __shfl_xor_sync(FULL, h8 ? a[i] : a[4 + i], 8);
+        b[i] = (h8 ? a[4 + i] : a[i]) + r;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double r = __shfl_xor_sync(FULL, h4 ? b[i] : b[2 + i], 4);
+        c[i] = (h4 ? b[2 + i] : b[i]) + r;
+    }
+    {
+        const double r = __shfl_xor_sync(FULL, h2 ? c[0] : c[1], 2);
+        d1 = (h2 ? c[1] : c[0]) + r;
+    }
+    d1 += __shfl_xor_sync(FULL, d1, 1);
+    // value index owned by this lane: bit 3 = h16, bit 2 = h8, bit 1 = h4, bit 0 = h2
+    const int idx = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
+    __syncwarp();
+    if (!(lane & 1)) slots[idx] = d1;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double2 t = *reinterpret_cast<const double2 *>(slots + 2 * i);
+        out[2 * i] = t.x;
+        out[2 * i + 1] = t.y;
     }
 }
 
@@ -391,13 +433,30 @@ SLB_DEV int usckf_update_smem(double *Ps, double *mus, double *scr, const double
     // ---- mean / innovation covariance (:280-282) from the deviations e = Z - Z0 -----------------------------------
     constexpr double NS = (double)(2 * N + 1);
     double ebar[NK], S[NK * (NK + 1) / 2];
+    if (NK == 3) {   // 3 + 6 sums in one reduce-scatter pass (the d_k slots are dead: every sigma point has been drawn)
+        double v[12], o[12];
 #pragma unroll
-    for (int c = 0; c < NK; ++c) ebar[c] = warp_sum(s.esum[c]) * (1.0 / NS);
+        for (int c = 0; c < 3; ++c) v[c] = s.esum[c];
 #pragma unroll
-    for (int r = 0; r < NK; ++r)
+        for (int e = 0; e < 6; ++e) v[3 + e] = s.eep[e];
+        v[9] = v[10] = v[11] = 0.0;
+        warp_sum12(v, o, dv, lane);
 #pragma unroll
-        for (int c = 0; c <= r; ++c)
-            S[tri(r, c)] = 0.5 * fma(-NS * ebar[r], ebar[c], warp_sum(s.eep[tri(r, c)])) + __ldg(a.R + r * NK + c);
+        for (int c = 0; c < 3; ++c) ebar[c] = o[c] * (1.0 / NS);
+#pragma unroll
+        for (int r = 0; r < NK; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c)
+                S[tri(r, c)] = 0.5 * fma(-NS * ebar[r], ebar[c], o[3 + tri(r, c)]) + __ldg(a.R + r * NK + c);
+    } else {
+#pragma unroll
+        for (int c = 0; c < NK; ++c) ebar[c] = warp_sum(s.esum[c]) * (1.0 / NS);
+#pragma unroll
+        for (int r = 0; r < NK; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c)
+                S[tri(r, c)] = 0.5 * fma(-NS * ebar[r], ebar[c], warp_sum(s.eep[tri(r, c)])) + __ldg(a.R + r * NK + c);
+    }
     // ---- K = covXZ S^-1 (:286-288), innovation, Mahalanobis gate (:290-294) --------------------------------------
     double Si[NK * (NK + 1) / 2];
     const bool sok = sym_inverse<NK>(S, Si);
@@ -497,7 +556,7 @@ SLB_DEV int usckf_predict_smem(double *Ps, double *mus, double *scr, const doubl
     typedef LayState12 L;
     typedef CycCfg<12> C;
     constexpr int ROW0 = 24, MU0 = 26;
-    double *Ls = scr, *D = Ls + PRED_LS, *W = D + 28 * PRED_DS, *Fk = W + 144, *rsd = Fk + 12 * PRED_DS;
+    double *Ls = scr, *D = Ls + PRED_LS, *W = D + 28 * PRED_DS, *Fk = W + 144, *rsd = Fk + 12 * PRED_DS, *slots = rsd + 16;
     auto PR = [&](int r, int c) -> double & { return Ps[tri(ROW0 + r, c)]; };        // row 24 + r, col c
     auto PF = [&](int fr, int c) -> double & { return Ps[tri(36 + fr, 24 + c)]; };   // feature row fr, col 24 + c
     const int a_ = lane & 3, b_ = lane >> 2;
@@ -551,10 +610,13 @@ SLB_DEV int usckf_predict_smem(double *Ps, double *mus, double *scr, const doubl
     do {
         double dd[12], md[12], nr[13];
         boxminus<L>(Y, ref, dd);
+#pragma unroll
+        for (int r = 0; r < 12; ++r) dd[r] = act ? dd[r] : 0.0;
+        warp_sum12(dd, md, slots, lane);
         nrm2 = 0.0;
 #pragma unroll
         for (int r = 0; r < 12; ++r) {
-            md[r] = warp_sum(act ? dd[r] : 0.0) * (1.0 / 25.0);
+            md[r] *= (1.0 / 25.0);
             nrm2 += md[r] * md[r];
         }
         boxplus<L>(ref, md, 1.0, nr);
