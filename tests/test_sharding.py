@@ -33,10 +33,22 @@ def _free_port():
     return p
 
 
+class _FakeEngine:
+    """Stands in for slam_localization_b200.engine on CPU: records what fleet.make_nccl_comm hands to NcclComm."""
+
+    class NcclComm:
+        def __init__(self, rank, world, exchange, device=None):
+            ident = bytes(range(128)) if rank == 0 else None      # rank 0 "creates" the 128-byte unique id ...
+            self.ident = exchange(ident)                          # ... and every rank must end up holding it
+            self.rank, self.world = rank, world
+
+
 def _worker(rank, world, port, total, n, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = fleet.make_nccl_comm(_FakeEngine, rank, world)         # the id exchange of the C-level gather (slb_gather_stats)
+    assert comm.ident == bytes(range(128)) and (comm.rank, comm.world) == (rank, world)
     x = np.random.default_rng(7).normal(size=(total, n))          # every rank can build the whole fleet ...
     lo, hi = fleet.shard_range(total, rank, world)
     local = torch.from_numpy(fleet.stats_from_vectors(x[lo:hi]))  # ... but only reduces its own shard
