@@ -39,6 +39,23 @@ def usckf():
                         Q=sc["Q"], R=sc["R"], mu1=mu1, P1=P1, mu2=mu2, P2=P2)
 
 
+def usckf_shapes():
+    """One fused predict+update step for feature sizes other than the bench's (3, 9), and checkSigmaPoints of the result."""
+    out = {}
+    for nk, nl in ((6, 6), (9, 3), (3, 0)):
+        sc = synth.usckf_scenario(4, seed=106 + nk, nk=nk, nl=nl)
+        mu2, P2, st, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, nk, nl, sc["mu"], sc["P"], sc["u"], sc["dt"], sc["Q"],
+                                        sc["z"], sc["R"])
+        assert not st.any()
+        fl, diff = slo.check_sigma_points(2, mu2, P2, nk=nk, nl=nl)
+        assert not fl.any()
+        tag = "_%d_%d" % (nk, nl)
+        for k, v in dict(mu0=sc["mu"], P0=sc["P"], u=sc["u"], z=sc["z"], Q=sc["Q"], R=sc["R"], mu2=mu2, P2=P2, diff=diff).items():
+            out[k + tag] = v
+        out["dt"] = sc["dt"]
+    np.savez_compressed(os.path.join(OUT, "usckf_shapes.npz"), **out)
+
+
 def msckf():
     sc = synth.msckf_scenario(4, seed=103, k=10, nfeat=50)
     mu1, P1, st = slo.msckf_predict(slo.PM_MSCKF_DELTAPOSE, 10, sc["mu"], sc["P"], sc["u"], 0.0, sc["Q"])
@@ -74,7 +91,12 @@ def next_rows():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                      # e.g. `make_golden.py usckf_shapes`: (re)generate the named fixtures only
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     ukf()
+    usckf_shapes()
     usckf()
     msckf()
     fusion()

@@ -449,3 +449,16 @@ def test_usckf_step_host_output_slice_returns_statek_i():
     np.testing.assert_array_equal(out, want)
     with pytest.raises(engine.SlbError):
         c.set_output_slice(40, 13)
+
+
+@pytest.mark.parametrize("nk,nl", [(6, 6), (9, 3), (3, 0)])
+def test_usckf_other_shapes_against_the_committed_golden_vectors(slo, nk, nl):
+    g = np.load(os.path.join(G, "usckf_shapes.npz"))
+    t = "_%d_%d" % (nk, nl)
+    f = engine.Usckf(g["mu0" + t].shape[0], nk=nk, nl=nl)
+    f.set_state(g["mu0" + t], g["P0" + t])
+    f.step(engine.PM_USCKF_TEST, engine.MM_USCKF_VO, g["u" + t], float(g["dt"]), g["Q" + t], g["z" + t], g["R" + t])
+    assert not f.status().any()
+    parity.assert_parity(slo, AUG, f.mu(), f.P(), g["mu2" + t], parity.symmetrize_lower(g["P2" + t]), nfeat=nk + nl)
+    fl, diff = f.check_sigma_points()
+    assert not fl.any() and diff.max() < 1e-12

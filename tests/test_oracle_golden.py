@@ -27,6 +27,19 @@ def test_usckf_golden(slo):
     np.testing.assert_allclose(P2, g["P2"], **TOL)
 
 
+def test_usckf_other_shapes_golden(slo):
+    g = np.load(os.path.join(G, "usckf_shapes.npz"))
+    for nk, nl in ((6, 6), (9, 3), (3, 0)):
+        t = "_%d_%d" % (nk, nl)
+        mu2, P2, st, _ = slo.usckf_step(slo.PM_USCKF_TEST, slo.MM_USCKF_VO, nk, nl, g["mu0" + t], g["P0" + t], g["u" + t],
+                                        float(g["dt"]), g["Q" + t], g["z" + t], g["R" + t])
+        assert not st.any()
+        np.testing.assert_allclose(mu2, g["mu2" + t], **TOL)
+        np.testing.assert_allclose(P2, g["P2" + t], **TOL)
+        fl, diff = slo.check_sigma_points(2, mu2, P2, nk=nk, nl=nl)
+        assert not fl.any() and diff.max() < 1e-12
+
+
 def test_msckf_golden(slo):
     g = np.load(os.path.join(G, "msckf_k10_f50.npz"))
     mu1, P1, _ = slo.msckf_predict(slo.PM_MSCKF_DELTAPOSE, 10, g["mu0"], g["P0"], g["u"], 0.0, g["Q"])
